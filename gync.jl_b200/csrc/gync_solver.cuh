@@ -1,0 +1,235 @@
+// GynCycle stiff forward solve: one RODAS4 (Hairer & Wanner, order 4(3), L-stable, stiffly
+// accurate, 6 stages) step on the generated straight-line RHS / Jacobian / sparse LU, plus the
+// step-size controller.  One parameter vector per thread; everything here is per-thread state.
+//
+// Replaces the per-sample CVODE forward solve behind gync()/forwardsol()
+// (reference src/gync/gyncycle.jl:8-26, src/gync/model.jl:90).  The reference's BDF/Newton at
+// reltol=abstol=1e-4 is NOT reproduced step for step (CVODE is not vendored); this solver
+// integrates the same ODE to a tolerance the caller sets, and parity is stated against the
+// converged solution.
+//
+// Compiles as CUDA device code and, for the CPU-side unit tests only, as host C++.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include "gen/gync_model_gen.h"
+
+#define GYNC_NX 116        /* sample width: 82 parameters | 33 initial values | period (model.jl:82-84) */
+#define GYNC_NS 82
+#define GYNC_NP 114
+#define GYNC_NMEAS 4       /* measuredinds = [2,7,24,25] (model.jl:1) */
+#define GYNC_NDAYS 31
+
+// status bits (0 = ok)
+#define GYNC_ST_OK          0
+#define GYNC_ST_MAXSTEPS    1   /* step budget exhausted */
+#define GYNC_ST_HMIN        2   /* step size underflow */
+#define GYNC_ST_NONFINITE   4   /* non-finite input or state (e.g. negative base of the real power) */
+
+#ifndef GYNC_CONSTANT
+#  ifdef __CUDA_ARCH__
+#    define GYNC_CONSTANT __constant__
+#  else
+#    define GYNC_CONSTANT static const
+#  endif
+#endif
+
+struct GyncSolverOpts {
+  double rtol, atol;
+  double h0;          // initial step; <=0: automatic
+  double hmax;        // <=0: none
+  int    max_steps;   // accepted+rejected, per solve
+};
+
+struct GyncStepStats {   // per-sample work counters (roofline bookkeeping)
+  int nacc, nrej;
+};
+
+// ---- RODAS4 coefficients (Hairer & Wanner, Solving ODEs II, RODAS code; gamma = 1/4)
+#define RD_G   0.25
+#define RD_A21 0.1544e1
+#define RD_A31 0.9466785280815826
+#define RD_A32 0.2557011698983284
+#define RD_A41 0.3314825187068521e1
+#define RD_A42 0.2896124015972201e1
+#define RD_A43 0.9986419139977817
+#define RD_A51 0.1221224509226641e1
+#define RD_A52 0.6019134481288629e1
+#define RD_A53 0.1253708332932087e2
+#define RD_A54 (-0.6878860361058950)
+#define RD_C21 (-0.56688e1)
+#define RD_C31 (-0.2430093356833875e1)
+#define RD_C32 (-0.2063599157091915)
+#define RD_C41 (-0.1073529058151375)
+#define RD_C42 (-0.9594562251023355e1)
+#define RD_C43 (-0.2047028614809616e2)
+#define RD_C51 0.7496443313967647e1
+#define RD_C52 (-0.1024680431464352e2)
+#define RD_C53 (-0.3399990352819905e2)
+#define RD_C54 0.1170890893206160e2
+#define RD_C61 0.8083246795921522e1
+#define RD_C62 (-0.7981132988064893e1)
+#define RD_C63 (-0.3152159432874371e2)
+#define RD_C64 0.1631930543123136e2
+#define RD_C65 (-0.6058818238834054e1)
+
+struct GyncWork {
+  double q[GYNC_NQ];
+  double y[GYNC_NY];
+  double yn[GYNC_NY];
+  double k1[GYNC_NY], k2[GYNC_NY], k3[GYNC_NY], k4[GYNC_NY], k5[GYNC_NY], e[GYNC_NY];
+  double A[GYNC_NLU];
+};
+
+// One step attempt of size h from W.y; on return W.yn = y(t+h) candidate, returns the scaled
+// error norm (RMS over the 33 species of e_i / (atol + rtol*max(|y_i|,|yn_i|))).
+GYNC_HD static inline double gync_rodas4_step(GyncWork& W, const double h, const double rtol, const double atol) {
+  const double ih = 1.0 / h;
+  gync_rhs_w(W.y, W.q, ih * (1.0 / RD_G), W.k1, W.A);
+  gync_lu(W.A);
+  gync_lusolve(W.A, W.k1);
+#pragma unroll
+  for (int i = 0; i < GYNC_NY; ++i) W.yn[i] = W.y[i] + RD_A21 * W.k1[i];
+  gync_rhs(W.yn, W.q, W.k2);
+#pragma unroll
+  for (int i = 0; i < GYNC_NY; ++i) W.k2[i] += (RD_C21 * ih) * W.k1[i];
+  gync_lusolve(W.A, W.k2);
+#pragma unroll
+  for (int i = 0; i < GYNC_NY; ++i) W.yn[i] = W.y[i] + RD_A31 * W.k1[i] + RD_A32 * W.k2[i];
+  gync_rhs(W.yn, W.q, W.k3);
+#pragma unroll
+  for (int i = 0; i < GYNC_NY; ++i) W.k3[i] += ih * (RD_C31 * W.k1[i] + RD_C32 * W.k2[i]);
+  gync_lusolve(W.A, W.k3);
+#pragma unroll
+  for (int i = 0; i < GYNC_NY; ++i) W.yn[i] = W.y[i] + RD_A41 * W.k1[i] + RD_A42 * W.k2[i] + RD_A43 * W.k3[i];
+  gync_rhs(W.yn, W.q, W.k4);
+#pragma unroll
+  for (int i = 0; i < GYNC_NY; ++i) W.k4[i] += ih * (RD_C41 * W.k1[i] + RD_C42 * W.k2[i] + RD_C43 * W.k3[i]);
+  gync_lusolve(W.A, W.k4);
+#pragma unroll
+  for (int i = 0; i < GYNC_NY; ++i)
+    W.yn[i] = W.y[i] + RD_A51 * W.k1[i] + RD_A52 * W.k2[i] + RD_A53 * W.k3[i] + RD_A54 * W.k4[i];
+  gync_rhs(W.yn, W.q, W.k5);
+#pragma unroll
+  for (int i = 0; i < GYNC_NY; ++i)
+    W.k5[i] += ih * (RD_C51 * W.k1[i] + RD_C52 * W.k2[i] + RD_C53 * W.k3[i] + RD_C54 * W.k4[i]);
+  gync_lusolve(W.A, W.k5);
+#pragma unroll
+  for (int i = 0; i < GYNC_NY; ++i) W.yn[i] += W.k5[i];
+  gync_rhs(W.yn, W.q, W.e);
+#pragma unroll
+  for (int i = 0; i < GYNC_NY; ++i)
+    W.e[i] += ih * (RD_C61 * W.k1[i] + RD_C62 * W.k2[i] + RD_C63 * W.k3[i] + RD_C64 * W.k4[i] + RD_C65 * W.k5[i]);
+  gync_lusolve(W.A, W.e);
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < GYNC_NY; ++i) {
+    W.yn[i] += W.e[i];
+    const double sc = atol + rtol * fmax(fabs(W.y[i]), fabs(W.yn[i]));
+    const double r = W.e[i] / sc;
+    s += r * r;
+  }
+  return sqrt(s * (1.0 / GYNC_NY));
+}
+
+// Step-size controller state (Hairer's RODAS controller with Gustafsson's predictive term).
+struct GyncCtrl {
+  double h;        // next step to try
+  double hacc, erracc;
+  int    nacc, nrej, rej_last;
+};
+
+// Decide on a step attempt of size h with scaled error err.  Returns true if accepted.
+// Updates c.h with the proposal for the next attempt.
+GYNC_HD static inline bool gync_ctrl_update(GyncCtrl& c, const double h, double err, const bool finite) {
+  const double SAFE = 0.9, FAC1 = 5.0, FAC2 = 1.0 / 6.0;
+  if (!finite || !(err == err)) {          // NaN/Inf in the stage values: shrink hard
+    c.h = 0.2 * h;
+    c.nrej++;
+    c.rej_last = 1;
+    return false;
+  }
+  double fac = fmax(FAC2, fmin(FAC1, sqrt(sqrt(err)) * (1.0 / SAFE)));
+  double hnew = h / fac;
+  if (err <= 1.0) {
+    if (c.nacc > 0) {
+      double facgus = (c.hacc / h) * sqrt(sqrt(err * err / c.erracc)) * (1.0 / SAFE);
+      facgus = fmax(FAC2, fmin(FAC1, facgus));
+      fac = fmax(fac, facgus);
+      hnew = h / fac;
+    }
+    c.hacc = h;
+    c.erracc = fmax(1.0e-2, err);
+    if (c.rej_last) hnew = fmin(hnew, h);
+    c.rej_last = 0;
+    c.nacc++;
+    c.h = hnew;
+    return true;
+  }
+  c.nrej++;
+  c.rej_last = 1;
+  c.h = hnew;
+  return false;
+}
+
+// Build the per-thread parameter state from one sample x (strided access: x[k*stride]).
+// allparms (model.jl:20-24): the 82 sampled values are scattered into a copy of refallparms.
+// `refallparms` and `sampledinds` come from the caller (constant memory on the device).
+template <class LoadX>
+GYNC_HD static inline void gync_load_sample(GyncWork& W, LoadX ldx, const double* refallparms,
+                                            const unsigned char* sampledinds, double* period) {
+  double p[GYNC_NP];
+#pragma unroll
+  for (int k = 0; k < GYNC_NP; ++k) p[k] = refallparms[k];
+#pragma unroll
+  for (int k = 0; k < GYNC_NS; ++k) p[sampledinds[k]] = ldx(k);
+  gync_pack_params(p, W.q);
+#pragma unroll
+  for (int i = 0; i < GYNC_NY; ++i) W.y[i] = ldx(GYNC_NS + i);
+  *period = ldx(GYNC_NX - 1);
+}
+
+GYNC_HD static inline bool gync_all_finite(const double* v, int n) {
+  double s = 0.0;
+  for (int i = 0; i < n; ++i) s += v[i] * 0.0;   // NaN/Inf -> NaN
+  return s == 0.0;
+}
+
+// Automatic initial step: h0 = 0.01 * ||y||/||f|| in the scaled RMS norm, clamped.
+GYNC_HD static inline double gync_initial_step(GyncWork& W, const double rtol, const double atol) {
+  gync_rhs(W.y, W.q, W.k1);
+  double d0 = 0.0, d1 = 0.0;
+  for (int i = 0; i < GYNC_NY; ++i) {
+    const double sc = atol + rtol * fabs(W.y[i]);
+    d0 += (W.y[i] / sc) * (W.y[i] / sc);
+    d1 += (W.k1[i] / sc) * (W.k1[i] / sc);
+  }
+  double h = (d0 > 1e-10 && d1 > 1e-10) ? 0.01 * sqrt(d0 / d1) : 1e-6;
+  if (!(h == h)) h = 1e-6;
+  return fmin(fmax(h, 1e-8), 1e-2);
+}
+
+// Integrate from t to tend (tend > t), landing exactly on tend.  Returns status bits.
+GYNC_HD static inline int gync_advance(GyncWork& W, GyncCtrl& c, double& t, const double tend,
+                                       const GyncSolverOpts& o, int& budget) {
+  while (t < tend) {
+    if (budget <= 0) return GYNC_ST_MAXSTEPS;
+    --budget;
+    double h = c.h;
+    if (o.hmax > 0.0) h = fmin(h, o.hmax);
+    const double rem = tend - t;
+    const bool last = (h * 1.0001 >= rem);
+    if (last) h = rem;
+    if (!(h > 1e-14 * fmax(1.0, fabs(t)))) return GYNC_ST_HMIN;
+    const double hprop = c.h;
+    const double err = gync_rodas4_step(W, h, o.rtol, o.atol);
+    const bool fin = gync_all_finite(W.yn, GYNC_NY);
+    if (gync_ctrl_update(c, h, err, fin)) {
+      t = last ? tend : t + h;
+#pragma unroll
+      for (int i = 0; i < GYNC_NY; ++i) W.y[i] = W.yn[i];
+      if (last && h < hprop) c.h = fmax(c.h, hprop);   // output truncation must not shrink the step
+    }
+  }
+  return GYNC_ST_OK;
+}
