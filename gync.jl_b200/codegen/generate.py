@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Code generator: symbolic GynCycle model -> straight-line FP64 code for sm_100a.
 
-Emits gync.jl_b200/csrc/gen/gync_model_gen.h containing (all `GYNC_HD static inline`,
+Emits gync.jl_b200/csrc/gen/gync_model_gen.h containing (all `GYNC_HD static`,
 usable from CUDA device code and, for the CPU-side unit tests, from plain C++):
 
   gync_pack_params(p114, q)        derived per-sample parameter vector q[GYNC_NQ]
@@ -101,14 +101,14 @@ def _wrap(a, cnt):
 
 _POWMULS = {2: 1, 3: 2, 4: 2, 5: 3, 6: 3, 8: 3, 9: 4, 10: 4}
 _IPOW_SRC = """
-GYNC_HD static inline double gync_ipow2(double x){return x*x;}
-GYNC_HD static inline double gync_ipow3(double x){return x*x*x;}
-GYNC_HD static inline double gync_ipow4(double x){double a=x*x;return a*a;}
-GYNC_HD static inline double gync_ipow5(double x){double a=x*x;return a*a*x;}
-GYNC_HD static inline double gync_ipow6(double x){double a=x*x;return a*a*a;}
-GYNC_HD static inline double gync_ipow8(double x){double a=x*x;a=a*a;return a*a;}
-GYNC_HD static inline double gync_ipow9(double x){double a=x*x;a=a*a;return a*a*x;}
-GYNC_HD static inline double gync_ipow10(double x){double a=x*x;double b=a*a;return b*b*a;}
+GYNC_HD static double gync_ipow2(double x){return x*x;}
+GYNC_HD static double gync_ipow3(double x){return x*x*x;}
+GYNC_HD static double gync_ipow4(double x){double a=x*x;return a*a;}
+GYNC_HD static double gync_ipow5(double x){double a=x*x;return a*a*x;}
+GYNC_HD static double gync_ipow6(double x){double a=x*x;return a*a*a;}
+GYNC_HD static double gync_ipow8(double x){double a=x*x;a=a*a;return a*a;}
+GYNC_HD static double gync_ipow9(double x){double a=x*x;a=a*a;return a*a*x;}
+GYNC_HD static double gync_ipow10(double x){double a=x*x;double b=a*a;return b*b*a;}
 """
 
 NAMES: dict = {}
@@ -243,14 +243,18 @@ def main():
     rows = {i: sorted([j for (a, j) in full if a == i], key=lambda j: rank[j]) for i in range(NY)}
     cols = {j: sorted([i for (i, b) in full if b == j], key=lambda i: rank[i]) for j in range(NY)}
     for k in order:
+        right = [j for j in rows[k] if rank[j] > rank[k]]
+        below = [i for i in cols[k] if rank[i] > rank[k]]
         lu_lines.append(f"  {{ const double piv = GYNC_RCP(A[{pos[(k, k)]}]); A[{pos[(k, k)]}] = piv;")
         c_lu.rcp += 1
-        right = [j for j in rows[k] if rank[j] > rank[k]]
-        for i in [i for i in cols[k] if rank[i] > rank[k]]:
+        if below:   # read the pivot row once (the storage may be shared memory: every read is a real load)
+            for j in right:
+                lu_lines.append(f"    const double u{j} = A[{pos[(k, j)]}];")
+        for i in below:
             lu_lines.append(f"    {{ const double l = A[{pos[(i, k)]}] * piv; A[{pos[(i, k)]}] = l;")
             c_lu.mul += 1
             for j in right:
-                lu_lines.append(f"      A[{pos[(i, j)]}] -= l * A[{pos[(k, j)]}];")
+                lu_lines.append(f"      A[{pos[(i, j)]}] -= l * u{j};")
                 c_lu.mul += 1
                 c_lu.add += 1
             lu_lines.append("    }")
@@ -293,7 +297,7 @@ def main():
 #  ifdef __CUDACC__
 #    define GYNC_HD __host__ __device__ __forceinline__
 #  else
-#    define GYNC_HD
+#    define GYNC_HD inline
 #  endif
 #endif
 #ifndef GYNC_RCP
@@ -335,32 +339,32 @@ static const unsigned char GYNC_USED_P[{len(used_p)}] = {{{", ".join(map(str, us
 
 /* q <- derived parameters from the 114 reference-ordered parameters */
 template <class PT, class QT>
-GYNC_HD static inline void gync_pack_params(const PT& p, QT& q) {{
+GYNC_HD static void gync_pack_params(const PT& p, QT& q) {{
 {chr(10).join(pack)}
 }}
 
 /* f = dy/dt */
 template <class YT, class QT, class FT>
-GYNC_HD static inline void gync_rhs(const YT& y, const QT& q, FT& f) {{
+GYNC_HD static void gync_rhs(const YT& y, const QT& q, FT& f) {{
 {src_rhs}
 }}
 
 /* f = dy/dt and A = fac*I - df/dy in LU storage */
 template <class YT, class QT, class FT, class AT>
-GYNC_HD static inline void gync_rhs_w(const YT& y, const QT& q, const double fac, FT& f, AT& A) {{
+GYNC_HD static void gync_rhs_w(const YT& y, const QT& q, const double fac, FT& f, AT& A) {{
 {src_w}
 {zero_fill}
 }}
 
 /* in-place LU, inverse pivots on the diagonal */
 template <class AT>
-GYNC_HD static inline void gync_lu(AT& A) {{
+GYNC_HD static void gync_lu(AT& A) {{
 {src_lu}
 }}
 
 /* b <- (LU)^-1 b */
 template <class AT, class BT>
-GYNC_HD static inline void gync_lusolve(const AT& A, BT& b) {{
+GYNC_HD static void gync_lusolve(const AT& A, BT& b) {{
 {src_sol}
 }}
 """

@@ -1,0 +1,120 @@
+// C ABI, part 2: log-prior, many-chain Metropolis, WeightedChain normalisation.
+// (included at the end of gync_b200.cu)
+extern "C" {
+
+static_assert(sizeof(gync_prior) == sizeof(GyncPriorDev), "gync_prior layout");
+
+int gync_logprior_batch(const double* X, int64_t N, const gync_prior* prior, double* LP) {
+  if (N < 0 || !prior || (N > 0 && (!X || !LP))) return fail(GYNC_ERR_ARG, "gync_logprior_batch: bad arguments");
+  if (int rc = ensure_init()) return rc;
+  if (N == 0) return GYNC_OK;
+  DBuf dX, dP, dL;
+  CK(dX.alloc(sizeof(double) * N * GYNC_NX));
+  CK(dP.alloc(sizeof(gync_prior)));
+  CK(dL.alloc(sizeof(double) * N));
+  CK(cudaMemcpyAsync(dX.p, X, sizeof(double) * N * GYNC_NX, cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemcpyAsync(dP.p, prior, sizeof(gync_prior), cudaMemcpyHostToDevice, g_stream));
+  gync_logprior_kernel<<<blocks_for(N, 128), 128, 0, g_stream>>>(dX.as<double>(), N, dP.as<GyncPriorDev>(), dL.as<double>());
+  g_launches += 1;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(LP, dL.p, sizeof(double) * N, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
+  return GYNC_OK;
+}
+
+int gync_mcmc_run(double* state, double* logf, int64_t C, const double* chol, double prop_sd, const double* data,
+                  int32_t M, const double* sigma_rho, const int32_t* patient_of_chain, const gync_prior* prior,
+                  const gync_solver_opts* opts, int64_t iters, int32_t thin, uint64_t seed, uint64_t iter_offset,
+                  const double* inj_z, const double* inj_u, double* samples_out, int64_t* naccept) {
+  if (C < 0 || M < 1 || iters < 0 || thin < 1 || !prior || (C > 0 && (!state || !logf || !data || !sigma_rho)))
+    return fail(GYNC_ERR_ARG, "gync_mcmc_run: bad arguments");
+  if (!chol && !(prop_sd > 0.0)) return fail(GYNC_ERR_ARG, "gync_mcmc_run: need chol or prop_sd > 0");
+  if ((inj_z == nullptr) != (inj_u == nullptr)) return fail(GYNC_ERR_ARG, "gync_mcmc_run: inj_z and inj_u go together");
+  if (patient_of_chain)
+    for (int64_t c = 0; c < C; ++c)
+      if (patient_of_chain[c] < 0 || patient_of_chain[c] >= M) return fail(GYNC_ERR_ARG, "gync_mcmc_run: patient index out of range");
+  if (int rc = ensure_init()) return rc;
+  if (C == 0) return GYNC_OK;
+  const int64_t n_out = iters / thin;
+  DBuf dS, dLf, dCh, dD, dSig, dPat, dPr, dZ, dU, dOut, dAcc, dIsc, dNan;
+  CK(dS.alloc(sizeof(double) * C * GYNC_NX));
+  CK(dLf.alloc(sizeof(double) * C));
+  CK(dD.alloc(sizeof(double) * 124 * M));
+  CK(dSig.alloc(sizeof(double) * M));
+  CK(dPr.alloc(sizeof(gync_prior)));
+  CK(dIsc.alloc(sizeof(double) * 4 * M));
+  CK(dNan.alloc(sizeof(int) * M));
+  CK(dAcc.alloc(sizeof(long long) * C));
+  CK(cudaMemcpyAsync(dS.p, state, sizeof(double) * C * GYNC_NX, cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemcpyAsync(dLf.p, logf, sizeof(double) * C, cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemcpyAsync(dD.p, data, sizeof(double) * 124 * M, cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemcpyAsync(dSig.p, sigma_rho, sizeof(double) * M, cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemcpyAsync(dPr.p, prior, sizeof(gync_prior), cudaMemcpyHostToDevice, g_stream));
+  if (chol) {
+    CK(dCh.alloc(sizeof(double) * GYNC_NX * GYNC_NX));
+    CK(cudaMemcpyAsync(dCh.p, chol, sizeof(double) * GYNC_NX * GYNC_NX, cudaMemcpyHostToDevice, g_stream));
+  }
+  if (patient_of_chain) {
+    CK(dPat.alloc(sizeof(int32_t) * C));
+    CK(cudaMemcpyAsync(dPat.p, patient_of_chain, sizeof(int32_t) * C, cudaMemcpyHostToDevice, g_stream));
+  }
+  if (inj_z) {
+    CK(dZ.alloc(sizeof(double) * iters * GYNC_NX * C));
+    CK(dU.alloc(sizeof(double) * iters * C));
+    CK(cudaMemcpyAsync(dZ.p, inj_z, sizeof(double) * iters * GYNC_NX * C, cudaMemcpyHostToDevice, g_stream));
+    CK(cudaMemcpyAsync(dU.p, inj_u, sizeof(double) * iters * C, cudaMemcpyHostToDevice, g_stream));
+  }
+  if (samples_out && n_out > 0) CK(dOut.alloc(sizeof(double) * n_out * GYNC_NX * C));
+  gync_prep_patients_kernel<<<blocks_for(M, 64), 64, 0, g_stream>>>(dD.as<double>(), dSig.as<double>(), M, dIsc.as<double>(), dNan.as<int>());
+  // chains are latency-bound (one solve per iteration): spread them over the SMs, 32 per CTA
+  if (int rc = prep_solver_kernel(gync_mcmc_kernel<32>, GyncWorkSm<32>::kSmemBytes, 32)) return rc;
+  gync_mcmc_kernel<32><<<std::min<unsigned>(blocks_for(C, 32), 2 * g_num_sms), 32, GyncWorkSm<32>::kSmemBytes, g_stream>>>(
+      dS.as<double>(), dLf.as<double>(), C, chol ? dCh.as<double>() : nullptr, prop_sd, dD.as<double>(),
+      dIsc.as<double>(), dNan.as<int>(), patient_of_chain ? dPat.as<int>() : nullptr, dPr.as<GyncPriorDev>(),
+      to_opts(opts), iters, thin, seed, iter_offset, inj_z ? dZ.as<double>() : nullptr,
+      inj_u ? dU.as<double>() : nullptr, (samples_out && n_out > 0) ? dOut.as<double>() : nullptr,
+      dAcc.as<long long>());
+  g_launches += 2;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(state, dS.p, sizeof(double) * C * GYNC_NX, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaMemcpyAsync(logf, dLf.p, sizeof(double) * C, cudaMemcpyDeviceToHost, g_stream));
+  if (samples_out && n_out > 0)
+    CK(cudaMemcpyAsync(samples_out, dOut.p, sizeof(double) * n_out * GYNC_NX * C, cudaMemcpyDeviceToHost, g_stream));
+  if (naccept) CK(cudaMemcpyAsync(naccept, dAcc.p, sizeof(long long) * C, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
+  return GYNC_OK;
+}
+
+int gync_wc_normalize(const double* LL, const double* logprior, const int64_t* counts, int64_t K, int32_t M,
+                      double* L, double* weights, double* density) {
+  if (K < 1 || M < 1 || !LL || !logprior || !counts || !L || !weights || !density)
+    return fail(GYNC_ERR_ARG, "gync_wc_normalize: bad arguments");
+  if (int rc = ensure_init()) return rc;
+  DBuf dLL, dLp, dCn, dW, dDn, dCs, dSc, dPart;
+  const int nb = g_num_sms * 4;
+  CK(dLL.alloc(sizeof(double) * K * M));
+  CK(dLp.alloc(sizeof(double) * K));
+  CK(dCn.alloc(sizeof(long long) * K));
+  CK(dW.alloc(sizeof(double) * K));
+  CK(dDn.alloc(sizeof(double) * K));
+  CK(dCs.alloc(sizeof(double) * M));
+  CK(dSc.alloc(sizeof(double) * 2));
+  CK(dPart.alloc(sizeof(double) * nb));
+  CK(cudaMemcpyAsync(dLL.p, LL, sizeof(double) * K * M, cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemcpyAsync(dLp.p, logprior, sizeof(double) * K, cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemcpyAsync(dCn.p, counts, sizeof(long long) * K, cudaMemcpyHostToDevice, g_stream));
+  gync_wc_colpass_kernel<<<M + 2, GYNC_WC_THREADS, 0, g_stream>>>(dLL.as<double>(), dLp.as<double>(), dCn.as<long long>(), K, M,
+                                                                  dLL.as<double>(), dCs.as<double>(), dSc.as<double>());
+  gync_wc_rowpass_kernel<<<nb, 256, 0, g_stream>>>(dLL.as<double>(), dLp.as<double>(), dCn.as<long long>(), K, M, dCs.as<double>(),
+                                                   dSc.as<double>(), dW.as<double>(), dDn.as<double>(), dPart.as<double>());
+  gync_wc_scale_kernel<<<nb, 256, 0, g_stream>>>(dDn.as<double>(), K, dPart.as<double>(), nb);
+  g_launches += 3;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(L, dLL.p, sizeof(double) * K * M, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaMemcpyAsync(weights, dW.p, sizeof(double) * K, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaMemcpyAsync(density, dDn.p, sizeof(double) * K, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
+  return GYNC_OK;
+}
+
+}  // extern "C"

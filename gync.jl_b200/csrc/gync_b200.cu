@@ -1,0 +1,384 @@
+// C ABI of the B200-native GynC.jl hot path (declared in include/gync_b200.h).
+// Host wrappers: argument checks, H2D/D2H staging, kernel launches.  No CPU fallback.
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "gync_kernels.cuh"
+#include "gync_mcmc.cuh"
+#include "../../include/gync_b200.h"
+
+namespace {
+
+thread_local std::string g_err;
+cudaStream_t g_stream = nullptr;
+int g_device = -1;
+int g_num_sms = 0;
+std::atomic<int64_t> g_launches{0};
+int g_llk_variant = 0;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CK(expr)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      return fail(GYNC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));              \
+    }                                                                                              \
+  } while (0)
+
+int ensure_init() {
+  if (g_device >= 0) return GYNC_OK;
+  return gync_init(0);
+}
+
+// RAII device buffer
+struct DBuf {
+  void* p = nullptr;
+  ~DBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 8); }
+  template <class T> T* as() { return static_cast<T*>(p); }
+};
+
+GyncSolverOpts to_opts(const gync_solver_opts* o) {
+  GyncSolverOpts r;
+  r.rtol = (o && o->rtol > 0) ? o->rtol : 1e-8;
+  r.atol = (o && o->atol > 0) ? o->atol : 1e-8;
+  r.h0 = o ? o->h0 : 0.0;
+  r.hmax = o ? o->hmax : 0.0;
+  r.max_steps = (o && o->max_steps > 0) ? o->max_steps : 200000;
+  return r;
+}
+
+inline unsigned blocks_for(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+// opt in to the large dynamic shared-memory carve-out the solver kernels need
+template <class K>
+int prep_solver_kernel(K kern, size_t smem, int block) {
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  (void)block;
+  return GYNC_OK;
+}
+
+}  // namespace
+
+extern "C" int gync_init(int device);
+
+// EM launch helpers (templates: outside extern "C")
+namespace {
+
+template <int MT>
+int em_persistent_launch(double* dw, const double* dL, int64_t K, int M, int niter, double* d_hist, cudaStream_t s) {
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gync_em_persistent_kernel<MT>, GYNC_EM_THREADS, 0));
+  if (per_sm < 1) return fail(GYNC_ERR_CUDA, "EM kernel does not fit on an SM");
+  int64_t want = (K + GYNC_EM_THREADS - 1) / GYNC_EM_THREADS;
+  int nb = (int)std::min<int64_t>((int64_t)g_num_sms * per_sm, std::max<int64_t>(want, 1));
+  double* partials = nullptr;
+  CK(cudaMallocAsync((void**)&partials, sizeof(double) * 2 * nb * MT, s));
+  void* args[] = {&dw, &dL, &K, &M, &niter, &partials, &d_hist};
+  CK(cudaLaunchCooperativeKernel((void*)gync_em_persistent_kernel<MT>, dim3(nb), dim3(GYNC_EM_THREADS), args, 0, s));
+  g_launches += 1;
+  CK(cudaFreeAsync(partials, s));
+  return GYNC_OK;
+}
+
+struct EmScratch {   // per-stream scratch for the sharded step kernels
+  double* partials = nullptr;
+  int nb = 0, MT = 0;
+} g_em_scratch;
+
+template <int MT>
+int em_grid(int64_t K) {
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gync_em_step_kernel<MT>, GYNC_EM_THREADS, 0);
+  if (per_sm < 1) per_sm = 1;
+  int64_t want = (K + GYNC_EM_THREADS - 1) / GYNC_EM_THREADS;
+  return (int)std::min<int64_t>((int64_t)g_num_sms * per_sm, std::max<int64_t>(want, 1));
+}
+
+int em_scratch(int nb, int MT) {
+  if (g_em_scratch.partials && g_em_scratch.nb >= nb && g_em_scratch.MT == MT) return GYNC_OK;
+  if (g_em_scratch.partials) cudaFree(g_em_scratch.partials);
+  g_em_scratch.partials = nullptr;
+  CK(cudaMalloc((void**)&g_em_scratch.partials, sizeof(double) * nb * MT));
+  g_em_scratch.nb = nb;
+  g_em_scratch.MT = MT;
+  return GYNC_OK;
+}
+
+template <int MT>
+int em_norms_launch(const double* dw, const double* dL, int64_t K, int M, double* d_out, cudaStream_t s) {
+  const int nb = em_grid<MT>(K);
+  if (int rc = em_scratch(nb, MT)) return rc;
+  gync_em_norms_kernel<MT><<<nb, GYNC_EM_THREADS, 0, s>>>(dw, dL, K, M, g_em_scratch.partials);
+  gync_em_finish_kernel<<<1, 64, 0, s>>>(g_em_scratch.partials, nb, MT, M, d_out);
+  g_launches += 2;
+  CK(cudaGetLastError());
+  return GYNC_OK;
+}
+
+template <int MT>
+int em_step_launch(double* dw, const double* dL, int64_t K, int M, const double* d_in, double* d_out, cudaStream_t s) {
+  const int nb = em_grid<MT>(K);
+  if (int rc = em_scratch(nb, MT)) return rc;
+  gync_em_step_kernel<MT><<<nb, GYNC_EM_THREADS, 0, s>>>(dw, dL, K, M, d_in, g_em_scratch.partials);
+  gync_em_finish_kernel<<<1, 64, 0, s>>>(g_em_scratch.partials, nb, MT, M, d_out);
+  g_launches += 2;
+  CK(cudaGetLastError());
+  return GYNC_OK;
+}
+
+#define EM_DISPATCH(M, CALL)                                        \
+  do {                                                              \
+    if ((M) <= 8) return CALL(8);                                   \
+    if ((M) <= 16) return CALL(16);                                 \
+    if ((M) <= 24) return CALL(24);                                 \
+    if ((M) <= 32) return CALL(32);                                 \
+    if ((M) <= 40) return CALL(40);                                 \
+    if ((M) <= 64) return CALL(64);                                 \
+    return fail(GYNC_ERR_ARG, "EM: M > 64 patients not supported"); \
+  } while (0)
+
+}  // namespace
+
+extern "C" {
+
+int gync_abi_version(void) { return 1; }
+
+const char* gync_last_error(void) { return g_err.c_str(); }
+
+int64_t gync_launch_count(void) { return g_launches.load(); }
+
+void gync_dims(int32_t* ny, int32_t* np, int32_t* nx, int32_t* nq, int32_t* nlu) {
+  if (ny) *ny = GYNC_NY;
+  if (np) *np = GYNC_NP;
+  if (nx) *nx = GYNC_NX;
+  if (nq) *nq = GYNC_NQ;
+  if (nlu) *nlu = GYNC_NLU;
+}
+
+int gync_init(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(GYNC_ERR_CUDA, std::string("no CUDA device (this library has no CPU fallback): ") +
+                                   (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0"));
+  if (device < 0 || device >= count) return fail(GYNC_ERR_ARG, "device index out of range");
+  CK(cudaSetDevice(device));
+  if (g_stream && g_device != device) { cudaStreamDestroy(g_stream); g_stream = nullptr; }
+  if (!g_stream) CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  g_num_sms = prop.multiProcessorCount;
+  if (const char* v = getenv("GYNC_LLK_VARIANT")) g_llk_variant = atoi(v);
+  g_device = device;
+  return GYNC_OK;
+}
+
+void gync_shutdown(void) {
+  if (g_stream) { cudaStreamDestroy(g_stream); g_stream = nullptr; }
+  g_device = -1;
+}
+
+// ------------------------------------------------------------------------------------------ K1
+int gync_loglik_batch_dev(const double* dX, int64_t N, const double* d_data, int32_t M,
+                          const double* d_sigma_rho, const gync_solver_opts* opts, double* dLL,
+                          double* dYmeas, int32_t* d_status, int32_t* d_nsteps, void* stream) {
+  if (N < 0 || M < 1 || !dLL || (N > 0 && (!dX || !d_data || !d_sigma_rho)))
+    return fail(GYNC_ERR_ARG, "gync_loglik_batch: bad arguments");
+  if (int rc = ensure_init()) return rc;
+  if (N == 0) return GYNC_OK;
+  cudaStream_t s = (cudaStream_t)stream;   // NULL = the legacy default stream, as torch uses
+  double* iscale = nullptr;
+  int* allnan = nullptr;
+  CK(cudaMallocAsync((void**)&iscale, sizeof(double) * 4 * M, s));
+  CK(cudaMallocAsync((void**)&allnan, sizeof(int) * M, s));
+  gync_prep_patients_kernel<<<blocks_for(M, 64), 64, 0, s>>>(d_data, d_sigma_rho, M, iscale, allnan);
+  const GyncSolverOpts so = to_opts(opts);
+  unsigned long long* counter = nullptr;
+  CK(cudaMallocAsync((void**)&counter, sizeof(unsigned long long), s));
+  CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), s));
+  // persistent lanes: one CTA of GYNC_SOLVE_BLOCK threads per SM (variant 1: two CTAs of 32)
+#define LLK(B)                                                                                                  \
+  do {                                                                                                          \
+    if (int rc = prep_solver_kernel(gync_loglik_kernel<B>, GyncWorkSm<B>::kSmemBytes, B)) return rc;            \
+    const int64_t want = (N + B - 1) / B;                                                                       \
+    const int nb = (int)std::min<int64_t>(want, (int64_t)g_num_sms * (GYNC_SOLVE_BLOCK / B));                   \
+    gync_loglik_kernel<B><<<nb, B, GyncWorkSm<B>::kSmemBytes, s>>>(dX, N, d_data, iscale, allnan, M, so, dLL,   \
+                                                                   dYmeas, d_status, d_nsteps, counter);        \
+  } while (0)
+  if (g_llk_variant == 1) LLK(32); else LLK(GYNC_SOLVE_BLOCK);
+#undef LLK
+  CK(cudaFreeAsync(counter, s));
+  g_launches += 2;
+  CK(cudaGetLastError());
+  CK(cudaFreeAsync(iscale, s));
+  CK(cudaFreeAsync(allnan, s));
+  return GYNC_OK;
+}
+
+int gync_loglik_batch(const double* X, int64_t N, const double* data, int32_t M, const double* sigma_rho,
+                      const gync_solver_opts* opts, double* LL, double* Ymeas, int32_t* status,
+                      int32_t* nsteps) {
+  if (N < 0 || M < 1 || !LL || (N > 0 && (!X || !data || !sigma_rho)))
+    return fail(GYNC_ERR_ARG, "gync_loglik_batch: bad arguments");
+  if (int rc = ensure_init()) return rc;
+  if (N == 0) return GYNC_OK;
+  DBuf dX, dD, dS, dLL, dY, dSt, dNs;
+  CK(dX.alloc(sizeof(double) * N * GYNC_NX));
+  CK(dD.alloc(sizeof(double) * 124 * M));
+  CK(dS.alloc(sizeof(double) * M));
+  CK(dLL.alloc(sizeof(double) * N * M));
+  if (Ymeas) CK(dY.alloc(sizeof(double) * N * GYNC_NT_MEAS * GYNC_NMEAS));
+  CK(dSt.alloc(sizeof(int32_t) * N));
+  if (nsteps) CK(dNs.alloc(sizeof(int32_t) * N * 2));
+  CK(cudaMemcpyAsync(dX.p, X, sizeof(double) * N * GYNC_NX, cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemcpyAsync(dD.p, data, sizeof(double) * 124 * M, cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemcpyAsync(dS.p, sigma_rho, sizeof(double) * M, cudaMemcpyHostToDevice, g_stream));
+  int rc = gync_loglik_batch_dev(dX.as<double>(), N, dD.as<double>(), M, dS.as<double>(), opts, dLL.as<double>(),
+                                 Ymeas ? dY.as<double>() : nullptr, dSt.as<int32_t>(),
+                                 nsteps ? dNs.as<int32_t>() : nullptr, g_stream);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(LL, dLL.p, sizeof(double) * N * M, cudaMemcpyDeviceToHost, g_stream));
+  if (Ymeas) CK(cudaMemcpyAsync(Ymeas, dY.p, sizeof(double) * N * GYNC_NT_MEAS * GYNC_NMEAS, cudaMemcpyDeviceToHost, g_stream));
+  if (status) CK(cudaMemcpyAsync(status, dSt.p, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, g_stream));
+  if (nsteps) CK(cudaMemcpyAsync(nsteps, dNs.p, sizeof(int32_t) * N * 2, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
+  return GYNC_OK;
+}
+
+static int solve_common(const double* X, const double* Y0, const double* P, int64_t N, const double* t, int32_t nT,
+                        const gync_solver_opts* opts, double* Y, int32_t* status) {
+  if (N < 0 || nT < 1 || !t || !Y || (N > 0 && !X && (!Y0 || !P)))
+    return fail(GYNC_ERR_ARG, "gync_solve: bad arguments");
+  for (int k = 1; k < nT; ++k)
+    if (t[k] < t[k - 1]) return fail(GYNC_ERR_ARG, "gync_solve: time grid must be sorted ascending");
+  if (int rc = ensure_init()) return rc;
+  if (N == 0) return GYNC_OK;
+  DBuf dX, dY0, dP, dT, dY, dSt;
+  if (X) {
+    CK(dX.alloc(sizeof(double) * N * GYNC_NX));
+    CK(cudaMemcpyAsync(dX.p, X, sizeof(double) * N * GYNC_NX, cudaMemcpyHostToDevice, g_stream));
+  } else {
+    CK(dY0.alloc(sizeof(double) * N * GYNC_NY));
+    CK(dP.alloc(sizeof(double) * N * GYNC_NP));
+    CK(cudaMemcpyAsync(dY0.p, Y0, sizeof(double) * N * GYNC_NY, cudaMemcpyHostToDevice, g_stream));
+    CK(cudaMemcpyAsync(dP.p, P, sizeof(double) * N * GYNC_NP, cudaMemcpyHostToDevice, g_stream));
+  }
+  CK(dT.alloc(sizeof(double) * nT));
+  CK(dY.alloc(sizeof(double) * N * nT * GYNC_NY));
+  CK(dSt.alloc(sizeof(int32_t) * N));
+  CK(cudaMemcpyAsync(dT.p, t, sizeof(double) * nT, cudaMemcpyHostToDevice, g_stream));
+  if (int rc = prep_solver_kernel(gync_solve_kernel<GYNC_SOLVE_BLOCK>, GyncWorkSm<GYNC_SOLVE_BLOCK>::kSmemBytes, GYNC_SOLVE_BLOCK)) return rc;
+  gync_solve_kernel<GYNC_SOLVE_BLOCK><<<std::min<unsigned>(blocks_for(N, GYNC_SOLVE_BLOCK), g_num_sms), GYNC_SOLVE_BLOCK,
+                                         GyncWorkSm<GYNC_SOLVE_BLOCK>::kSmemBytes, g_stream>>>(
+      X ? dX.as<double>() : nullptr, dY0.as<double>(), dP.as<double>(), N, dT.as<double>(), nT, to_opts(opts),
+      dY.as<double>(), dSt.as<int32_t>());
+  g_launches += 1;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(Y, dY.p, sizeof(double) * N * nT * GYNC_NY, cudaMemcpyDeviceToHost, g_stream));
+  if (status) CK(cudaMemcpyAsync(status, dSt.p, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
+  return GYNC_OK;
+}
+
+int gync_solve(const double* Y0, const double* P, int64_t N, const double* t, int32_t nT,
+               const gync_solver_opts* opts, double* Y, int32_t* status) {
+  return solve_common(nullptr, Y0, P, N, t, nT, opts, Y, status);
+}
+
+int gync_forwardsol(const double* X, int64_t N, const double* t, int32_t nT, const gync_solver_opts* opts,
+                    double* Y, int32_t* status) {
+  if (N > 0 && !X) return fail(GYNC_ERR_ARG, "gync_forwardsol: X is NULL");
+  return solve_common(X, nullptr, nullptr, N, t, nT, opts, Y, status);
+}
+
+// ------------------------------------------------------------------------------------------ K4
+
+int gync_em_iterate_dev(double* dw, const double* dL, int64_t K, int32_t M, int32_t niter, double* d_history,
+                        void* stream) {
+  if (K < 0 || M < 1 || niter < 0 || (K > 0 && (!dw || !dL))) return fail(GYNC_ERR_ARG, "gync_em_iterate: bad arguments");
+  if (int rc = ensure_init()) return rc;
+  if (K == 0 || niter == 0) return GYNC_OK;
+  cudaStream_t s = (cudaStream_t)stream;   // NULL = the legacy default stream, as torch uses
+#define CALL(MT) em_persistent_launch<MT>(dw, dL, K, M, niter, d_history, s)
+  EM_DISPATCH(M, CALL);
+#undef CALL
+}
+
+int gync_em_norms_dev(const double* dw, const double* dL, int64_t K, int32_t M, double* d_norms_out, void* stream) {
+  if (K < 0 || M < 1 || !d_norms_out) return fail(GYNC_ERR_ARG, "gync_em_norms: bad arguments");
+  if (int rc = ensure_init()) return rc;
+  cudaStream_t s = (cudaStream_t)stream;   // NULL = the legacy default stream, as torch uses
+#define CALL(MT) em_norms_launch<MT>(dw, dL, K, M, d_norms_out, s)
+  EM_DISPATCH(M, CALL);
+#undef CALL
+}
+
+int gync_em_step_dev(double* dw, const double* dL, int64_t K, int32_t M, const double* d_norms_in,
+                     double* d_norms_out, void* stream) {
+  if (K < 0 || M < 1 || !d_norms_in || !d_norms_out) return fail(GYNC_ERR_ARG, "gync_em_step: bad arguments");
+  if (int rc = ensure_init()) return rc;
+  cudaStream_t s = (cudaStream_t)stream;   // NULL = the legacy default stream, as torch uses
+#define CALL(MT) em_step_launch<MT>(dw, dL, K, M, d_norms_in, d_norms_out, s)
+  EM_DISPATCH(M, CALL);
+#undef CALL
+}
+
+int gync_em_iterate(double* w, const double* L, int64_t K, int32_t M, int32_t niter, double* history) {
+  if (K < 0 || M < 1 || niter < 0 || (K > 0 && (!w || !L))) return fail(GYNC_ERR_ARG, "gync_em_iterate: bad arguments");
+  if (int rc = ensure_init()) return rc;
+  if (K == 0 || niter == 0) return GYNC_OK;
+  DBuf dw, dL, dH;
+  CK(dw.alloc(sizeof(double) * K));
+  CK(dL.alloc(sizeof(double) * K * M));
+  if (history) CK(dH.alloc(sizeof(double) * K * niter));
+  CK(cudaMemcpyAsync(dw.p, w, sizeof(double) * K, cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemcpyAsync(dL.p, L, sizeof(double) * K * M, cudaMemcpyHostToDevice, g_stream));
+  int rc = gync_em_iterate_dev(dw.as<double>(), dL.as<double>(), K, M, niter, history ? dH.as<double>() : nullptr, g_stream);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(w, dw.p, sizeof(double) * K, cudaMemcpyDeviceToHost, g_stream));
+  if (history) CK(cudaMemcpyAsync(history, dH.p, sizeof(double) * K * niter, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
+  return GYNC_OK;
+}
+
+// ------------------------------------------------------------------------------------------ misc
+int gync_fp64_peak(double* tflops) {
+  if (!tflops) return fail(GYNC_ERR_ARG, "gync_fp64_peak: NULL");
+  if (int rc = ensure_init()) return rc;
+  const int threads = 256, blocks = g_num_sms * 8, iters = 1 << 16;
+  DBuf out;
+  CK(out.alloc(sizeof(double) * threads * blocks));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  gync_fp64_peak_kernel<<<blocks, threads, 0, g_stream>>>(out.as<double>(), 1024);
+  double best = 0.0;
+  for (int rep = 0; rep < 3; ++rep) {
+    CK(cudaEventRecord(e0, g_stream));
+    gync_fp64_peak_kernel<<<blocks, threads, 0, g_stream>>>(out.as<double>(), iters);
+    CK(cudaEventRecord(e1, g_stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double fl = 2.0 * 8.0 * (double)iters * threads * blocks;
+    best = std::max(best, fl / (ms * 1e-3) * 1e-12);
+  }
+  g_launches += 4;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *tflops = best;
+  return GYNC_OK;
+}
+
+}  // extern "C"
+
+#include "gync_abi_more.inl"

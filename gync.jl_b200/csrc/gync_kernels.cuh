@@ -1,0 +1,367 @@
+// sm_100a kernels of the GynC.jl hot path.  See DESIGN.md for the layout and roofline of each.
+#pragma once
+#include <cuda_runtime.h>
+#include <cooperative_groups.h>
+#include "gync_llh.cuh"
+
+namespace cg = cooperative_groups;
+
+__constant__ double        c_refallparms[GYNC_NP] = {GYNC_REFALLPARMS_LIST};
+__constant__ unsigned char c_sampledinds[GYNC_NS] = {GYNC_SAMPLEDINDS0_LIST};
+__constant__ double        c_measmag[GYNC_NMEAS]  = {GYNC_MEASMAG_LIST};
+
+#define GYNC_NT_MEAS 62   /* 2 periods x 31 days (model.jl:126,128) */
+
+// ------------------------------------------------------------------------------------------
+// Patient tables -> per-(patient,hormone) inverse scale and the all-missing flag
+// (llh_measerror, model.jl:158-163: scale = model_measmagnitude * sigma_rho; all-NaN -> -Inf)
+__global__ void gync_prep_patients_kernel(const double* __restrict__ data, const double* __restrict__ sigma_rho,
+                                          int M, double* __restrict__ iscale, int* __restrict__ allnan) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  int any = 0;
+  for (int i = 0; i < GYNC_NDAYS * GYNC_NMEAS; ++i) {
+    const double d = data[(size_t)m * GYNC_NDAYS * GYNC_NMEAS + i];
+    any |= (d == d);
+  }
+  allnan[m] = !any;
+  for (int h = 0; h < GYNC_NMEAS; ++h) iscale[GYNC_NMEAS * m + h] = 1.0 / (c_measmag[h] * sigma_rho[m]);
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-thread solver state, B200 layout.
+//
+// One sample per thread needs ~520 doubles of live state per step (derived parameters q[93], the
+// LU factors A[165], five RODAS stage vectors, y/y_new/work vector) — four times what a thread
+// can hold in registers, and local-memory spills of that size miss L1 and serialise on L2
+// latency (measured: 14 k solves/s).  So the big arrays live in SHARED memory, interleaved
+// [element][thread] (a warp touches 32 consecutive doubles: conflict-free), with exactly
+// GYNC_SOLVE_BLOCK threads per SM and one CTA per SM (216.6 KB of the 227 KB), and the small
+// hot vectors (y, y_new, work) in registers.  The straight-line generated code indexes every
+// array with compile-time constants, so each access is one LDS/STS with an immediate offset.
+#ifndef GYNC_SOLVE_BLOCK
+#define GYNC_SOLVE_BLOCK 64
+#endif
+
+// Element proxy: reads are VOLATILE shared loads.  Without that the compiler forwards the values
+// it stored (it can prove the addresses) and, being out of registers, spills them to LOCAL
+// memory — i.e. right back to the L1/L2 path this layout exists to avoid.
+struct GyncSmRef {
+  double* p;
+  __device__ __forceinline__ operator double() const { return *(volatile double*)p; }
+  __device__ __forceinline__ const GyncSmRef& operator=(double v) const { *p = v; return *this; }
+  __device__ __forceinline__ const GyncSmRef& operator+=(double v) const { *p = *(volatile double*)p + v; return *this; }
+  __device__ __forceinline__ const GyncSmRef& operator-=(double v) const { *p = *(volatile double*)p - v; return *this; }
+};
+
+template <int BLOCK>
+struct GyncSmView {
+  double* p;
+  __device__ __forceinline__ GyncSmRef operator[](int i) const { return GyncSmRef{p + i * BLOCK}; }
+};
+
+template <int BLOCK>
+struct GyncWorkSm {
+  GyncSmView<BLOCK> q, k1, k2, k3, k4, k5, A;
+  double y[GYNC_NY], yn[GYNC_NY], e[GYNC_NY];
+  static constexpr int kDoublesPerThread = GYNC_NQ + 5 * GYNC_NY + GYNC_NLU;
+  static constexpr size_t kSmemBytes = sizeof(double) * kDoublesPerThread * BLOCK;
+  __device__ __forceinline__ void bind(double* sm) {
+    double* b = sm + threadIdx.x;
+    q.p = b;  b += GYNC_NQ * BLOCK;
+    k1.p = b; b += GYNC_NY * BLOCK;
+    k2.p = b; b += GYNC_NY * BLOCK;
+    k3.p = b; b += GYNC_NY * BLOCK;
+    k4.p = b; b += GYNC_NY * BLOCK;
+    k5.p = b; b += GYNC_NY * BLOCK;
+    A.p = b;
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// K1: forward solve + fused Gaussian log-likelihood epilogue.
+// Persistent lanes: each thread pulls sample indices from a global counter and walks its sample
+// through the merged measurement grid one step attempt per loop trip, so lanes of a warp stay
+// busy although their samples need different numbers of (adaptive) steps.
+struct GyncLlhSink {
+  const double* __restrict__ data;     // 31 x 4 x M
+  const double* __restrict__ iscale;   // 4 x M
+  int M;
+  int64_t N;
+  double* acc;                         // LL + n   (stride N over patients)
+  double* ymeas;                       // Ymeas + n (N x 62 x 4) or nullptr
+  __device__ __forceinline__ void operator()(int period, int day, const double* y) {
+    const double ym[GYNC_NMEAS] = {y[1], y[6], y[23], y[24]};   // measuredinds (model.jl:1)
+    if (ymeas) {
+#pragma unroll
+      for (int h = 0; h < GYNC_NMEAS; ++h) ymeas[N * ((period * GYNC_NDAYS + day) + GYNC_NT_MEAS * h)] = ym[h];
+    }
+    for (int m = 0; m < M; ++m) {
+      double a = 0.0;
+#pragma unroll
+      for (int h = 0; h < GYNC_NMEAS; ++h) {
+        const double d = __ldg(data + day + GYNC_NDAYS * h + GYNC_NDAYS * GYNC_NMEAS * m);
+        if (d == d) {
+          const double r = (d - ym[h]) * __ldg(iscale + GYNC_NMEAS * m + h);
+          a = fma(r, r, a);
+        }
+      }
+      acc[N * m] += a;
+    }
+  }
+};
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, 1)
+gync_loglik_kernel(const double* __restrict__ X, int64_t N, const double* __restrict__ data,
+                   const double* __restrict__ iscale, const int* __restrict__ allnan, int M,
+                   GyncSolverOpts o, double* __restrict__ LL, double* __restrict__ Ymeas,
+                   int* __restrict__ status, int* __restrict__ nsteps, unsigned long long* __restrict__ counter) {
+  extern __shared__ double gync_sm[];
+  GyncWorkSm<BLOCK> W;
+  W.bind(gync_sm);
+  const double big = 1.0e300, ninf = -INFINITY;
+  bool active = false, done = false;
+  int64_t n = 0;
+  double T = 0.0, t = 0.0, tn = 0.0;
+  int i0 = 0, i1 = 0, budget = 0, st = GYNC_ST_OK;
+  GyncCtrl c;
+  GyncLlhSink sink = {data, iscale, M, N, nullptr, nullptr};
+  for (;;) {
+    if (!active && !done) {
+      n = (int64_t)atomicAdd(counter, 1ull);
+      if (n >= N) {
+        done = true;
+      } else {
+        gync_load_sample(W, [&](int k) { return __ldg(X + n + N * k); }, c_refallparms, c_sampledinds, &T);
+        for (int m = 0; m < M; ++m) LL[n + N * m] = 0.0;
+        sink.acc = LL + n;
+        sink.ymeas = Ymeas ? Ymeas + n : nullptr;
+        i0 = i1 = 0;
+        budget = o.max_steps;
+        t = fmin(1.0, 1.0 + T);
+        tn = t;
+        st = (gync_all_finite(W.y, GYNC_NY) && gync_all_finite(W.q, GYNC_NQ) && (T * 0.0 == 0.0)) ? GYNC_ST_OK
+                                                                                                 : GYNC_ST_NONFINITE;
+        gync_ctrl_init(c, (st == GYNC_ST_OK) ? ((o.h0 > 0.0) ? o.h0 : gync_initial_step(W, o.rtol, o.atol)) : 1.0);
+        active = true;
+      }
+    }
+    if (__all_sync(0xffffffffu, done)) break;
+    if (active) {
+      bool finished = (st != GYNC_ST_OK);
+      if (!finished) {
+        if (tn > t) {
+          if (budget-- <= 0) {
+            st = GYNC_ST_MAXSTEPS;
+          } else {
+            const int r = gync_attempt(W, c, t, tn, o);
+            if (r < 0) st = -r;
+          }
+        }
+        if (st == GYNC_ST_OK && t >= tn) {
+          // serve every measurement time equal to t, then pick the next target
+          for (;;) {
+            const double tA = (i0 < GYNC_NDAYS) ? (double)(i0 + 1) : big;
+            const double tB = (i1 < GYNC_NDAYS) ? (double)(i1 + 1) + T : big;
+            tn = fmin(tA, tB);
+            if (tn > t) break;
+            if (tA == tn) { sink(0, i0, W.y); ++i0; }
+            if (tB == tn) { sink(1, i1, W.y); ++i1; }
+          }
+          if (i0 >= GYNC_NDAYS && i1 >= GYNC_NDAYS) finished = true;
+        }
+        if (st != GYNC_ST_OK) finished = true;
+      }
+      if (finished) {
+        for (int m = 0; m < M; ++m) {
+          const double a = LL[n + N * m];
+          LL[n + N * m] = (st != GYNC_ST_OK || allnan[m]) ? ninf : -0.5 * a;
+        }
+        if (st != GYNC_ST_OK && Ymeas)
+          for (int k = 0; k < GYNC_NT_MEAS * GYNC_NMEAS; ++k) Ymeas[n + N * k] = NAN;
+        if (status) status[n] = st;
+        if (nsteps) { nsteps[n] = c.nacc; nsteps[n + N] = c.nrej; }
+        active = false;
+      }
+    }
+  }
+}
+
+// gync(y0,p,t) / forwardsol(x,t): full 33-species trajectory on a shared sorted time grid.
+struct GyncGridSink {
+  double* Y;        // Y + n ; layout N x nT x 33
+  int64_t N;
+  int nT;
+  __device__ __forceinline__ void operator()(int k, const double* y) {
+#pragma unroll
+    for (int i = 0; i < GYNC_NY; ++i) Y[N * (k + (int64_t)nT * i)] = y[i];
+  }
+};
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, 1)
+gync_solve_kernel(const double* __restrict__ X, const double* __restrict__ Y0, const double* __restrict__ P,
+                  int64_t N, const double* __restrict__ tgrid, int nT, GyncSolverOpts o,
+                  double* __restrict__ Y, int* __restrict__ status) {
+  extern __shared__ double gync_sm[];
+  GyncWorkSm<BLOCK> W;
+  W.bind(gync_sm);
+  for (int64_t n = (int64_t)blockIdx.x * BLOCK + threadIdx.x; n < N; n += (int64_t)gridDim.x * BLOCK) {
+    if (X) {
+      double T;
+      gync_load_sample(W, [&](int k) { return __ldg(X + n + N * k); }, c_refallparms, c_sampledinds, &T);
+    } else {
+      double p[GYNC_NP];
+#pragma unroll
+      for (int k = 0; k < GYNC_NP; ++k) p[k] = __ldg(P + n + N * k);
+      gync_pack_params(p, W.q);
+#pragma unroll
+      for (int i = 0; i < GYNC_NY; ++i) W.y[i] = __ldg(Y0 + n + N * i);
+    }
+    GyncGridSink sink = {Y + n, N, nT};
+    const int s = gync_run_time_grid(W, tgrid, nT, o, sink, (GyncStepStats*)nullptr);
+    if (s != GYNC_ST_OK) {
+      for (int64_t k = 0; k < (int64_t)nT * GYNC_NY; ++k) Y[n + N * k] = NAN;   // gyncycle.jl:18-19
+    }
+    if (status) status[n] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: EM / self-consistency iteration  w_k <- w_k/M * sum_m L_km / (L'w)_m   (em.jl:27-41)
+//
+// Fused single-pass form: one read of L per iteration.  While row k's new weight is produced,
+// the NEXT iteration's denominators sum_k L_km w_k' are accumulated in registers; block partials
+// go to a double-buffered global scratch and every block re-reduces them in a fixed order after
+// one grid-wide barrier (deterministic, no atomics).  All `niter` iterations run inside one
+// cooperative launch.  HBM-bound: 8KM + 16K bytes per iteration.
+#define GYNC_EM_THREADS 256
+
+template <int MT>
+__device__ __forceinline__ void em_block_reduce(double (&acc)[MT], double* s_red /*[warps][MT]*/, double* out /*[MT]*/, int M) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int m = 0; m < MT; ++m) {
+    double v = acc[m];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (lane == 0) s_red[warp * MT + m] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < M) {
+    double v = 0.0;
+    for (int w = 0; w < GYNC_EM_THREADS / 32; ++w) v += s_red[w * MT + threadIdx.x];
+    out[threadIdx.x] = v;
+  }
+  __syncthreads();
+}
+
+// partial denominators of this block's rows: out[m] = sum_k L[k,m] w[k]
+template <int MT>
+__device__ __forceinline__ void em_norms_pass(const double* __restrict__ w, const double* __restrict__ L,
+                                              int64_t K, int M, double* s_red, double* out) {
+  double acc[MT];
+#pragma unroll
+  for (int m = 0; m < MT; ++m) acc[m] = 0.0;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < K; k += (int64_t)gridDim.x * blockDim.x) {
+    const double wk = w[k];
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+      if (m < M) acc[m] = fma(__ldg(L + k + K * m), wk, acc[m]);
+  }
+  em_block_reduce<MT>(acc, s_red, out, M);
+}
+
+// one EM step over this block's rows given s_rinv[m] = 1/norms[m]; accumulates next partials
+template <int MT>
+__device__ __forceinline__ void em_step_pass(double* __restrict__ w, const double* __restrict__ L, int64_t K, int M,
+                                             const double* s_rinv, double* s_red, double* out, double* hist) {
+  double acc[MT];
+#pragma unroll
+  for (int m = 0; m < MT; ++m) acc[m] = 0.0;
+  const double invM = 1.0 / (double)M;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < K; k += (int64_t)gridDim.x * blockDim.x) {
+    double l[MT];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) l[m] = (m < M) ? __ldg(L + k + K * m) : 0.0;
+    double s = 0.0;
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+      if (m < M) s = fma(l[m], s_rinv[m], s);
+    const double wn = w[k] * invM * s;
+    w[k] = wn;
+    if (hist) hist[k] = wn;
+#pragma unroll
+    for (int m = 0; m < MT; ++m) acc[m] = fma(l[m], wn, acc[m]);
+  }
+  em_block_reduce<MT>(acc, s_red, out, M);
+}
+
+template <int MT>
+__global__ void __launch_bounds__(GYNC_EM_THREADS)
+gync_em_persistent_kernel(double* __restrict__ w, const double* __restrict__ L, int64_t K, int M, int niter,
+                          double* __restrict__ partials /* 2 x gridDim.x x MT */, double* __restrict__ history) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double s_red[(GYNC_EM_THREADS / 32) * MT];
+  __shared__ double s_rinv[MT];
+  const int nb = gridDim.x;
+  em_norms_pass<MT>(w, L, K, M, s_red, partials + (size_t)blockIdx.x * MT);
+  __threadfence();
+  grid.sync();
+  for (int it = 0; it < niter; ++it) {
+    const double* pin = partials + (size_t)(it & 1) * nb * MT;
+    double* pout = partials + (size_t)((it + 1) & 1) * nb * MT;
+    if (threadIdx.x < M) {
+      double v = 0.0;
+      for (int b = 0; b < nb; ++b) v += __ldcg(pin + (size_t)b * MT + threadIdx.x);
+      s_rinv[threadIdx.x] = 1.0 / v;
+    }
+    __syncthreads();
+    em_step_pass<MT>(w, L, K, M, s_rinv, s_red, pout + (size_t)blockIdx.x * MT,
+                     history ? history + (size_t)it * K : nullptr);
+    __threadfence();
+    grid.sync();
+  }
+}
+
+// Sharded form: block partials -> scratch, then a one-block finishing kernel sums them.
+template <int MT>
+__global__ void __launch_bounds__(GYNC_EM_THREADS)
+gync_em_norms_kernel(const double* __restrict__ w, const double* __restrict__ L, int64_t K, int M,
+                     double* __restrict__ partials) {
+  __shared__ double s_red[(GYNC_EM_THREADS / 32) * MT];
+  em_norms_pass<MT>(w, L, K, M, s_red, partials + (size_t)blockIdx.x * MT);
+}
+
+template <int MT>
+__global__ void __launch_bounds__(GYNC_EM_THREADS)
+gync_em_step_kernel(double* __restrict__ w, const double* __restrict__ L, int64_t K, int M,
+                    const double* __restrict__ norms_in, double* __restrict__ partials) {
+  __shared__ double s_red[(GYNC_EM_THREADS / 32) * MT];
+  __shared__ double s_rinv[MT];
+  if (threadIdx.x < M) s_rinv[threadIdx.x] = 1.0 / norms_in[threadIdx.x];
+  __syncthreads();
+  em_step_pass<MT>(w, L, K, M, s_rinv, s_red, partials + (size_t)blockIdx.x * MT, nullptr);
+}
+
+__global__ void gync_em_finish_kernel(const double* __restrict__ partials, int nb, int MT, int M, double* __restrict__ out) {
+  const int m = threadIdx.x;
+  if (m < M) {
+    double v = 0.0;
+    for (int b = 0; b < nb; ++b) v += partials[(size_t)b * MT + m];
+    out[m] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// FP64 FMA peak microbenchmark: 8 independent DFMA chains per thread.
+__global__ void gync_fp64_peak_kernel(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double b = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}

@@ -12,10 +12,10 @@
 #include "gync_solver.cuh"
 
 // Sink concept:  void operator()(int period, int day /*0..30*/, const double* y /*33*/)
-template <class Sink>
-GYNC_HD static inline int gync_run_meas_grid(GyncWork& W, const double T, const GyncSolverOpts& o,
+template <class WK, class Sink>
+GYNC_HD static int gync_run_meas_grid(WK& W, const double T, const GyncSolverOpts& o,
                                              Sink& sink, GyncStepStats* st) {
-  if (!gync_all_finite(W.y, GYNC_NY) || !gync_all_finite(W.q, GYNC_NQ) || !gync_all_finite(&T, 1))
+  if (!gync_all_finite(W.y, GYNC_NY) || !gync_all_finite(W.q, GYNC_NQ) || !(T * 0.0 == 0.0))
     return GYNC_ST_NONFINITE;
   GyncCtrl c;
   c.h = (o.h0 > 0.0) ? o.h0 : gync_initial_step(W, o.rtol, o.atol);
@@ -41,8 +41,8 @@ GYNC_HD static inline int gync_run_meas_grid(GyncWork& W, const double T, const 
 }
 
 // Generic sorted time grid (gync(y0,p,t): gyncycle.jl:8-26).  Sink: void(int k, const double* y).
-template <class Sink>
-GYNC_HD static inline int gync_run_time_grid(GyncWork& W, const double* tgrid, const int nT,
+template <class WK, class Sink>
+GYNC_HD static int gync_run_time_grid(WK& W, const double* tgrid, const int nT,
                                              const GyncSolverOpts& o, Sink& sink, GyncStepStats* st) {
   if (!gync_all_finite(W.y, GYNC_NY) || !gync_all_finite(W.q, GYNC_NQ)) return GYNC_ST_NONFINITE;
   GyncCtrl c;

@@ -83,39 +83,50 @@ struct GyncWork {
 
 // One step attempt of size h from W.y; on return W.yn = y(t+h) candidate, returns the scaled
 // error norm (RMS over the 33 species of e_i / (atol + rtol*max(|y_i|,|yn_i|))).
-GYNC_HD static inline double gync_rodas4_step(GyncWork& W, const double h, const double rtol, const double atol) {
+// Storage: W.q, W.A, W.k1..k5 may be shared-memory views (every read a real load, so each value
+// is read once per use); W.y, W.yn and the work vector W.e are per-thread registers.  Each stage
+// is evaluated into W.e, solved there, and then parked in its k-slot.
+template <class WK>
+GYNC_HD static double gync_rodas4_step(WK& W, const double h, const double rtol, const double atol) {
   const double ih = 1.0 / h;
-  gync_rhs_w(W.y, W.q, ih * (1.0 / RD_G), W.k1, W.A);
+  gync_rhs_w(W.y, W.q, ih * (1.0 / RD_G), W.e, W.A);
   gync_lu(W.A);
-  gync_lusolve(W.A, W.k1);
+  gync_lusolve(W.A, W.e);
 #pragma unroll
-  for (int i = 0; i < GYNC_NY; ++i) W.yn[i] = W.y[i] + RD_A21 * W.k1[i];
-  gync_rhs(W.yn, W.q, W.k2);
+  for (int i = 0; i < GYNC_NY; ++i) { const double k1 = W.e[i]; W.k1[i] = k1; W.yn[i] = W.y[i] + RD_A21 * k1; }
+  gync_rhs(W.yn, W.q, W.e);
 #pragma unroll
-  for (int i = 0; i < GYNC_NY; ++i) W.k2[i] += (RD_C21 * ih) * W.k1[i];
-  gync_lusolve(W.A, W.k2);
+  for (int i = 0; i < GYNC_NY; ++i) W.e[i] += (RD_C21 * ih) * W.k1[i];
+  gync_lusolve(W.A, W.e);
 #pragma unroll
-  for (int i = 0; i < GYNC_NY; ++i) W.yn[i] = W.y[i] + RD_A31 * W.k1[i] + RD_A32 * W.k2[i];
-  gync_rhs(W.yn, W.q, W.k3);
+  for (int i = 0; i < GYNC_NY; ++i) { const double k2 = W.e[i]; W.k2[i] = k2; W.yn[i] = W.y[i] + RD_A31 * W.k1[i] + RD_A32 * k2; }
+  gync_rhs(W.yn, W.q, W.e);
 #pragma unroll
-  for (int i = 0; i < GYNC_NY; ++i) W.k3[i] += ih * (RD_C31 * W.k1[i] + RD_C32 * W.k2[i]);
-  gync_lusolve(W.A, W.k3);
+  for (int i = 0; i < GYNC_NY; ++i) W.e[i] += ih * (RD_C31 * W.k1[i] + RD_C32 * W.k2[i]);
+  gync_lusolve(W.A, W.e);
 #pragma unroll
-  for (int i = 0; i < GYNC_NY; ++i) W.yn[i] = W.y[i] + RD_A41 * W.k1[i] + RD_A42 * W.k2[i] + RD_A43 * W.k3[i];
-  gync_rhs(W.yn, W.q, W.k4);
+  for (int i = 0; i < GYNC_NY; ++i) {
+    const double k3 = W.e[i];
+    W.k3[i] = k3;
+    W.yn[i] = W.y[i] + RD_A41 * W.k1[i] + RD_A42 * W.k2[i] + RD_A43 * k3;
+  }
+  gync_rhs(W.yn, W.q, W.e);
 #pragma unroll
-  for (int i = 0; i < GYNC_NY; ++i) W.k4[i] += ih * (RD_C41 * W.k1[i] + RD_C42 * W.k2[i] + RD_C43 * W.k3[i]);
-  gync_lusolve(W.A, W.k4);
+  for (int i = 0; i < GYNC_NY; ++i) W.e[i] += ih * (RD_C41 * W.k1[i] + RD_C42 * W.k2[i] + RD_C43 * W.k3[i]);
+  gync_lusolve(W.A, W.e);
+#pragma unroll
+  for (int i = 0; i < GYNC_NY; ++i) {
+    const double k4 = W.e[i];
+    W.k4[i] = k4;
+    W.yn[i] = W.y[i] + RD_A51 * W.k1[i] + RD_A52 * W.k2[i] + RD_A53 * W.k3[i] + RD_A54 * k4;
+  }
+  gync_rhs(W.yn, W.q, W.e);
 #pragma unroll
   for (int i = 0; i < GYNC_NY; ++i)
-    W.yn[i] = W.y[i] + RD_A51 * W.k1[i] + RD_A52 * W.k2[i] + RD_A53 * W.k3[i] + RD_A54 * W.k4[i];
-  gync_rhs(W.yn, W.q, W.k5);
+    W.e[i] += ih * (RD_C51 * W.k1[i] + RD_C52 * W.k2[i] + RD_C53 * W.k3[i] + RD_C54 * W.k4[i]);
+  gync_lusolve(W.A, W.e);
 #pragma unroll
-  for (int i = 0; i < GYNC_NY; ++i)
-    W.k5[i] += ih * (RD_C51 * W.k1[i] + RD_C52 * W.k2[i] + RD_C53 * W.k3[i] + RD_C54 * W.k4[i]);
-  gync_lusolve(W.A, W.k5);
-#pragma unroll
-  for (int i = 0; i < GYNC_NY; ++i) W.yn[i] += W.k5[i];
+  for (int i = 0; i < GYNC_NY; ++i) { const double k5 = W.e[i]; W.k5[i] = k5; W.yn[i] += k5; }
   gync_rhs(W.yn, W.q, W.e);
 #pragma unroll
   for (int i = 0; i < GYNC_NY; ++i)
@@ -141,7 +152,7 @@ struct GyncCtrl {
 
 // Decide on a step attempt of size h with scaled error err.  Returns true if accepted.
 // Updates c.h with the proposal for the next attempt.
-GYNC_HD static inline bool gync_ctrl_update(GyncCtrl& c, const double h, double err, const bool finite) {
+GYNC_HD static bool gync_ctrl_update(GyncCtrl& c, const double h, double err, const bool finite) {
   const double SAFE = 0.9, FAC1 = 5.0, FAC2 = 1.0 / 6.0;
   if (!finite || !(err == err)) {          // NaN/Inf in the stage values: shrink hard
     c.h = 0.2 * h;
@@ -175,8 +186,8 @@ GYNC_HD static inline bool gync_ctrl_update(GyncCtrl& c, const double h, double 
 // Build the per-thread parameter state from one sample x (strided access: x[k*stride]).
 // allparms (model.jl:20-24): the 82 sampled values are scattered into a copy of refallparms.
 // `refallparms` and `sampledinds` come from the caller (constant memory on the device).
-template <class LoadX>
-GYNC_HD static inline void gync_load_sample(GyncWork& W, LoadX ldx, const double* refallparms,
+template <class WK, class LoadX>
+GYNC_HD static void gync_load_sample(WK& W, LoadX ldx, const double* refallparms,
                                             const unsigned char* sampledinds, double* period) {
   double p[GYNC_NP];
 #pragma unroll
@@ -189,47 +200,64 @@ GYNC_HD static inline void gync_load_sample(GyncWork& W, LoadX ldx, const double
   *period = ldx(GYNC_NX - 1);
 }
 
-GYNC_HD static inline bool gync_all_finite(const double* v, int n) {
+template <class VT>
+GYNC_HD static bool gync_all_finite(const VT& v, int n) {
   double s = 0.0;
   for (int i = 0; i < n; ++i) s += v[i] * 0.0;   // NaN/Inf -> NaN
   return s == 0.0;
 }
 
 // Automatic initial step: h0 = 0.01 * ||y||/||f|| in the scaled RMS norm, clamped.
-GYNC_HD static inline double gync_initial_step(GyncWork& W, const double rtol, const double atol) {
-  gync_rhs(W.y, W.q, W.k1);
+template <class WK>
+GYNC_HD static double gync_initial_step(WK& W, const double rtol, const double atol) {
+  gync_rhs(W.y, W.q, W.e);
   double d0 = 0.0, d1 = 0.0;
   for (int i = 0; i < GYNC_NY; ++i) {
     const double sc = atol + rtol * fabs(W.y[i]);
     d0 += (W.y[i] / sc) * (W.y[i] / sc);
-    d1 += (W.k1[i] / sc) * (W.k1[i] / sc);
+    d1 += (W.e[i] / sc) * (W.e[i] / sc);
   }
   double h = (d0 > 1e-10 && d1 > 1e-10) ? 0.01 * sqrt(d0 / d1) : 1e-6;
   if (!(h == h)) h = 1e-6;
   return fmin(fmax(h, 1e-8), 1e-2);
 }
 
+// One step attempt towards tend (> t), clipping the step so that tend is hit exactly.
+// Returns 0: keep going, 1: tend reached, <0: -(status bits) failure.
+template <class WK>
+GYNC_HD static int gync_attempt(WK& W, GyncCtrl& c, double& t, const double tend, const GyncSolverOpts& o) {
+  double h = c.h;
+  if (o.hmax > 0.0) h = fmin(h, o.hmax);
+  const double rem = tend - t;
+  const bool last = (h * 1.0001 >= rem);
+  if (last) h = rem;
+  if (!(h > 1e-14 * fmax(1.0, fabs(t)))) return -GYNC_ST_HMIN;
+  const double hprop = c.h;
+  const double err = gync_rodas4_step(W, h, o.rtol, o.atol);
+  const bool fin = gync_all_finite(W.yn, GYNC_NY);
+  if (gync_ctrl_update(c, h, err, fin)) {
+    t = last ? tend : t + h;
+#pragma unroll
+    for (int i = 0; i < GYNC_NY; ++i) W.y[i] = W.yn[i];
+    if (last && h < hprop) c.h = fmax(c.h, hprop);   // output truncation must not shrink the step
+    return last ? 1 : 0;
+  }
+  return 0;
+}
+
 // Integrate from t to tend (tend > t), landing exactly on tend.  Returns status bits.
-GYNC_HD static inline int gync_advance(GyncWork& W, GyncCtrl& c, double& t, const double tend,
-                                       const GyncSolverOpts& o, int& budget) {
-  while (t < tend) {
+template <class WK>
+GYNC_HD static int gync_advance(WK& W, GyncCtrl& c, double& t, const double tend,
+                                const GyncSolverOpts& o, int& budget) {
+  for (;;) {
     if (budget <= 0) return GYNC_ST_MAXSTEPS;
     --budget;
-    double h = c.h;
-    if (o.hmax > 0.0) h = fmin(h, o.hmax);
-    const double rem = tend - t;
-    const bool last = (h * 1.0001 >= rem);
-    if (last) h = rem;
-    if (!(h > 1e-14 * fmax(1.0, fabs(t)))) return GYNC_ST_HMIN;
-    const double hprop = c.h;
-    const double err = gync_rodas4_step(W, h, o.rtol, o.atol);
-    const bool fin = gync_all_finite(W.yn, GYNC_NY);
-    if (gync_ctrl_update(c, h, err, fin)) {
-      t = last ? tend : t + h;
-#pragma unroll
-      for (int i = 0; i < GYNC_NY; ++i) W.y[i] = W.yn[i];
-      if (last && h < hprop) c.h = fmax(c.h, hprop);   // output truncation must not shrink the step
-    }
+    const int r = gync_attempt(W, c, t, tend, o);
+    if (r == 1) return GYNC_ST_OK;
+    if (r < 0) return -r;
   }
-  return GYNC_ST_OK;
+}
+
+GYNC_HD static void gync_ctrl_init(GyncCtrl& c, double h) {
+  c.h = h; c.hacc = h; c.erracc = 1.0; c.nacc = 0; c.nrej = 0; c.rej_last = 0;
 }

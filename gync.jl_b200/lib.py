@@ -1,0 +1,99 @@
+"""ctypes binding of the C-ABI shared library (include/gync_b200.h).
+
+This is the same ABI a Julia `ccall` binds: column-major arrays, Int64/Cint
+widths, in-place mutation.  There is NO CPU fallback: if the library is missing or no CUDA
+device is present, every compute call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libgync_b200.so")
+
+c_double_p = C.POINTER(C.c_double)
+c_int32_p = C.POINTER(C.c_int32)
+c_int64_p = C.POINTER(C.c_int64)
+
+
+class SolverOpts(C.Structure):
+    _fields_ = [("rtol", C.c_double), ("atol", C.c_double), ("h0", C.c_double), ("hmax", C.c_double),
+                ("max_steps", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Prior(C.Structure):
+    _fields_ = [("gmm_means", C.c_double * (31 * 33)), ("gmm_stds", C.c_double * 33),
+                ("upper", C.c_double * 82), ("mu_T", C.c_double), ("sd_T", C.c_double)]
+
+
+class GyncError(RuntimeError):
+    pass
+
+
+#: every symbol include/gync_b200.h declares (tests check that the .so exports all of them)
+EXPORTS = [
+    "gync_init", "gync_shutdown", "gync_last_error", "gync_abi_version", "gync_dims",
+    "gync_solve", "gync_forwardsol", "gync_loglik_batch", "gync_loglik_batch_dev",
+    "gync_logprior_batch", "gync_mcmc_run", "gync_em_iterate", "gync_em_iterate_dev",
+    "gync_em_norms_dev", "gync_em_step_dev", "gync_launch_count", "gync_wc_normalize", "gync_fp64_peak",
+]
+
+_lib = None
+
+
+def load():
+    """Load the shared library (no device needed for loading)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GyncError(f"{LIB_PATH} not found — run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    lib.gync_last_error.restype = C.c_char_p
+    lib.gync_launch_count.restype = C.c_int64
+    lib.gync_init.argtypes = [C.c_int]
+    lib.gync_dims.argtypes = [c_int32_p] * 5
+    lib.gync_solve.argtypes = [c_double_p, c_double_p, C.c_int64, c_double_p, C.c_int32, C.POINTER(SolverOpts),
+                               c_double_p, c_int32_p]
+    lib.gync_forwardsol.argtypes = [c_double_p, C.c_int64, c_double_p, C.c_int32, C.POINTER(SolverOpts),
+                                    c_double_p, c_int32_p]
+    lib.gync_loglik_batch.argtypes = [c_double_p, C.c_int64, c_double_p, C.c_int32, c_double_p,
+                                      C.POINTER(SolverOpts), c_double_p, c_double_p, c_int32_p, c_int32_p]
+    lib.gync_loglik_batch_dev.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p,
+                                          C.POINTER(SolverOpts), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p]
+    lib.gync_logprior_batch.argtypes = [c_double_p, C.c_int64, C.POINTER(Prior), c_double_p]
+    lib.gync_mcmc_run.argtypes = [c_double_p, c_double_p, C.c_int64, c_double_p, C.c_double, c_double_p, C.c_int32,
+                                  c_double_p, c_int32_p, C.POINTER(Prior), C.POINTER(SolverOpts), C.c_int64,
+                                  C.c_int32, C.c_uint64, C.c_uint64, c_double_p, c_double_p, c_double_p, c_int64_p]
+    lib.gync_em_iterate.argtypes = [c_double_p, c_double_p, C.c_int64, C.c_int32, C.c_int32, c_double_p]
+    lib.gync_em_iterate_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.gync_em_norms_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.gync_em_step_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.gync_wc_normalize.argtypes = [c_double_p, c_double_p, c_int64_p, C.c_int64, C.c_int32, c_double_p,
+                                      c_double_p, c_double_p]
+    lib.gync_fp64_peak.argtypes = [c_double_p]
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise GyncError(f"gync_b200 error {rc}: {load().gync_last_error().decode()}")
+
+
+def dptr(a):
+    return None if a is None else a.ctypes.data_as(c_double_p)
+
+
+def fcol(a, dtype=np.float64):
+    """Column-major copy/view (Julia layout)."""
+    return np.asfortranarray(a, dtype=dtype)
+
+
+def opts(rtol=None, atol=None, h0=0.0, hmax=0.0, max_steps=0):
+    return SolverOpts(rtol or 0.0, atol or 0.0, h0, hmax, max_steps, 0)

@@ -1,0 +1,134 @@
+/* gync_b200 — C ABI of the B200-native GynC.jl hot path.
+ *
+ * The reference (axsk/GynC.jl) has no FFI layer: the seam is Julia-method level.  Each entry
+ * point below replaces the body of one reference method (cited as file:line, paths relative to
+ * the reference repo) and is what a `ccall` from that method binds; INTEGRATION.md shows the
+ * Julia stubs.  Conventions:
+ *   - all matrices are COLUMN-MAJOR, as Julia stores them; `int64_t` for Julia `Int` sizes,
+ *     `int32_t` for `Cint`;
+ *   - the caller owns every host buffer; nothing is retained past return;
+ *   - return 0 on success, <0 on argument / CUDA errors (text via gync_last_error()); never
+ *     throws.  A NUMERICAL failure of one sample is not an error: its status is non-zero, its
+ *     trajectory NaN and its log-likelihood -Inf (gyncycle.jl:18-19, model.jl:138-141);
+ *   - calls block until results are in the output buffers; one host thread at a time;
+ *   - there is NO CPU fallback: without a CUDA device every compute call returns GYNC_ERR_CUDA.
+ *   - `*_dev` variants take DEVICE pointers and a cudaStream_t (as void*) and do not
+ *     synchronise; they are what a host that keeps data resident in HBM calls.
+ */
+#ifndef GYNC_B200_H
+#define GYNC_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GYNC_OK          0
+#define GYNC_ERR_ARG    -1
+#define GYNC_ERR_CUDA   -2
+#define GYNC_ERR_NOMEM  -3
+
+/* per-sample solver status bits */
+#define GYNC_STATUS_OK        0
+#define GYNC_STATUS_MAXSTEPS  1
+#define GYNC_STATUS_HMIN      2
+#define GYNC_STATUS_NONFINITE 4
+
+/* ---- lifecycle ------------------------------------------------------------------------ */
+int  gync_init(int device);              /* select device, create the library stream */
+void gync_shutdown(void);
+const char* gync_last_error(void);
+int  gync_abi_version(void);
+/* model dimensions: ny=33, np=114, nx=116, nq (derived params), nlu (LU nonzeros) */
+void gync_dims(int32_t* ny, int32_t* np, int32_t* nx, int32_t* nq, int32_t* nlu);
+
+/* solver options shared by the solve / likelihood / MCMC entry points.
+ * rtol/atol are the `reltol`/`abstol` keywords of gync() (gyncycle.jl:8).  max_steps<=0 -> default. */
+typedef struct {
+  double  rtol, atol;
+  double  h0;          /* initial step, <=0 automatic */
+  double  hmax;        /* <=0 none */
+  int32_t max_steps;   /* step attempts per solve (the reference's CVODE cap is 500 per output) */
+  int32_t reserved;
+} gync_solver_opts;
+
+/* ---- gync(y0,p,t;reltol,abstol)  — gyncycle.jl:8-26 --------------------------------------
+ * Y0: N x 33, P: N x 114 (full parameter vectors), t: nT sorted times, t[0] = initial time.
+ * Y:  N x nT x 33 (for N=1 this is exactly the reference's nT x 33 matrix). */
+int gync_solve(const double* Y0, const double* P, int64_t N, const double* t, int32_t nT,
+               const gync_solver_opts* opts, double* Y, int32_t* status);
+
+/* ---- forwardsol(x,tspan) — model.jl:90 (allparms: model.jl:20-24) ------------------------
+ * X: N x 116 samples [82 parms | 33 y0 | period]. */
+int gync_forwardsol(const double* X, int64_t N, const double* t, int32_t nT,
+                    const gync_solver_opts* opts, double* Y, int32_t* status);
+
+/* ---- llh(c,x) / llh(s::Sampling) / llh block of WeightedChain(...) ----------------------
+ * model.jl:128-163, sampling.jl:32, weightedchain.jl:53-56.
+ * data: 31 x 4 x M patient tables (NaN = missing), sigma_rho: M.
+ * LL: N x M log-likelihoods (one forward solve per sample serves all M patients).
+ * Ymeas (nullable): N x 62 x 4 measured-species trajectory at meastimes(31,2,T) in
+ * [period0; period1] order (model.jl:126,136).  nsteps (nullable): N x 2 accepted/rejected. */
+int gync_loglik_batch(const double* X, int64_t N, const double* data, int32_t M,
+                      const double* sigma_rho, const gync_solver_opts* opts,
+                      double* LL, double* Ymeas, int32_t* status, int32_t* nsteps);
+int gync_loglik_batch_dev(const double* dX, int64_t N, const double* d_data, int32_t M,
+                          const double* d_sigma_rho, const gync_solver_opts* opts,
+                          double* dLL, double* dYmeas, int32_t* d_status, int32_t* d_nsteps,
+                          void* stream);
+
+/* ---- logprior(c,x) — model.jl:111-117, priors model.jl:69-77 ---------------------------- */
+typedef struct {
+  double gmm_means[31 * 33];   /* row-major: component i, species j (rows of referencesolution()) */
+  double gmm_stds[33];
+  double upper[82];            /* box (0, upper_i): Truncated(Flat(),0,5*refparms_i) */
+  double mu_T, sd_T;           /* Normal(28.9, 3.4) */
+} gync_prior;
+int gync_logprior_batch(const double* X, int64_t N, const gync_prior* prior, double* LP);
+
+/* ---- sample!(s::Sampling, iters) for many chains — sampling.jl:62-79, model.jl:97-107 ----
+ * Non-adaptive Mamba AMM step: x' = x + SigmaL z, accept iff u < exp(logf(x')-logf(x)),
+ * logf(x) = logpost(c, exp(x)) + sum(x).
+ * state: C x 116 log-space chain states (in/out); logf: C current log-target (in/out; pass NaN
+ *   to have it computed); chol: 116 x 116 lower Cholesky factor of propvar, or NULL with
+ *   `prop_sd` > 0 for the isotropic default (model.jl:14-16: sd = sqrt(log(1.01)));
+ * patient_of_chain: C indices into data (0-based);
+ * samples_out: n_out x 116 x C with n_out = iters/thin rows of exp(state) (sampling.jl:74);
+ * rng: Philox4x32-10 keyed by (seed, chain), counter = (iteration offset) so runs are resumable;
+ * inj_z (iters x 116 x C) / inj_u (iters x C): if non-NULL, use these draws instead (tests). */
+int gync_mcmc_run(double* state, double* logf, int64_t C, const double* chol, double prop_sd,
+                  const double* data, int32_t M, const double* sigma_rho,
+                  const int32_t* patient_of_chain, const gync_prior* prior,
+                  const gync_solver_opts* opts, int64_t iters, int32_t thin,
+                  uint64_t seed, uint64_t iter_offset,
+                  const double* inj_z, const double* inj_u,
+                  double* samples_out, int64_t* naccept);
+
+/* ---- emiteration!(w,L) / emiterations — em.jl:27-41, em.jl:5 ----------------------------
+ * L: K x M, w: K (updated in place, niter times).  history (nullable): K x niter, column i =
+ * weights after iteration i+1. */
+int gync_em_iterate(double* w, const double* L, int64_t K, int32_t M, int32_t niter, double* history);
+int gync_em_iterate_dev(double* dw, const double* dL, int64_t K, int32_t M, int32_t niter,
+                        double* d_history, void* stream);
+/* Sharded form (one process per GPU): one EM step on the local rows given the GLOBAL
+ * denominators d_norms_in (M); writes this shard's partial denominators of the NEXT iteration
+ * to d_norms_out (M) for the caller's allreduce.  em_norms_dev computes the first partials. */
+int gync_em_norms_dev(const double* dw, const double* dL, int64_t K, int32_t M, double* d_norms_out, void* stream);
+int gync_em_step_dev(double* dw, const double* dL, int64_t K, int32_t M, const double* d_norms_in,
+                     double* d_norms_out, void* stream);
+/* launches of our kernels since init (bench bookkeeping) */
+int64_t gync_launch_count(void);
+
+/* ---- WeightedChain normalisation — weightedchain.jl:59-67 -------------------------------
+ * LL: K x M log-likelihoods (in) -> L (out, may alias): exp(LL - colmax) ./ colsum;
+ * logprior: K, counts: K (int64) -> weights = counts/sum, density = rowmean(L).*exp(lp-max), normalised. */
+int gync_wc_normalize(const double* LL, const double* logprior, const int64_t* counts, int64_t K, int32_t M,
+                      double* L, double* weights, double* density);
+
+/* FP64 FMA peak microbenchmark (TFLOP/s) used as the solver's roofline denominator. */
+int gync_fp64_peak(double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
