@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native GynC.jl hot path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one pass of the hot path over one batch: the batched GynCycle forward solve + fused
+Gaussian log-likelihood for 10^5 synthetic parameter vectors against one patient
+(BASELINE.json configs[1]).  `value` = likelihood evaluations per second with the inputs resident
+in HBM (CUDA events on the launching stream, max over ranks); `e2e` = the same metric through
+the host-buffer C-ABI call `gync_loglik_batch` (H2D of the samples from pinned memory and D2H of
+the log-likelihoods inside the timed region).  Under torchrun every rank solves its own 10^5
+samples (weak scaling, no data-path collective); the EM leg row-shards K = 10^6 x 40 and does
+one NCCL allreduce of the 40 denominators per iteration (BASELINE.json configs[4]).
+
+`--impl reference` times the CPU oracle port of the reference path (variable-order BDF at the
+reference's reltol=abstol=1e-4, all host threads) on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_SAMPLES = 100_000          # configs[1]
+SEED = 20160911 + 2
+RTOL = ATOL = 1e-8           # parity tolerance (tests/test_gpu_parity.py): llh within 1e-8 rel. of converged
+METRIC = "gyncycle_likelihood_evals_per_sec"
+UNIT = "evals/s"
+
+
+def near_set(n, seed=SEED):
+    """cfg 2 'near' set: x = exp(log(init) + 0.0998 z), z ~ N(0, I_116)."""
+    from gync_b200 import api
+    rng = np.random.Generator(np.random.PCG64(seed))
+    x0 = np.concatenate([api.refparms, api.refy0, [28.0]])
+    X = np.exp(np.log(x0)[None, :] + 0.0998 * rng.standard_normal((n, 116)))
+    X[0] = x0
+    return X
+
+
+def workload_config(n_gpus):
+    return {"workload": "batched GynCycle forward solve + log-likelihood, 1e5 synthetic parameter vectors (near set) x 1 "
+                        "patient (Lausanne 1) per GPU", "n_samples_per_gpu": N_SAMPLES, "n_patients": 1,
+            "rtol": RTOL, "atol": ATOL, "solver": "RODAS4 adaptive, sparse LU (165 nnz)",
+            "l2_policy": "solver state lives in shared memory/registers; the 93 MB sample matrix is read once per step "
+                         "(each step re-reads it from HBM/L2 — inputs are not larger than L2, a 256 MB buffer is written "
+                         "between timed steps to flush it)",
+            "parallelism": f"{n_gpus} GPU(s), samples sharded, no data-path collective"}
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.p = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                       "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for ln in self.p.stdout:
+            self.rows.append([c.strip() for c in ln.split(",")])
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU legs
+def cpu_reference_leg(steps, warmup, budget_s=12.0):
+    """The reference's CPU path, restated (oracle port): BDF at reltol=abstol=1e-4 (gyncycle.jl:8),
+    one OpenMP thread per sample — the analogue of the reference's pmap (sampling.jl:32)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import c_oracle as co
+    from gync_b200 import api
+    data = api.Lausanne(1).data
+    cores = co.num_threads()
+    # size the bounded sample so that one step takes ~budget_s/steps
+    X = near_set(2048)
+    t0 = time.perf_counter()
+    co.llh_batch(X[:256], [data], [0.1], 0, 1e-4, 1e-4)
+    per = (time.perf_counter() - t0) / 256
+    n = int(max(256, min(2048 * 16, budget_s / max(steps, 1) / per)))
+    X = near_set(n)
+    for _ in range(min(warmup, 1)):
+        co.llh_batch(X[: max(256, n // 4)], [data], [0.1], 0, 1e-4, 1e-4)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        LL = co.llh_batch(X, [data], [0.1], 0, 1e-4, 1e-4)
+        times.append(time.perf_counter() - t0)
+    ms = float(np.mean(times)) * 1e3
+    return {"value": n / (ms * 1e-3), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} of the 1e5 near-set samples per step, oracle BDF(1-5)/Newton/dense LU/DQ-Jacobian at "
+                      f"reltol=abstol=1e-4 (CVODE stand-in), {cores} OpenMP threads; "
+                      f"finite fraction {float(np.isfinite(LL).mean()):.4f}"}, ms
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb, ms = cpu_reference_leg(args.steps, args.warmup, budget_s=30.0)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args.gpus),
+            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU legs
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-em", action="store_true", help="skip the EM leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if rank == 0 and not os.path.exists(ge.LIB):
+        ge.build_cuda()
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+    import gync_b200 as g
+    from gync_b200 import lib as L
+    lib = L.load()
+    L.check(lib.gync_init(local))
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- inputs (each rank its own shard of the near set)
+    Xh = near_set(N_SAMPLES, SEED + rank)
+    data = g.Lausanne(1).data
+    Xp = torch.from_numpy(np.ascontiguousarray(Xh.T)).pin_memory()        # (116,N) row-major == N x 116 column-major
+    dX = Xp.to(dev)
+    dD = torch.from_numpy(np.ascontiguousarray(data.T)).to(dev)           # 31 x 4 column-major
+    dS = torch.tensor([0.1], dtype=torch.float64, device=dev)
+    dLL = torch.empty(N_SAMPLES, dtype=torch.float64, device=dev)
+    dSt = torch.empty(N_SAMPLES, dtype=torch.int32, device=dev)
+    dNs = torch.empty(2 * N_SAMPLES, dtype=torch.int32, device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
+    op = L.opts(RTOL, ATOL)
+
+    def step_dev():
+        L.check(lib.gync_loglik_batch_dev(dX.data_ptr(), N_SAMPLES, dD.data_ptr(), 1, dS.data_ptr(), C.byref(op),
+                                          dLL.data_ptr(), None, dSt.data_ptr(), dNs.data_ptr(), stream))
+
+    for _ in range(args.warmup):
+        step_dev()
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = lib.gync_launch_count()
+    evs = []
+    barrier()
+    for _ in range(args.steps):
+        flush.fill_(1.0)                                  # L2 flush between timed steps
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step_dev()
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    launches = int(lib.gync_launch_count() - l0)
+    ms_dev = max_over_ranks(sum(a.elapsed_time(b) for a, b in evs) / args.steps)
+    clk = clocks.stop() if rank == 0 else None
+    value = world * N_SAMPLES / (ms_dev * 1e-3)
+
+    # ---- roofline of the dominant kernel (the solver): counted work / kernel time vs measured FP64 peak
+    ns = dNs.cpu().numpy().astype(np.int64)
+    attempts = int(ns.sum())
+    nfail = int((dSt != 0).sum().item())
+    fl_step = flops_per_step(lib)
+    peak = C.c_double()
+    L.check(lib.gync_fp64_peak(C.byref(peak)))
+    achieved = attempts * fl_step / (ms_dev * 1e-3) * 1e-12          # TFLOP/s on this rank's kernel
+    roofline = {"bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
+                "frac": achieved / peak.value if peak.value else None, "traffic": None,
+                "kernel": "gync_loglik_kernel<64,32>", "kernel_ms": ms_dev,
+                "how": f"{attempts} RODAS4 step attempts x {fl_step} FP64 flops per step (counted from the generated "
+                       "code, DESIGN.md §5) / CUDA-event time; peak = FP64 FMA microbenchmark measured in this run "
+                       "(MEASURED_PEAKS.json has no FP64 figure)",
+                "step_attempts_per_sample": attempts / N_SAMPLES, "failed_samples": nfail}
+
+    # ---- e2e through the host-buffer C-ABI call (pinned H2D + D2H inside the timed region)
+    Xnp = Xp.numpy().T                                     # F-ordered view over the pinned buffer
+    LLh = np.empty((N_SAMPLES, 1), order="F")
+    sth = np.zeros(N_SAMPLES, dtype=np.int32)
+    Dh = np.asfortranarray(data)
+    sig = np.array([0.1])
+
+    def step_e2e():
+        L.check(lib.gync_loglik_batch(L.dptr(Xnp), N_SAMPLES, L.dptr(Dh), 1, L.dptr(sig), C.byref(op), L.dptr(LLh),
+                                      None, sth.ctypes.data_as(L.c_int32_p), None))
+    assert Xnp.flags.f_contiguous
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+    e2e = {"value": world * N_SAMPLES / (ms_e2e * 1e-3), "unit": UNIT,
+           "h2d_bytes_per_step": int(N_SAMPLES * 116 * 8 + 124 * 8 + 8), "d2h_bytes_per_step": int(N_SAMPLES * 12),
+           "ms_per_step": ms_e2e, "llh_checksum": float(np.nansum(LLh[np.isfinite(LLh)]))}
+
+    # ---- EM leg
+    em = None
+    if not args.no_em:
+        em = em_leg(lib, L, torch, dist, dev, stream, world, rank, barrier, max_over_ranks)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world),
+                "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline}
+        if em:
+            line["em"] = em
+            line["roofline_em"] = em.get("roofline")
+        if world == 1 and not args.no_cpu:
+            cb, _ = cpu_reference_leg(2, 1)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def flops_per_step(lib):
+    """FP64 flops of one RODAS4 step attempt, from the generated code's operation counts
+    (csrc/gen/gync_model_gen.h) plus the hand-written stage algebra."""
+    f = getattr(lib, "gync_flops_per_step", None)
+    if f is not None:
+        f.restype = C.c_double
+        return float(f())
+    return 7746.0
+
+
+def em_leg(lib, L, torch, dist, dev, stream, world, rank, barrier, max_over_ranks, niter=100):
+    """EM iterations/s: cfg 3 (K=1e5 x 40, L2-resident) on one GPU and cfg 5 (K=1e6 x 40, 320 MB > L2)
+    row-sharded over the ranks with one allreduce of the 40 denominators per iteration."""
+    import json as _json
+    M = 40
+    out = {}
+    peaks = {}
+    try:
+        peaks = _json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+
+    def make(K):
+        Lm = torch.rand(M, K, dtype=torch.float64, device=dev, generator=gen)      # (M,K) row-major == K x M col-major
+        return Lm
+
+    def time_persistent(K):
+        Lm = make(K)
+        Lm /= Lm.sum(1, keepdim=True)
+        w = torch.full((K,), 1.0 / K, dtype=torch.float64, device=dev)
+        L.check(lib.gync_em_iterate_dev(w.data_ptr(), Lm.data_ptr(), K, M, 10, None, stream))
+        torch.cuda.synchronize()
+        best = None
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            L.check(lib.gync_em_iterate_dev(w.data_ptr(), Lm.data_ptr(), K, M, niter, None, stream))
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        return best / niter
+
+    if world == 1:
+        for name, K in (("cfg3_K1e5", 100_000), ("cfg5_K1e6", 1_000_000)):
+            ms = time_persistent(K)
+            by = 8 * K * M + 16 * K + 16 * M
+            out[name] = {"K": K, "M": M, "us_per_iter": ms * 1e3, "iters_per_s": 1e3 / ms,
+                         "algorithmic_GBps": by / ms / 1e6, "frac_of_hbm": by / ms / 1e6 / hbm}
+        K = 1_000_000
+        by = 8 * K * M + 16 * K + 16 * M
+        out["roofline"] = {"bound": "hbm", "achieved": out["cfg5_K1e6"]["algorithmic_GBps"], "peak": hbm, "unit": "GB/s",
+                           "frac": out["cfg5_K1e6"]["frac_of_hbm"], "traffic": None,
+                           "kernel": "gync_em_persistent_kernel<40>", "peak_source": hbm_src,
+                           "how": "8KM+16K+16M algorithmic bytes per iteration (L read once) / (CUDA-event time of one "
+                                  "100-iteration cooperative launch / 100); K=1e6 x 40 = 320 MB > 126 MB L2"}
+        return out
+    # sharded cfg 5
+    K = 1_000_000 // world
+    Lm = make(K)
+    colsum = Lm.sum(1)
+    dist.all_reduce(colsum)
+    Lm /= colsum[:, None]
+    w = torch.full((K,), 1.0 / (K * world), dtype=torch.float64, device=dev)
+    na = torch.empty(M, dtype=torch.float64, device=dev)
+    nb = torch.empty(M, dtype=torch.float64, device=dev)
+
+    def run(n):
+        L.check(lib.gync_em_norms_dev(w.data_ptr(), Lm.data_ptr(), K, M, na.data_ptr(), stream))
+        dist.all_reduce(na)
+        a, b = na, nb
+        for _ in range(n):
+            L.check(lib.gync_em_step_dev(w.data_ptr(), Lm.data_ptr(), K, M, a.data_ptr(), b.data_ptr(), stream))
+            dist.all_reduce(b)
+            a, b = b, a
+    run(10)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run(niter)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / niter
+    by = 8 * K * M + 16 * K + 16 * M
+    wsum = w.sum()
+    dist.all_reduce(wsum)
+    out["cfg5_K1e6_sharded"] = {"K_total": K * world, "K_per_gpu": K, "M": M, "us_per_iter": ms * 1e3, "iters_per_s": 1e3 / ms,
+                                "algorithmic_GBps_per_gpu": by / ms / 1e6, "frac_of_hbm": by / ms / 1e6 / hbm,
+                                "collective": "one NCCL allreduce(sum) of 40 f64 per iteration", "sum_w": float(wsum.item())}
+    out["roofline"] = {"bound": "hbm", "achieved": by / ms / 1e6, "peak": hbm, "unit": "GB/s", "frac": by / ms / 1e6 / hbm,
+                       "traffic": None, "kernel": "gync_em_step_kernel<40> + NCCL allreduce", "peak_source": hbm_src}
+    return out
+
+
+if __name__ == "__main__":
+    main()

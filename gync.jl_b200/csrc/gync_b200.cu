@@ -156,6 +156,18 @@ const char* gync_last_error(void) { return g_err.c_str(); }
 
 int64_t gync_launch_count(void) { return g_launches.load(); }
 
+// FP64 flops of one RODAS4 step attempt: generated-code counts (add+mul; a reciprocal = seed + 4 DFMA = 8,
+// the real power = exp+log ~ 60) + the hand-written stage algebra of gync_rodas4_step
+// (33 x [2+2+4+5+6+7+8+9+1+11+1] for the stage combinations + 33 x 15 for the error norm).
+double gync_flops_per_step(void) {
+  const double rcp = 8.0, pw = 60.0;
+  const double rhs = GYNC_OPS_RHS_FLOP + rcp * GYNC_OPS_RHS_RCP + pw * GYNC_OPS_RHS_POW;
+  const double rhsw = GYNC_OPS_RHSW_FLOP + rcp * GYNC_OPS_RHSW_RCP + pw * GYNC_OPS_RHSW_POW;
+  const double lu = GYNC_OPS_LU_FLOP + rcp * GYNC_OPS_LU_RCP;
+  const double stage = 33.0 * (2 + 2 + 4 + 5 + 6 + 7 + 8 + 9 + 1 + 11 + 1) + 33.0 * 15.0;
+  return rhsw + 5.0 * rhs + lu + 6.0 * GYNC_OPS_SOLVE_FLOP + stage;
+}
+
 void gync_dims(int32_t* ny, int32_t* np, int32_t* nx, int32_t* nq, int32_t* nlu) {
   if (ny) *ny = GYNC_NY;
   if (np) *np = GYNC_NP;
@@ -205,16 +217,23 @@ int gync_loglik_batch_dev(const double* dX, int64_t N, const double* d_data, int
   unsigned long long* counter = nullptr;
   CK(cudaMallocAsync((void**)&counter, sizeof(unsigned long long), s));
   CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), s));
-  // persistent lanes: one CTA of GYNC_SOLVE_BLOCK threads per SM (variant 1: two CTAs of 32)
-#define LLK(B)                                                                                                  \
+  // persistent lanes: one CTA of 64 sample slots per SM, spread over 32/LPW * 2 warps
+#define LLK(B, LPW)                                                                                             \
   do {                                                                                                          \
-    if (int rc = prep_solver_kernel(gync_loglik_kernel<B>, GyncWorkSm<B>::kSmemBytes, B)) return rc;            \
+    if (int rc = prep_solver_kernel(gync_loglik_kernel<B, LPW>, GyncWorkSm<B>::kSmemBytes, B)) return rc;       \
     const int64_t want = (N + B - 1) / B;                                                                       \
     const int nb = (int)std::min<int64_t>(want, (int64_t)g_num_sms * (GYNC_SOLVE_BLOCK / B));                   \
-    gync_loglik_kernel<B><<<nb, B, GyncWorkSm<B>::kSmemBytes, s>>>(dX, N, d_data, iscale, allnan, M, so, dLL,   \
-                                                                   dYmeas, d_status, d_nsteps, counter);        \
+    gync_loglik_kernel<B, LPW><<<nb, B * (32 / LPW), GyncWorkSm<B>::kSmemBytes, s>>>(                           \
+        dX, N, d_data, iscale, allnan, M, so, dLL, dYmeas, d_status, d_nsteps, counter);                        \
   } while (0)
-  if (g_llk_variant == 1) LLK(32); else LLK(GYNC_SOLVE_BLOCK);
+  switch (g_llk_variant) {   // tuning variants (env GYNC_LLK_VARIANT)
+    case 1: LLK(32, 32); break;
+    case 2: LLK(64, 16); break;
+    case 3: LLK(64, 8); break;
+    case 4: LLK(32, 16); break;
+    case 5: LLK(32, 8); break;
+    default: LLK(64, 32); break;
+  }
 #undef LLK
   CK(cudaFreeAsync(counter, s));
   g_launches += 2;

@@ -60,14 +60,19 @@ struct GyncSmView {
   __device__ __forceinline__ GyncSmRef operator[](int i) const { return GyncSmRef{p + i * BLOCK}; }
 };
 
+// BLOCK = sample slots per CTA.  LPW = active lanes per warp: the solver is bound by per-warp
+// latency (dependent FP64 chains, shared-memory loads, instruction fetch of ~12 k straight-line
+// instructions per step), not by FP64 issue, and shared memory caps an SM at 64 samples — so
+// the 64 samples are spread over 32/LPW times as many warps, each running LPW lanes, to give
+// every SM sub-partition more warps to interleave.
 template <int BLOCK>
 struct GyncWorkSm {
   GyncSmView<BLOCK> q, k1, k2, k3, k4, k5, A;
   double y[GYNC_NY], yn[GYNC_NY], e[GYNC_NY];
   static constexpr int kDoublesPerThread = GYNC_NQ + 5 * GYNC_NY + GYNC_NLU;
   static constexpr size_t kSmemBytes = sizeof(double) * kDoublesPerThread * BLOCK;
-  __device__ __forceinline__ void bind(double* sm) {
-    double* b = sm + threadIdx.x;
+  __device__ __forceinline__ void bind(double* sm, int slot) {
+    double* b = sm + slot;
     q.p = b;  b += GYNC_NQ * BLOCK;
     k1.p = b; b += GYNC_NY * BLOCK;
     k2.p = b; b += GYNC_NY * BLOCK;
@@ -111,15 +116,18 @@ struct GyncLlhSink {
   }
 };
 
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, 1)
+template <int BLOCK, int LPW>
+__global__ void __launch_bounds__(BLOCK * (32 / LPW), 1)
 gync_loglik_kernel(const double* __restrict__ X, int64_t N, const double* __restrict__ data,
                    const double* __restrict__ iscale, const int* __restrict__ allnan, int M,
                    GyncSolverOpts o, double* __restrict__ LL, double* __restrict__ Ymeas,
                    int* __restrict__ status, int* __restrict__ nsteps, unsigned long long* __restrict__ counter) {
   extern __shared__ double gync_sm[];
+  const int lane = threadIdx.x & 31;
+  if (lane >= LPW) return;
+  constexpr unsigned kMask = (LPW == 32) ? 0xffffffffu : ((1u << LPW) - 1u);
   GyncWorkSm<BLOCK> W;
-  W.bind(gync_sm);
+  W.bind(gync_sm, (threadIdx.x >> 5) * LPW + lane);
   const double big = 1.0e300, ninf = -INFINITY;
   bool active = false, done = false;
   int64_t n = 0;
@@ -147,7 +155,7 @@ gync_loglik_kernel(const double* __restrict__ X, int64_t N, const double* __rest
         active = true;
       }
     }
-    if (__all_sync(0xffffffffu, done)) break;
+    if (__all_sync(kMask, done)) break;
     if (active) {
       bool finished = (st != GYNC_ST_OK);
       if (!finished) {
@@ -206,7 +214,7 @@ gync_solve_kernel(const double* __restrict__ X, const double* __restrict__ Y0, c
                   double* __restrict__ Y, int* __restrict__ status) {
   extern __shared__ double gync_sm[];
   GyncWorkSm<BLOCK> W;
-  W.bind(gync_sm);
+  W.bind(gync_sm, threadIdx.x);
   for (int64_t n = (int64_t)blockIdx.x * BLOCK + threadIdx.x; n < N; n += (int64_t)gridDim.x * BLOCK) {
     if (X) {
       double T;

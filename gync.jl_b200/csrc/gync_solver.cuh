@@ -12,6 +12,25 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+
+// Branch-free FP64 reciprocal for the device: MUFU.RCP64H seed (>= 20 bits) + two Newton steps
+// (2^-20 -> 2^-40 -> 2^-80).  The compiler's 1.0/x carries a slow-path CALL per division (283
+// per RODAS step), which chops the straight-line code into ~40-instruction basic blocks and
+// serialises independent Hill terms; this keeps each RHS / LU one schedulable block.
+// 0, Inf and NaN inputs give NaN (the step is then rejected as non-finite), subnormals flush.
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ double gync_rcp_dev(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+#  define GYNC_RCP(x) gync_rcp_dev(x)
+#  define GYNC_POW0689(x) exp(0.689 * log(x))
+#endif
 #include "gen/gync_model_gen.h"
 
 #define GYNC_NX 116        /* sample width: 82 parameters | 33 initial values | period (model.jl:82-84) */
@@ -86,60 +105,96 @@ struct GyncWork {
 // Storage: W.q, W.A, W.k1..k5 may be shared-memory views (every read a real load, so each value
 // is read once per use); W.y, W.yn and the work vector W.e are per-thread registers.  Each stage
 // is evaluated into W.e, solved there, and then parked in its k-slot.
+#if defined(GYNC_PHASE_TIMING) && defined(__CUDACC__)
+__device__ long long gync_phase_clk[8];
+#endif
+#if defined(GYNC_PHASE_TIMING) && defined(__CUDA_ARCH__)
+#  define GYNC_TICK(slot) { const long long _now = clock64(); if (threadIdx.x == 0 && blockIdx.x == 0) gync_phase_clk[slot] += _now - _t0; _t0 = clock64(); }
+#  define GYNC_TICK_INIT long long _t0 = clock64();
+#else
+#  define GYNC_TICK(slot)
+#  define GYNC_TICK_INIT
+#endif
+
 template <class WK>
 GYNC_HD static double gync_rodas4_step(WK& W, const double h, const double rtol, const double atol) {
-  const double ih = 1.0 / h;
+  const double ih = GYNC_RCP(h);
+  GYNC_TICK_INIT
   gync_rhs_w(W.y, W.q, ih * (1.0 / RD_G), W.e, W.A);
+  GYNC_TICK(0)
   gync_lu(W.A);
+  GYNC_TICK(1)
   gync_lusolve(W.A, W.e);
+  GYNC_TICK(2)
 #pragma unroll
   for (int i = 0; i < GYNC_NY; ++i) { const double k1 = W.e[i]; W.k1[i] = k1; W.yn[i] = W.y[i] + RD_A21 * k1; }
+  GYNC_TICK(3)
   gync_rhs(W.yn, W.q, W.e);
+  GYNC_TICK(4)
 #pragma unroll
   for (int i = 0; i < GYNC_NY; ++i) W.e[i] += (RD_C21 * ih) * W.k1[i];
+  GYNC_TICK(5)
   gync_lusolve(W.A, W.e);
+  GYNC_TICK(2)
 #pragma unroll
   for (int i = 0; i < GYNC_NY; ++i) { const double k2 = W.e[i]; W.k2[i] = k2; W.yn[i] = W.y[i] + RD_A31 * W.k1[i] + RD_A32 * k2; }
+  GYNC_TICK(3)
   gync_rhs(W.yn, W.q, W.e);
+  GYNC_TICK(4)
 #pragma unroll
   for (int i = 0; i < GYNC_NY; ++i) W.e[i] += ih * (RD_C31 * W.k1[i] + RD_C32 * W.k2[i]);
+  GYNC_TICK(5)
   gync_lusolve(W.A, W.e);
+  GYNC_TICK(2)
 #pragma unroll
   for (int i = 0; i < GYNC_NY; ++i) {
     const double k3 = W.e[i];
     W.k3[i] = k3;
     W.yn[i] = W.y[i] + RD_A41 * W.k1[i] + RD_A42 * W.k2[i] + RD_A43 * k3;
   }
+  GYNC_TICK(3)
   gync_rhs(W.yn, W.q, W.e);
+  GYNC_TICK(4)
 #pragma unroll
   for (int i = 0; i < GYNC_NY; ++i) W.e[i] += ih * (RD_C41 * W.k1[i] + RD_C42 * W.k2[i] + RD_C43 * W.k3[i]);
+  GYNC_TICK(5)
   gync_lusolve(W.A, W.e);
+  GYNC_TICK(2)
 #pragma unroll
   for (int i = 0; i < GYNC_NY; ++i) {
     const double k4 = W.e[i];
     W.k4[i] = k4;
     W.yn[i] = W.y[i] + RD_A51 * W.k1[i] + RD_A52 * W.k2[i] + RD_A53 * W.k3[i] + RD_A54 * k4;
   }
+  GYNC_TICK(3)
   gync_rhs(W.yn, W.q, W.e);
+  GYNC_TICK(4)
 #pragma unroll
   for (int i = 0; i < GYNC_NY; ++i)
     W.e[i] += ih * (RD_C51 * W.k1[i] + RD_C52 * W.k2[i] + RD_C53 * W.k3[i] + RD_C54 * W.k4[i]);
+  GYNC_TICK(5)
   gync_lusolve(W.A, W.e);
+  GYNC_TICK(2)
 #pragma unroll
   for (int i = 0; i < GYNC_NY; ++i) { const double k5 = W.e[i]; W.k5[i] = k5; W.yn[i] += k5; }
+  GYNC_TICK(3)
   gync_rhs(W.yn, W.q, W.e);
+  GYNC_TICK(4)
 #pragma unroll
   for (int i = 0; i < GYNC_NY; ++i)
     W.e[i] += ih * (RD_C61 * W.k1[i] + RD_C62 * W.k2[i] + RD_C63 * W.k3[i] + RD_C64 * W.k4[i] + RD_C65 * W.k5[i]);
+  GYNC_TICK(5)
   gync_lusolve(W.A, W.e);
+  GYNC_TICK(2)
   double s = 0.0;
 #pragma unroll
   for (int i = 0; i < GYNC_NY; ++i) {
     W.yn[i] += W.e[i];
     const double sc = atol + rtol * fmax(fabs(W.y[i]), fabs(W.yn[i]));
-    const double r = W.e[i] / sc;
+    const double r = W.e[i] * GYNC_RCP(sc);
     s += r * r;
   }
+  GYNC_TICK(6)
   return sqrt(s * (1.0 / GYNC_NY));
 }
 

@@ -39,6 +39,7 @@ EXPORTS = [
     "gync_solve", "gync_forwardsol", "gync_loglik_batch", "gync_loglik_batch_dev",
     "gync_logprior_batch", "gync_mcmc_run", "gync_em_iterate", "gync_em_iterate_dev",
     "gync_em_norms_dev", "gync_em_step_dev", "gync_launch_count", "gync_wc_normalize", "gync_fp64_peak",
+    "gync_flops_per_step",
 ]
 
 _lib = None
@@ -77,6 +78,7 @@ def load():
     lib.gync_wc_normalize.argtypes = [c_double_p, c_double_p, c_int64_p, C.c_int64, C.c_int32, c_double_p,
                                       c_double_p, c_double_p]
     lib.gync_fp64_peak.argtypes = [c_double_p]
+    lib.gync_flops_per_step.restype = C.c_double
     _lib = lib
     return lib
 

@@ -125,6 +125,8 @@ int64_t gync_launch_count(void);
 int gync_wc_normalize(const double* LL, const double* logprior, const int64_t* counts, int64_t K, int32_t M,
                       double* L, double* weights, double* density);
 
+/* FP64 flops of one RODAS4 step attempt (counted from the generated code; roofline bookkeeping). */
+double gync_flops_per_step(void);
 /* FP64 FMA peak microbenchmark (TFLOP/s) used as the solver's roofline denominator. */
 int gync_fp64_peak(double* tflops);
 

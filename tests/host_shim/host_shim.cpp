@@ -5,6 +5,7 @@
 #include <string.h>
 #include <stdint.h>
 #include "gync_llh.cuh"
+#include "gync_philox.h"
 
 static const double REFALLPARMS[GYNC_NP] = {GYNC_REFALLPARMS_LIST};
 static const unsigned char SAMPLEDINDS[GYNC_NS] = {GYNC_SAMPLEDINDS0_LIST};
@@ -64,6 +65,13 @@ struct GridSink {
   double* Y;
   void operator()(int k, const double* y) { for (int i = 0; i < GYNC_NY; ++i) Y[k * GYNC_NY + i] = y[i]; }
 };
+
+void hs_philox(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t* out) { Philox::gen(seed, c0, c1, c2, c3, out); }
+void hs_draw(uint64_t seed, uint64_t chain, uint64_t iter, double* z116, double* u) {
+  for (int b = 0; b < 58; ++b) gync_draw_n2(seed, chain, iter, (uint32_t)b, z116[2 * b], z116[2 * b + 1]);
+  double u1;
+  gync_draw_u2(seed, chain, iter, 58u, *u, u1);
+}
 
 // gync(y0,p,t): full trajectory nT x 33 row-major
 int hs_solve(const double* y0, const double* p, const double* t, int nT, double rtol, double atol, int max_steps, double* Y) {

@@ -1,0 +1,59 @@
+"""N>1 host logic on CPU: world_size-2 gloo run of the sharded EM driver (gync.jl_b200/dist.py) with the
+oracle's arithmetic standing in for the CUDA kernels; result must equal the unsharded oracle."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "oracle"))
+from gync_b200.dist import shard_bounds, em_iterate_sharded
+import gync_oracle as o
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+rng = np.random.default_rng(11)
+K, M, niter = 1003, 7, 25
+L = rng.random((K, M)); L /= L.sum(0, keepdims=True)
+w0 = rng.random(K); w0 /= w0.sum()
+lo, hi = shard_bounds(K, world, rank)
+Ll, wl = L[lo:hi].copy(), w0[lo:hi].copy()
+def norms():
+    return torch.from_numpy(Ll.T @ wl)
+def step(n):
+    n = n.numpy()
+    s = (Ll / n[None, :]).sum(1)
+    wl[:] = wl / M * s                      # em.jl:33-39 on the local rows
+    return torch.from_numpy(Ll.T @ wl)
+calls = [0]
+def allreduce(x):
+    calls[0] += 1
+    dist.all_reduce(x)
+em_iterate_sharded(niter, norms, step, allreduce)
+assert calls[0] == niter + 1                 # ONE collective per iteration (+1 to start)
+ref = w0.copy()
+for _ in range(niter):
+    ref = o.emiteration(ref, L)
+err = np.max(np.abs(wl - ref[lo:hi]) / ref[lo:hi])
+assert err < 1e-12, err
+tot = torch.tensor([wl.sum()]); dist.all_reduce(tot)
+assert abs(tot.item() - 1) < 1e-12
+print("rank", rank, "ok", err)
+dist.destroy_process_group()
+'''
+
+
+def test_sharded_em_gloo_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29561", str(script)],
+                       capture_output=True, text=True, env=env, timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ok") == 2

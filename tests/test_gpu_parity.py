@@ -1,0 +1,330 @@
+"""GPU suite: the CUDA path (through the C ABI) against the oracle, the frozen golden vectors, and
+size-independent properties at BASELINE.json's full sizes.
+
+Tolerances (BASELINE.json north_star): trajectories at the measurement times within rtol 1e-6,
+log-likelihoods within 1e-8 relative, EM weights within 1e-10 after a fixed number of iterations —
+against the CONVERGED solution of the reference's ODE (the reference's own CVODE run
+at reltol=abstol=1e-4 is ~1e-3 away from it, and CVODE is not available to clone step for step).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden")
+RTOL_TRAJ, RTOL_LLH, RTOL_EM = 1e-6, 1e-8, 1e-10
+
+
+def relerr(a, b):
+    return np.max(np.abs(a - b) / (np.abs(b) + 1e-300))
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(G, "solution_golden.npz"))
+
+
+def near_set(n, seed):
+    import gync_oracle as o
+    rng = np.random.Generator(np.random.PCG64(seed))
+    X = np.exp(np.log(o.init_x())[None, :] + 0.0998 * rng.standard_normal((n, 116)))
+    return X
+
+
+# ---------------------------------------------------------------------------------------- K1
+def test_loglik_and_trajectories_vs_golden(gpu, gold):
+    datas = [gold["data"][:, :, m] for m in range(4)]
+    LL, st, Ym = gpu.loglik_matrix(gold["X"], datas, [0.1] * 4, want_traj=True)
+    ok = np.isfinite(gold["LL"][:, 0])
+    assert np.array_equal(st == 0, ok)                         # failures: same samples as the oracle
+    assert np.all(LL[~ok] == -np.inf) and np.isnan(Ym[~ok]).all()   # gyncycle.jl:18-19, model.jl:138-141
+    assert relerr(Ym[ok], gold["traj"][ok]) < RTOL_TRAJ
+    assert relerr(LL[ok], gold["LL"][ok]) < RTOL_LLH
+
+
+def test_loglik_vs_c_oracle_fresh_samples(gpu):
+    """Seeded samples that are not in the fixtures; the C oracle (converged mode) runs here in seconds."""
+    import c_oracle as co
+    import gync_oracle as o
+    X = near_set(48, 777)
+    X[5, 115] = 27.0            # integer period -> duplicated times
+    X[6, 115] = 31.75
+    data = o.lausanne(2)
+    LLo, tro = co.llh_batch(X, [data], [0.15], 1, 1e-11, 1e-11, want_traj=True)
+    LL, st, Ym = gpu.loglik_matrix(X, [data], [0.15], want_traj=True)
+    assert np.all(st == 0) and np.all(np.isfinite(LLo))
+    assert relerr(Ym, tro) < RTOL_TRAJ
+    assert relerr(LL, LLo) < RTOL_LLH
+
+
+def test_loglik_epilogue_in_isolation(gpu, gold):
+    """Oracle likelihood of the KERNEL's own trajectory: isolates the fused epilogue (<=1e-13)."""
+    import gync_oracle as o
+    datas = [gold["data"][:, :, m] for m in range(4)]
+    LL, st, Ym = gpu.loglik_matrix(gold["X"][:8], datas, [0.1, 0.2, 0.05, 0.1], want_traj=True)
+    for i in range(8):
+        for m, s in enumerate([0.1, 0.2, 0.05, 0.1]):
+            ref = o.llh_from_traj(Ym[i], datas[m], s)
+            assert abs(LL[i, m] - ref) <= 1e-13 * abs(ref)
+
+
+def test_loglik_edge_cases(gpu, gold):
+    x = gold["X"][:3].copy()
+    nanpat = np.full((31, 4), np.nan)
+    LL, st = gpu.loglik_matrix(x, [nanpat, gold["data"][:, :, 0]], [0.1, 0.1])
+    assert np.all(LL[:, 0] == -np.inf) and np.all(np.isfinite(LL[:, 1]))        # all-missing table (model.jl:161)
+    x[1, 115] = np.nan
+    x[2, 85] = -1.0      # LH_R(0) < 0: negative base of the real power
+    LL, st = gpu.loglik_matrix(x, [gold["data"][:, :, 0]], [0.1])
+    assert st[0] == 0 and st[1] == 4 and st[2] != 0 and LL[1, 0] == -np.inf and LL[2, 0] == -np.inf
+    # empty batch
+    LL, st = gpu.loglik_matrix(np.empty((0, 116)), [gold["data"][:, :, 0]], [0.1])
+    assert LL.shape == (0, 1)
+    # step budget exhaustion is a per-sample status, not an error
+    lib = gpu.lib.load()
+    X = gpu.lib.fcol(gold["X"][:2])
+    D = np.asfortranarray(gold["data"][:, :, :1])
+    out = np.empty((2, 1), order="F")
+    stt = np.zeros(2, dtype=np.int32)
+    o_ = gpu.lib.opts(1e-8, 1e-8, max_steps=50)
+    gpu.lib.check(lib.gync_loglik_batch(gpu.lib.dptr(X), 2, gpu.lib.dptr(D), 1, gpu.lib.dptr(np.array([0.1])), C.byref(o_),
+                                        gpu.lib.dptr(out), None, stt.ctypes.data_as(gpu.lib.c_int32_p), None))
+    assert np.all(stt == 1) and np.all(out == -np.inf)
+    # bad arguments -> error code + message, no exception across the ABI
+    rc = lib.gync_loglik_batch(None, 5, None, 1, None, None, None, None, None, None)
+    assert rc == -1 and b"bad arguments" in lib.gync_last_error()
+
+
+def test_api_llh_config_and_sampling(gpu, gold):
+    c = gpu.Config()
+    x0 = gpu.api.init(c)
+    l = gpu.llh(c, x0)
+    assert abs(l - gold["LL"][0, 0]) <= RTOL_LLH * abs(l)
+    s = gpu.Sampling(gold["X"][:5], c, None)
+    assert relerr(gpu.llh(s), gold["LL"][:5, 0]) < RTOL_LLH                       # llh(s::Sampling), sampling.jl:32
+
+
+def test_gync_and_forwardsol_generic_grid(gpu, gold):
+    import c_oracle as co
+    import gync_oracle as o
+    t = np.arange(0.0, 31.0)
+    Y = gpu.gync(o.REFY0, o.allparms(o.REFPARMS), t)
+    ref = co.gync(o.REFY0, o.allparms(o.REFPARMS), t, mode=1, rtol=1e-11, atol=1e-11)
+    big = np.abs(ref) > 1e-6 * np.abs(ref).max(0)
+    assert np.array_equal(Y[0], o.REFY0)                       # t[0] is the initial time (cvode semantics)
+    assert np.max(np.abs(Y - ref)[big] / np.abs(ref)[big]) < RTOL_TRAJ
+    Yf = gpu.forwardsol(gold["X"][:4], np.array([1.0, 2.5, 2.5, 17.0, 40.0]))
+    for i in range(4):
+        parms, y0, _ = o.split(gold["X"][i])
+        ref = co.gync(y0, o.allparms(parms), np.array([1.0, 2.5, 17.0, 40.0]), mode=1, rtol=1e-11, atol=1e-11)
+        got = Yf[i][[0, 1, 3, 4]][:, o.MEASUREDINDS]
+        assert relerr(got, ref[:, o.MEASUREDINDS]) < RTOL_TRAJ
+        assert np.array_equal(Yf[i][1], Yf[i][2])
+    assert relerr(gpu.referencesolution()[:, o.MEASUREDINDS], gold["refsol"][:, o.MEASUREDINDS]) < RTOL_TRAJ
+    bad = np.flatnonzero(~np.isfinite(gold["LL"][:, 0]))[0]
+    assert np.isnan(gpu.forwardsol(gold["X"][bad])).all()      # failure -> NaN matrix
+
+
+def test_full_size_properties(gpu, gold):
+    """cfg 2 size (1e5 samples): order-invariance (bit-exact: persistent lanes must not change any
+    sample's arithmetic), M-consistency, finite fraction."""
+    N = 100_000
+    X = near_set(N, 20160913)
+    data = gold["data"][:, :, 0]
+    LL1, st1 = gpu.loglik_matrix(X, [data], [0.1])
+    assert (st1 == 0).mean() > 0.999
+    perm = np.random.default_rng(5).permutation(N)
+    LL2, st2 = gpu.loglik_matrix(X[perm], [data], [0.1])
+    assert np.array_equal(LL2[:, 0], LL1[perm, 0]) and np.array_equal(st2, st1[perm])
+    sub = slice(0, 4096)
+    datas = [gold["data"][:, :, m] for m in range(4)]
+    LL4, _ = gpu.loglik_matrix(X[sub], datas, [0.1] * 4)
+    assert np.array_equal(LL4[:, 0], LL1[sub, 0])              # column m is independent of the other patients
+    import c_oracle as co
+    pick = np.random.default_rng(6).choice(N, 16, replace=False)
+    LLo = co.llh_batch(X[pick], [data], [0.1], 1, 1e-11, 1e-11)
+    assert relerr(LL1[pick], LLo) < RTOL_LLH
+
+
+# ---------------------------------------------------------------------------------------- K2
+def test_logprior_vs_golden(gpu, gold):
+    c = gpu.Config(priory0=gpu.api.GaussianMixture(gold["gmm_means"], gold["gmm_stds"]))
+    lp = gpu.logprior(c, gold["X"])
+    f = np.isfinite(gold["logprior"])
+    assert np.array_equal(np.isfinite(lp), f)
+    assert relerr(lp[f], gold["logprior"][f]) < 1e-12
+    x = gold["X"][0].copy()
+    x[3] = 5.0001 * gpu.api.refparms[3]
+    assert gpu.logprior(c, x) == -np.inf
+    # the default prior is built from the device's own converged reference solution
+    c2 = gpu.Config()
+    assert abs(gpu.logprior(c2, gold["X"][0]) - gold["logprior"][0]) < 1e-6 * abs(gold["logprior"][0])
+
+
+# ---------------------------------------------------------------------------------------- K4
+def test_em_vs_golden_and_oracle(gpu, gold):
+    import gync_oracle as o
+    L = gold["em_L"]
+    K, M = L.shape
+    w = np.full(K, 1.0 / K)
+    gpu.emiteration_bang(w, L, niter=1)
+    assert relerr(w, gold["em_w1"]) < RTOL_EM
+    gpu.emiteration_bang(w, L, niter=9)
+    assert relerr(w, gold["em_w10"]) < RTOL_EM
+    gpu.emiteration_bang(w, L, niter=90)
+    assert relerr(w, gold["em_w100"]) < RTOL_EM
+    ws = gpu.emiterations(np.full(K, 1.0 / K), L, 11)                       # em.jl:5: w0 first
+    assert len(ws) == 11 and relerr(ws[1], gold["em_w1"]) < RTOL_EM and relerr(ws[10], gold["em_w10"]) < RTOL_EM
+    rng = np.random.default_rng(2)
+    for K, M in ((1, 1), (7, 3), (257, 8), (1000, 17), (5000, 40), (3001, 64), (70001, 33)):
+        L = rng.random((K, M)) ** 4
+        w0 = rng.random(K)
+        ref = w0.copy()
+        for _ in range(3):
+            ref = o.emiteration(ref, L)
+        got = gpu.emiteration_bang(w0.copy(), L, niter=3)
+        assert relerr(got, ref) < RTOL_EM, (K, M)
+    wc = gpu.WeightedChain(rng.random((100, 3)), rng.random((100, 5)), rng.random(100))    # test/priorestimation.jl:6-7
+    before = wc.weights.copy()
+    gpu.emiteration_bang(wc)
+    assert relerr(wc.weights, o.emiteration(before, wc.likelihoods)) < RTOL_EM
+
+
+def test_em_edge_and_full_size(gpu):
+    rng = np.random.default_rng(3)
+    # zero rows (samples whose likelihood underflowed) stay exactly zero; Inf/NaN propagate like the reference
+    L = rng.random((1000, 5))
+    L[17] = 0.0
+    w = gpu.emiteration_bang(np.full(1000, 1e-3), L, niter=4)
+    assert w[17] == 0.0 and abs(w.sum() - 1) < 1e-12
+    L[:, 2] = 0.0                                                # norms[m] == 0 -> 0/0 (em.jl has no guard)
+    assert np.isnan(gpu.emiteration_bang(np.full(1000, 1e-3), L)).all()
+    with pytest.raises(ValueError):
+        gpu.emiteration_bang(np.ones(3), np.ones((4, 2)))
+    # cfg 5 size on one GPU: K = 1e6 x 40; properties (iii) sum w = 1, (iv) equal rows -> w/sum(w)
+    K, M = 1_000_000, 40
+    L = rng.random((K, M))
+    w = gpu.emiteration_bang(rng.random(K), L)
+    assert abs(w.sum() - 1) < 1e-11
+    Le = np.tile(rng.random((1, M)), (K, 1))
+    w0 = rng.random(K)
+    assert relerr(gpu.emiteration_bang(w0.copy(), Le), w0 / w0.sum()) < 1e-11
+
+
+def test_em_sharded_step_kernels(gpu):
+    """The kernels behind the multi-GPU path (norms / step with external denominators), emulated
+    on one device as two shards with the 'allreduce' done on the host."""
+    import torch
+    import gync_oracle as o
+    from gync_b200.dist import DeviceEM, shard_bounds, em_iterate_sharded
+    rng = np.random.default_rng(4)
+    K, M, niter = 20011, 40, 6
+    L = rng.random((K, M))
+    L /= L.sum(0, keepdims=True)
+    w0 = np.full(K, 1.0 / K)
+    shards = []
+    for r in range(2):
+        lo, hi = shard_bounds(K, 2, r)
+        shards.append(DeviceEM(torch.from_numpy(w0[lo:hi].copy()).cuda(),
+                               torch.from_numpy(np.ascontiguousarray(L[lo:hi].T)).cuda()))
+    norms = shards[0].norms() + shards[1].norms()
+    for _ in range(niter):
+        norms = shards[0].step(norms) + shards[1].step(norms)
+    ref = w0.copy()
+    for _ in range(niter):
+        ref = o.emiteration(ref, L)
+    got = np.concatenate([s.w.cpu().numpy() for s in shards])
+    assert relerr(got, ref) < RTOL_EM
+
+
+# ---------------------------------------------------------------------------------------- K3 / K5
+def test_mcmc_step_with_injected_randomness(gpu, gold):
+    """Deterministic parity of the Metropolis step: same normals/uniforms into the
+    oracle's step function (logf through the converged C oracle) and into the kernel."""
+    import c_oracle as co
+    import gync_oracle as o
+    lib, L = gpu.lib.load(), gpu.lib
+    c = gpu.Config(priory0=gpu.api.GaussianMixture(gold["gmm_means"], gold["gmm_stds"]))
+    Cn, iters = 4, 5
+    rng = np.random.default_rng(8)
+    z = rng.standard_normal((iters, 116, Cn))
+    u = rng.random((iters, Cn))
+    u[1] = 1e-300                      # force an accept
+    u[3] = 1.0                         # force a reject
+    datas = [gold["data"][:, :, m] for m in range(4)]
+    sd = np.sqrt(np.log(1.01))
+    chol = np.linalg.cholesky(np.eye(116) * np.log(1.01) + 1e-4 * np.ones((116, 116)))     # dense proposal for chain test
+
+    def logf(xl, m):
+        x = np.exp(xl)
+        lp = o.logprior(x, gold["gmm_means"], gold["gmm_stds"])
+        if lp == -np.inf:
+            return lp
+        return lp + co.llh_batch(x[None, :], [datas[m]], [0.1], 1, 1e-11, 1e-11)[0, 0] + xl.sum()
+
+    for use_chol in (False, True):
+        state = L.fcol(np.tile(np.log(o.init_x()), (Cn, 1)))
+        lf = np.full(Cn, np.nan)
+        out = np.empty((iters, 116, Cn), order="F")
+        nacc = np.zeros(Cn, dtype=np.int64)
+        pr = c.prior()
+        op = L.opts(1e-9, 1e-9)
+        D = np.asfortranarray(gold["data"])
+        sig = np.full(4, 0.1)
+        pat = np.arange(Cn, dtype=np.int32)
+        L.check(lib.gync_mcmc_run(L.dptr(state), L.dptr(lf), Cn, L.dptr(L.fcol(chol)) if use_chol else None,
+                                  0.0 if use_chol else sd, L.dptr(D), 4, L.dptr(sig), pat.ctypes.data_as(L.c_int32_p),
+                                  C.byref(pr), C.byref(op), iters, 1, 0, 0, L.dptr(np.asfortranarray(z)),
+                                  L.dptr(np.asfortranarray(u)), L.dptr(out), nacc.ctypes.data_as(L.c_int64_p)))
+        for cidx in range(Cn):
+            xs = np.log(o.init_x())
+            cur = logf(xs, cidx)
+            acc = 0
+            SL = chol if use_chol else np.eye(116) * sd
+            for it in range(iters):
+                xs, cur, a = o.metropolis_step(xs, cur, SL, z[it, :, cidx], u[it, cidx], lambda v: logf(v, cidx))
+                acc += a
+                assert relerr(out[it, :, cidx], np.exp(xs)) < 1e-12          # rows are exp(state) (sampling.jl:74)
+            assert acc == nacc[cidx] and acc >= 1
+            assert abs(lf[cidx] - cur) <= 1e-8 * abs(cur)
+            assert np.allclose(state[cidx], xs, rtol=0, atol=1e-13)
+
+
+def test_sample_api_shapes_and_reproducibility(gpu):
+    c = gpu.Config(gpu.Lausanne(1), thin=2)
+    s = gpu.sample(c, 20, seed=3)
+    assert s.samples.shape == (10, 116)
+    s = gpu.sample_bang(s, 20)
+    assert s.samples.shape == (20, 116)                                         # test/gync.jl:14
+    s2 = gpu.sample_bang(gpu.sample(c, 20, seed=3), 20)
+    assert np.array_equal(s.samples, s2.samples)                                # counter-based RNG: resumable, reproducible
+    assert 0 < s.variate.naccept <= 40 and np.all(s.samples > 0)
+    ss = gpu.sample_chains([gpu.new_sampling(gpu.Config(gpu.Lausanne(i)), seed=1) for i in (1, 2, 3)], 6)
+    assert all(x.samples.shape == (6, 116) for x in ss)
+    assert not np.array_equal(ss[0].samples, ss[1].samples)
+    w = gpu.WeightedChain([s, s])                                               # test/gync.jl:27-29
+    assert w.likelihoods.shape[1] == 2 and abs(w.weights.sum() - 1) < 1e-12
+    assert gpu.sample(w, 10).shape == (10, 116)
+    gpu.emiteration_bang(w)
+
+
+def test_wc_normalize_vs_oracle(gpu):
+    import gync_oracle as o
+    lib, L = gpu.lib.load(), gpu.lib
+    rng = np.random.default_rng(9)
+    for K, M in ((5, 1), (1000, 7), (30011, 40)):
+        LL = np.asfortranarray(-rng.random((K, M)) * 800)
+        LL[rng.integers(K), rng.integers(M)] = -np.inf
+        lp = -rng.random(K) * 50
+        counts = rng.integers(1, 9, K).astype(np.int64)
+        Lm, w, d = np.empty((K, M), order="F"), np.empty(K), np.empty(K)
+        L.check(lib.gync_wc_normalize(L.dptr(LL), L.dptr(lp), counts.ctypes.data_as(L.c_int64_p), K, M, L.dptr(Lm),
+                                      L.dptr(w), L.dptr(d)))
+        l0, w0, d0 = o.weightedchain_normalize(lp, LL, counts)
+        nz = l0 > 0
+        assert np.array_equal(Lm == 0, l0 == 0) and relerr(Lm[nz], l0[nz]) < 1e-12
+        assert relerr(w, w0) < 1e-14 and relerr(d, d0) < 1e-12

@@ -1,0 +1,198 @@
+"""CPU suite, part 2: generated code + solver core compiled for the host (tests/host_shim), the C-ABI
+library's symbol table, and the host-side mirror of the reference API.  No compute call on a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import c_oracle as co
+import gync_oracle as o
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden")
+dp = C.POINTER(C.c_double)
+P = lambda a: a.ctypes.data_as(dp)  # noqa: E731
+
+
+def relerr(a, b):
+    return np.max(np.abs(a - b) / (np.abs(b) + 1e-300))
+
+
+def test_generated_rhs_vs_reference_text(host_shim):
+    g = np.load(os.path.join(G, "rhs_golden.npz"))
+    for y, p, f in zip(g["Y"], g["P"], g["F"]):
+        out = np.empty(33)
+        host_shim.hs_rhs(P(y), P(p), P(out))
+        # reciprocal-threshold form: a few ulp on top of the cancellation already in f
+        assert np.max(np.abs(out - f) / (np.abs(f) + 1e-12 * np.abs(f).max())) < 1e-11
+
+
+def test_generated_jacobian_and_sparse_lu(host_shim):
+    g = np.load(os.path.join(G, "rhs_golden.npz"))
+    rng = np.random.default_rng(0)
+    nq, nlu = C.c_int(), C.c_int()
+    assert host_shim.hs_dims(C.byref(nq), C.byref(nlu)) == 33 and nlu.value == 165
+    for y, p in zip(g["Y"][:24], g["P"][:24]):
+        Jref = np.empty((33, 33))
+        co.lib().orc_jac_exact(P(y), P(p), P(Jref))           # oracle: complex-step Jacobian
+        for fac in (1e5, 400.0, 10.0, 0.5):
+            f = np.empty(33)
+            Wd = np.empty((33, 33))
+            host_shim.hs_rhs_w(P(y), P(p), C.c_double(fac), P(f), P(Wd))
+            Wref = fac * np.eye(33) - Jref
+            assert np.max(np.abs(Wd - Wref) / (np.abs(Wref) + 1e-9 * np.abs(Wref).max())) < 1e-12
+            b = rng.standard_normal(33) * (np.abs(f) + 1e-3)
+            x = b.copy()
+            host_shim.hs_lusolve(P(y), P(p), C.c_double(fac), P(x))     # no-pivot sparse LU (static Markowitz order)
+            xr = np.linalg.solve(Wref, b)
+            assert np.max(np.abs(x - xr)) / np.max(np.abs(xr)) < 1e-10
+
+
+def host_traj(host_shim, x, rtol, atol):
+    tr = np.empty((62, 4))
+    na, nr = C.c_int(), C.c_int()
+    st = host_shim.hs_meas_traj(P(np.ascontiguousarray(x)), C.c_double(rtol), C.c_double(atol), 200000, P(tr),
+                                C.byref(na), C.byref(nr))
+    return st, tr, na.value, nr.value
+
+
+def test_rodas4_solver_core_vs_converged_golden(host_shim):
+    """The device solver's source, compiled for the CPU, against the converged oracle values:
+    trajectories within 1e-6, log-likelihood within 1e-8 relative (north-star tolerances)."""
+    g = np.load(os.path.join(G, "solution_golden.npz"))
+    for i in (0, 1, 2, 9, 34):
+        st, tr, na, nr = host_traj(host_shim, g["X"][i], 1e-8, 1e-8)
+        assert st == 0 and 300 < na < 20000
+        assert relerr(tr, g["traj"][i]) < 1e-6
+        for m in range(4):
+            l = o.llh_from_traj(tr, g["data"][:, :, m], 0.1)
+            assert abs(l - g["LL"][i, m]) <= 1e-8 * abs(g["LL"][i, m]), (i, m, l, g["LL"][i, m])
+
+
+def test_rodas4_failure_status(host_shim):
+    g = np.load(os.path.join(G, "solution_golden.npz"))
+    bad = np.flatnonzero(~np.isfinite(g["LL"][:, 0]))[0]
+    st, tr, _, _ = host_traj(host_shim, g["X"][bad], 1e-8, 1e-8)
+    assert st != 0 and np.isnan(tr).all()
+    x = g["X"][0].copy()
+    x[115] = np.nan
+    st, tr, _, _ = host_traj(host_shim, x, 1e-6, 1e-6)
+    assert st == 4 and np.isnan(tr).all()
+
+
+def test_rodas4_generic_grid_and_order(host_shim):
+    g = np.load(os.path.join(G, "solution_golden.npz"))
+    t = np.arange(0.0, 31.0)
+    Y = np.empty((31, 33))
+    p = o.allparms(o.REFPARMS)
+    st = host_shim.hs_solve(P(o.REFY0), P(p), P(t), 31, C.c_double(1e-9), C.c_double(1e-11), 500000, P(Y))
+    assert st == 0
+    ref = co.gync(o.REFY0, p, t, mode=1, rtol=1e-11, atol=1e-11)
+    big = np.abs(ref) > 1e-6 * np.abs(ref).max(0)
+    assert np.max(np.abs(Y - ref)[big] / np.abs(ref)[big]) < 1e-6
+    assert relerr(o.referencesolution(Y)[:, o.MEASUREDINDS], g["refsol"][:, o.MEASUREDINDS]) < 1e-7
+    # repeated output time is served from the same state (CVODE semantics for a repeated tout)
+    t2 = np.array([0.0, 1.0, 1.0, 2.0])
+    Y2 = np.empty((4, 33))
+    assert host_shim.hs_solve(P(o.REFY0), P(p), P(t2), 4, C.c_double(1e-8), C.c_double(1e-8), 100000, P(Y2)) == 0
+    assert np.array_equal(Y2[1], Y2[2]) and np.array_equal(Y2[0], o.REFY0)
+
+
+def test_philox_known_answers(host_shim):
+    out = (C.c_uint32 * 4)()
+    kat = [((0, 0, 0, 0), 0, (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, 0xffffffffffffffff, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), 0x299f31d0a4093822,
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, exp in kat:      # Random123 kat_vectors, philox4x32-10
+        host_shim.hs_philox(C.c_uint64(key), *ctr, out)
+        assert tuple(out) == exp
+    z = np.empty(116)
+    u = C.c_double()
+    zs = []
+    for it in range(200):
+        host_shim.hs_draw(C.c_uint64(42), C.c_uint64(3), C.c_uint64(it), P(z), C.byref(u))
+        assert 0.0 < u.value < 1.0
+        zs.append(z.copy())
+    zs = np.array(zs)
+    assert abs(zs.mean()) < 0.03 and abs(zs.std() - 1) < 0.03
+
+
+# ---------------------------------------------------------------------------------------- C ABI
+def test_cabi_library_exports_every_declared_symbol(built):
+    from gync_b200 import lib as L
+    hdr = open(os.path.join(ROOT, "include", "gync_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(gync_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared == sorted(L.EXPORTS)
+    lib = L.load()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.gync_abi_version() == 1
+    dims = [C.c_int32() for _ in range(5)]
+    lib.gync_dims(*[C.byref(d) for d in dims])
+    assert [d.value for d in dims] == [33, 114, 116, 93, 165]
+    assert lib.gync_flops_per_step() > 5000
+
+
+def test_no_cpu_fallback(built):
+    """Without a CUDA device every compute call must fail loudly."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import gync_b200 as g
+    with pytest.raises(g.lib.GyncError, match="no CUDA device"):
+        g.llh(g.Config(), g.api.init(g.Config()))
+    with pytest.raises(g.lib.GyncError):
+        g.emiteration(np.ones(4) / 4, np.ones((4, 2)))
+
+
+def test_product_does_not_import_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "gync.jl_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".inl")):
+                src = open(os.path.join(dirpath, f)).read()
+                # no import / load / include of anything under oracle/ from the product tree
+                assert not re.search(r"import\s+(gync_oracle|c_oracle)|from\s+oracle|libgync_oracle|oracle/_build|"
+                                     r"#include\s+\"[^\"]*oracle", src), f
+
+
+# ---------------------------------------------------------------------------------------- host mirror
+def test_api_constants_and_config_defaults(built):
+    import gync_b200 as g
+    api = g.api
+    assert api.sampledinds.size == 82 and np.array_equal(api.sampledinds - 1, o.SAMPLEDINDS)
+    assert np.array_equal(api.allparms(api.refparms), api.refallparms)
+    c = g.Config()
+    assert c.patient.id == "l1" and c.sigma_rho == 0.1 and c.thin == 1 and not c.adapt        # model.jl:51
+    assert np.allclose(c.propvar, np.eye(116) * np.log(1.01)) and np.array_equal(c.priorparms, 5 * api.refparms)
+    assert np.array_equal(api.init(c), o.init_x())
+    assert np.array_equal(np.isnan(g.Lausanne(1).data), np.isnan(o.lausanne(1)))
+    assert (~np.isnan(g.Lausanne(1).data)).sum() == 60
+    assert len(api.alldatas()) == 53                                                           # notebook: 53 pass minmeas=20
+    with pytest.raises(NotImplementedError):
+        g.Config(adapt=True)
+
+
+def test_api_collapse_duplicates_matches_oracle(built):
+    import gync_b200 as g
+    rng = np.random.default_rng(3)
+    S = rng.random((9, 116))
+    S[2] = S[1]
+    S[3] = S[1]
+    S[5] = S[4]
+    c = g.Config()
+    s1 = g.Sampling(S[:5], c, None)
+    s2 = g.Sampling(S[5:], c, None)          # duplicate run continues across the chain boundary (weightedchain.jl:35-45)
+    rows, counts = g.api.collapse_duplicates([s1, s2])
+    r0, c0 = o.collapse_duplicates([S[:5], S[5:]])
+    assert np.array_equal(rows, r0) and np.array_equal(counts, c0)
+
+
+def test_shard_bounds():
+    from gync_b200.dist import shard_bounds
+    for n, w in ((10, 3), (1_000_000, 8), (5, 8)):
+        b = [shard_bounds(n, w, r) for r in range(w)]
+        assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+        assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1

@@ -1,0 +1,27 @@
+// Debug tool: per-phase clock64 attribution of one RODAS4 step (thread 0 of block 0).
+// slots: 0 rhs_w, 1 lu, 2 lusolve (first two only), 3 stage combos (first), 4 rhs (first), 5 everything after
+#define GYNC_PHASE_TIMING
+#include <cstdio>
+#include "gync_kernels.cuh"
+int main() {
+  const int N = 64 * 148;
+  double *X, *LL, *D, *S; double* isc; int* an; unsigned long long* cnt;
+  cudaMallocManaged(&X, sizeof(double) * N * 116); cudaMallocManaged(&LL, sizeof(double) * N);
+  cudaMallocManaged(&D, sizeof(double) * 124); cudaMallocManaged(&S, 8); cudaMallocManaged(&isc, 32); cudaMallocManaged(&an, 4);
+  cudaMallocManaged(&cnt, 8); *cnt = 0;
+  static const double refp[114] = {GYNC_REFALLPARMS_LIST}; static const double refy[33] = {GYNC_REFY0_LIST};
+  static const unsigned char si[82] = {GYNC_SAMPLEDINDS0_LIST};
+  for (int n = 0; n < N; ++n) { for (int k = 0; k < 82; ++k) X[n + (size_t)N * k] = refp[si[k]] * (1.0 + 0.001 * (n % 7));
+    for (int i = 0; i < 33; ++i) X[n + (size_t)N * (82 + i)] = refy[i]; X[n + (size_t)N * 115] = 28.0; }
+  for (int i = 0; i < 124; ++i) D[i] = 1.0; S[0] = 0.1;
+  gync_prep_patients_kernel<<<1, 64>>>(D, S, 1, isc, an);
+  GyncSolverOpts o = {1e-6, 1e-6, 0, 0, 100000};
+  cudaFuncSetAttribute(gync_loglik_kernel<64, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GyncWorkSm<64>::kSmemBytes);
+  gync_loglik_kernel<64, 32><<<148, 64, GyncWorkSm<64>::kSmemBytes>>>(X, N, D, isc, an, 1, o, LL, nullptr, nullptr, nullptr, cnt);
+  cudaError_t e = cudaDeviceSynchronize(); printf("%s LL0=%f\n", cudaGetErrorString(e), LL[0]);
+  long long h[8]; cudaMemcpyFromSymbol(h, gync_phase_clk, sizeof(h));
+  const char* nm[] = {"rhs_w", "lu", "lusolve x6", "yn combos x5", "rhs x5", "e += combos x5", "norm", "outside step"};
+  long long tot = 0; for (int i = 0; i < 7; ++i) tot += h[i];
+  for (int i = 0; i < 7; ++i) printf("%-40s %12lld  %.1f%%\n", nm[i], h[i], 100.0 * h[i] / tot);
+  return 0;
+}
