@@ -227,12 +227,19 @@ int gync_loglik_batch_dev(const double* dX, int64_t N, const double* d_data, int
         dX, N, d_data, iscale, allnan, M, so, dLL, dYmeas, d_status, d_nsteps, counter);                        \
   } while (0)
   switch (g_llk_variant) {   // tuning variants (env GYNC_LLK_VARIANT)
+    default: {               // production: stage vectors in tensor memory, 112 samples per SM
+      if (int rc = prep_solver_kernel(gync_loglik_tm_kernel, GyncWorkTm::kSmemBytes, 128)) return rc;
+      const int64_t want = (N + GYNC_TM_NSLOT - 1) / GYNC_TM_NSLOT;
+      const int nb = (int)std::min<int64_t>(want, (int64_t)g_num_sms);
+      gync_loglik_tm_kernel<<<nb, 128, GyncWorkTm::kSmemBytes, s>>>(dX, N, d_data, iscale, allnan, M, so, dLL, dYmeas,
+                                                                    d_status, d_nsteps, counter);
+    } break;
     case 1: LLK(32, 32); break;
     case 2: LLK(64, 16); break;
     case 3: LLK(64, 8); break;
     case 4: LLK(32, 16); break;
     case 5: LLK(32, 8); break;
-    default: LLK(64, 32); break;
+    case 6: LLK(64, 32); break;   // all-shared-memory layout, 64 samples per SM
   }
 #undef LLK
   CK(cudaFreeAsync(counter, s));

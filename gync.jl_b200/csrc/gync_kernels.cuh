@@ -67,18 +67,14 @@ struct GyncSmView {
 // every SM sub-partition more warps to interleave.
 template <int BLOCK>
 struct GyncWorkSm {
-  GyncSmView<BLOCK> q, k1, k2, k3, k4, k5, A;
+  GyncSmView<BLOCK> q, k, A;
   double y[GYNC_NY], yn[GYNC_NY], e[GYNC_NY];
   static constexpr int kDoublesPerThread = GYNC_NQ + 5 * GYNC_NY + GYNC_NLU;
   static constexpr size_t kSmemBytes = sizeof(double) * kDoublesPerThread * BLOCK;
   __device__ __forceinline__ void bind(double* sm, int slot) {
     double* b = sm + slot;
     q.p = b;  b += GYNC_NQ * BLOCK;
-    k1.p = b; b += GYNC_NY * BLOCK;
-    k2.p = b; b += GYNC_NY * BLOCK;
-    k3.p = b; b += GYNC_NY * BLOCK;
-    k4.p = b; b += GYNC_NY * BLOCK;
-    k5.p = b; b += GYNC_NY * BLOCK;
+    k.p = b;  b += 5 * GYNC_NY * BLOCK;
     A.p = b;
   }
 };
@@ -193,6 +189,270 @@ gync_loglik_kernel(const double* __restrict__ X, int64_t N, const double* __rest
         active = false;
       }
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1, TMEM variant: the five RODAS stage vectors live in TENSOR MEMORY.
+//
+// The solver is bound by per-thread latency and by how many samples an SM can hold, and shared
+// memory caps that at 64 (3.4 KB each).  Blackwell's 256 KB of tensor memory is per-thread
+// addressable scratch in the 32x32b access shape (thread i of warp w <-> TMEM lane 32(w%4)+i,
+// 512 columns x 32 bit each = 256 doubles per thread), with a 12-cycle load latency.  Moving
+// k1..k5 (330 columns) plus a 66-column scratch vector there leaves q + A = 2064 B per sample in
+// shared memory: 112 samples per SM as 4 warps x 28 lanes — one warp per SM sub-partition.
+// tcgen05.ld/st are warp-collective (.sync.aligned), so every lane of a warp executes the step
+// (idle lanes on dummy state, their shared-memory stores predicated off).
+#define GYNC_TM_NSLOT 112
+#define GYNC_TM_LPW 28
+#define GYNC_TM_COL_K 0
+#define GYNC_TM_COL_V (5 * 2 * GYNC_NY)
+
+struct GyncSmRefP {
+  double* p;
+  bool ok;
+  __device__ __forceinline__ operator double() const { return *(volatile double*)p; }
+  __device__ __forceinline__ const GyncSmRefP& operator=(double v) const { if (ok) *p = v; return *this; }
+  __device__ __forceinline__ const GyncSmRefP& operator-=(double v) const { const double t = *(volatile double*)p - v; if (ok) *p = t; return *this; }
+  __device__ __forceinline__ const GyncSmRefP& operator+=(double v) const { const double t = *(volatile double*)p + v; if (ok) *p = t; return *this; }
+};
+template <int NSLOT>
+struct GyncSmViewP {
+  double* p;
+  bool ok;
+  __device__ __forceinline__ GyncSmRefP operator[](int i) const { return GyncSmRefP{p + i * NSLOT, ok}; }
+};
+
+#define TM_R16(r) "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), \
+                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+#define TM_W16(r) "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), \
+                  "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+#define TM_I16(r) "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), \
+                  "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+
+// 8 doubles (16 columns) TMEM -> registers; the wait carries the registers as in/out operands so
+// no consumer can be scheduled ahead of it.
+__device__ __forceinline__ void gync_tm_ld8(uint32_t ta, double (&v)[8]) {
+  uint32_t r[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : TM_R16(r) : "r"(ta));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : TM_W16(r) :: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __hiloint2double((int)r[2 * i + 1], (int)r[2 * i]);
+}
+__device__ __forceinline__ double gync_tm_ld1(uint32_t ta) {
+  uint32_t lo, hi;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(ta));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(lo), "+r"(hi) :: "memory");
+  return __hiloint2double((int)hi, (int)lo);
+}
+__device__ __forceinline__ void gync_tm_st8(uint32_t ta, const double* v) {
+  uint32_t r[16];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { r[2 * i] = (uint32_t)__double2loint(v[i]); r[2 * i + 1] = (uint32_t)__double2hiint(v[i]); }
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};"
+               :: TM_I16(r), "r"(ta) : "memory");
+}
+__device__ __forceinline__ void gync_tm_st1(uint32_t ta, double v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%2], {%0,%1};"
+               :: "r"((uint32_t)__double2loint(v)), "r"((uint32_t)__double2hiint(v)), "r"(ta) : "memory");
+}
+__device__ __forceinline__ void gync_tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// store a 33-vector to TMEM columns [col, col+66)
+__device__ __forceinline__ void gync_tm_store_vec(uint32_t ta, const double* v) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) gync_tm_st8(ta + 16 * c, v + 8 * c);
+  gync_tm_st1(ta + 64, v[32]);
+  gync_tm_wait_st();
+}
+
+struct GyncWorkTm {
+  GyncSmViewP<GYNC_TM_NSLOT> q, A;
+  double y[GYNC_NY], yn[GYNC_NY], e[GYNC_NY];
+  uint32_t tm;   // TMEM address of this warp's lane quadrant, column 0
+  static constexpr size_t kSmemBytes = sizeof(double) * (GYNC_NQ + GYNC_NLU) * GYNC_TM_NSLOT;
+};
+
+// RODAS4 step with k in TMEM (same arithmetic as gync_rodas4_step up to the order of the stage
+// sums).  Each stage reads every earlier k once, producing the stage point (registers) and the
+// correction sum_j c_sj k_j, which is parked in the TMEM scratch vector while the RHS runs.
+__device__ __forceinline__ double gync_rodas4_step_tm(GyncWorkTm& W, const double h, const double rtol, const double atol) {
+  const double ih = GYNC_RCP(h);
+  gync_rhs_w(W.y, W.q, ih * (1.0 / RD_G), W.e, W.A);
+  gync_lu(W.A);
+  gync_lusolve(W.A, W.e);
+#pragma unroll 1
+  for (int s = 0; s < 5; ++s) {
+    gync_tm_store_vec(W.tm + GYNC_TM_COL_K + 2 * GYNC_NY * s, W.e);      // park k_{s+1}
+#pragma unroll
+    for (int i = 0; i < GYNC_NY; ++i) { W.yn[i] = W.y[i]; W.e[i] = 0.0; }
+#pragma unroll 1
+    for (int j = 0; j <= s; ++j) {
+      const double a = RD_TA[s][j], c = RD_TC[s][j];
+      const uint32_t ta = W.tm + GYNC_TM_COL_K + 2 * GYNC_NY * j;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        double k[8];
+        gync_tm_ld8(ta + 16 * ch, k);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { W.yn[8 * ch + i] = fma(a, k[i], W.yn[8 * ch + i]); W.e[8 * ch + i] = fma(c, k[i], W.e[8 * ch + i]); }
+      }
+      const double k32 = gync_tm_ld1(ta + 64);
+      W.yn[32] = fma(a, k32, W.yn[32]);
+      W.e[32] = fma(c, k32, W.e[32]);
+    }
+    gync_tm_store_vec(W.tm + GYNC_TM_COL_V, W.e);                          // park the correction
+    gync_rhs(W.yn, W.q, W.e);
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      double v[8];
+      gync_tm_ld8(W.tm + GYNC_TM_COL_V + 16 * ch, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) W.e[8 * ch + i] = fma(ih, v[i], W.e[8 * ch + i]);
+    }
+    W.e[32] = fma(ih, gync_tm_ld1(W.tm + GYNC_TM_COL_V + 64), W.e[32]);
+    gync_lusolve(W.A, W.e);
+  }
+  double sum = 0.0;
+#pragma unroll
+  for (int i = 0; i < GYNC_NY; ++i) {
+    W.yn[i] += W.e[i];
+    const double sc = atol + rtol * fmax(fabs(W.y[i]), fabs(W.yn[i]));
+    const double r = W.e[i] * GYNC_RCP(sc);
+    sum = fma(r, r, sum);
+  }
+  return sqrt(sum * (1.0 / GYNC_NY));
+}
+
+__global__ void __launch_bounds__(128, 1)
+gync_loglik_tm_kernel(const double* __restrict__ X, int64_t N, const double* __restrict__ data,
+                      const double* __restrict__ iscale, const int* __restrict__ allnan, int M,
+                      GyncSolverOpts o, double* __restrict__ LL, double* __restrict__ Ymeas,
+                      int* __restrict__ status, int* __restrict__ nsteps, unsigned long long* __restrict__ counter) {
+  extern __shared__ double gync_sm[];
+  __shared__ uint32_t s_tmem;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;"
+                 :: "r"((uint32_t)__cvta_generic_to_shared(&s_tmem)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = s_tmem;
+
+  const bool real = lane < GYNC_TM_LPW;                    // lanes 28..31 only keep the warp converged
+  GyncWorkTm W;
+  const int slot = warp * GYNC_TM_LPW + (real ? lane : GYNC_TM_LPW - 1);
+  W.q.p = gync_sm + slot;  W.q.ok = real;
+  W.A.p = gync_sm + (size_t)GYNC_NQ * GYNC_TM_NSLOT + slot;  W.A.ok = real;
+  W.tm = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+  for (int i = 0; i < GYNC_NY; ++i) { W.y[i] = 1.0; W.yn[i] = 1.0; W.e[i] = 0.0; }
+
+  const double big = 1.0e300, ninf = -INFINITY;
+  bool active = false, done = !real;
+  int64_t n = 0;
+  double T = 0.0, t = 0.0, tn = 0.0;
+  int i0 = 0, i1 = 0, budget = 0, st = GYNC_ST_OK;
+  GyncCtrl c;
+  gync_ctrl_init(c, 1e-3);
+  GyncLlhSink sink = {data, iscale, M, N, nullptr, nullptr};
+  if (!real) {   // benign dummy parameters (never stored: read-only alias of a real slot is fine)
+  }
+  for (;;) {
+    if (!active && !done) {
+      n = (int64_t)atomicAdd(counter, 1ull);
+      if (n >= N) {
+        done = true;
+      } else {
+        gync_load_sample(W, [&](int k) { return __ldg(X + n + N * k); }, c_refallparms, c_sampledinds, &T);
+        for (int m = 0; m < M; ++m) LL[n + N * m] = 0.0;
+        sink.acc = LL + n;
+        sink.ymeas = Ymeas ? Ymeas + n : nullptr;
+        i0 = i1 = 0;
+        budget = o.max_steps;
+        t = fmin(1.0, 1.0 + T);
+        tn = t;
+        st = (gync_all_finite(W.y, GYNC_NY) && gync_all_finite(W.q, GYNC_NQ) && (T * 0.0 == 0.0)) ? GYNC_ST_OK
+                                                                                                 : GYNC_ST_NONFINITE;
+        gync_ctrl_init(c, (st == GYNC_ST_OK) ? ((o.h0 > 0.0) ? o.h0 : gync_initial_step(W, o.rtol, o.atol)) : 1.0);
+        active = true;
+        // serve the measurement times equal to the start time
+        if (st == GYNC_ST_OK) {
+          for (;;) {
+            const double tA = (i0 < GYNC_NDAYS) ? (double)(i0 + 1) : big;
+            const double tB = (i1 < GYNC_NDAYS) ? (double)(i1 + 1) + T : big;
+            tn = fmin(tA, tB);
+            if (tn > t) break;
+            if (tA == tn) { sink(0, i0, W.y); ++i0; }
+            if (tB == tn) { sink(1, i1, W.y); ++i1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (__all_sync(0xffffffffu, done)) break;
+    // ---- one step attempt, executed by ALL lanes of the warp (TMEM ops are warp-collective)
+    const bool stepping = active && st == GYNC_ST_OK && tn > t;
+    double h = c.h;
+    if (o.hmax > 0.0) h = fmin(h, o.hmax);
+    const double rem = tn - t;
+    const bool last = stepping && (h * 1.0001 >= rem);
+    if (last) h = rem;
+    if (!stepping || !(h > 0.0)) h = 1.0;                  // dummy lanes: any finite positive step
+    const double hprop = c.h;
+    const double err = gync_rodas4_step_tm(W, h, o.rtol, o.atol);
+    __syncwarp();
+    if (stepping) {
+      if (budget-- <= 0) {
+        st = GYNC_ST_MAXSTEPS;
+      } else if (!(h > 1e-14 * fmax(1.0, fabs(t)))) {
+        st = GYNC_ST_HMIN;
+      } else {
+        const bool fin = gync_all_finite(W.yn, GYNC_NY);
+        if (gync_ctrl_update(c, h, err, fin)) {
+          t = last ? tn : t + h;
+#pragma unroll
+          for (int i = 0; i < GYNC_NY; ++i) W.y[i] = W.yn[i];
+          if (last && h < hprop) c.h = fmax(c.h, hprop);
+        }
+      }
+    }
+    if (active) {
+      bool finished = (st != GYNC_ST_OK);
+      if (!finished && t >= tn) {
+        for (;;) {
+          const double tA = (i0 < GYNC_NDAYS) ? (double)(i0 + 1) : big;
+          const double tB = (i1 < GYNC_NDAYS) ? (double)(i1 + 1) + T : big;
+          tn = fmin(tA, tB);
+          if (tn > t) break;
+          if (tA == tn) { sink(0, i0, W.y); ++i0; }
+          if (tB == tn) { sink(1, i1, W.y); ++i1; }
+        }
+        if (i0 >= GYNC_NDAYS && i1 >= GYNC_NDAYS) finished = true;
+      }
+      if (finished) {
+        for (int m = 0; m < M; ++m) {
+          const double a = LL[n + N * m];
+          LL[n + N * m] = (st != GYNC_ST_OK || allnan[m]) ? ninf : -0.5 * a;
+        }
+        if (st != GYNC_ST_OK && Ymeas)
+          for (int k = 0; k < GYNC_NT_MEAS * GYNC_NMEAS; ++k) Ymeas[n + N * k] = NAN;
+        if (status) status[n] = st;
+        if (nsteps) { nsteps[n] = c.nacc; nsteps[n + N] = c.nrej; }
+        active = false;
+        // keep the dummy state benign for the lock-step iterations that may follow
+#pragma unroll
+        for (int i = 0; i < GYNC_NY; ++i) if (!(W.y[i] * 0.0 == 0.0)) W.y[i] = 1.0;
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem_base) : "memory");
   }
 }
 

@@ -92,19 +92,15 @@ struct GyncStepStats {   // per-sample work counters (roofline bookkeeping, SURV
 #define RD_C64 0.1631930543123136e2
 #define RD_C65 (-0.6058818238834054e1)
 
-struct GyncWork {
+struct GyncWork {          // host layout (tests); the device layout is GyncWorkSm in gync_kernels.cuh
   double q[GYNC_NQ];
   double y[GYNC_NY];
   double yn[GYNC_NY];
-  double k1[GYNC_NY], k2[GYNC_NY], k3[GYNC_NY], k4[GYNC_NY], k5[GYNC_NY], e[GYNC_NY];
+  double k[5 * GYNC_NY];    // stage vectors k1..k5
+  double e[GYNC_NY];
   double A[GYNC_NLU];
 };
 
-// One step attempt of size h from W.y; on return W.yn = y(t+h) candidate, returns the scaled
-// error norm (RMS over the 33 species of e_i / (atol + rtol*max(|y_i|,|yn_i|))).
-// Storage: W.q, W.A, W.k1..k5 may be shared-memory views (every read a real load, so each value
-// is read once per use); W.y, W.yn and the work vector W.e are per-thread registers.  Each stage
-// is evaluated into W.e, solved there, and then parked in its k-slot.
 #if defined(GYNC_PHASE_TIMING) && defined(__CUDACC__)
 __device__ long long gync_phase_clk[8];
 #endif
@@ -116,6 +112,31 @@ __device__ long long gync_phase_clk[8];
 #  define GYNC_TICK_INIT
 #endif
 
+// RODAS4 stage tables.  Row s (0-based) serves stage s+2: y_stage = y + sum_j RD_TA[s][j] k_{j+1},
+// rhs += (1/h) sum_j RD_TC[s][j] k_{j+1}, j <= s.  Stage 6 starts from the embedded solution
+// y + a51 k1 + .. + a54 k4 + k5, hence the last row of RD_TA.
+#ifdef __CUDA_ARCH__
+#  define GYNC_TABLE __constant__
+#else
+#  define GYNC_TABLE static const
+#endif
+GYNC_TABLE double RD_TA[5][5] = {{RD_A21, 0, 0, 0, 0},
+                                 {RD_A31, RD_A32, 0, 0, 0},
+                                 {RD_A41, RD_A42, RD_A43, 0, 0},
+                                 {RD_A51, RD_A52, RD_A53, RD_A54, 0},
+                                 {RD_A51, RD_A52, RD_A53, RD_A54, 1.0}};
+GYNC_TABLE double RD_TC[5][5] = {{RD_C21, 0, 0, 0, 0},
+                                 {RD_C31, RD_C32, 0, 0, 0},
+                                 {RD_C41, RD_C42, RD_C43, 0, 0},
+                                 {RD_C51, RD_C52, RD_C53, RD_C54, 0},
+                                 {RD_C61, RD_C62, RD_C63, RD_C64, RD_C65}};
+
+// One step attempt of size h from W.y; on return W.yn = y(t+h) candidate, returns the scaled
+// error norm (RMS over the 33 species of e_i / (atol + rtol*max(|y_i|,|yn_i|))).
+// Storage: W.q, W.A, W.k may be shared-memory views (every read a real load); W.y, W.yn and the
+// work vector W.e are per-thread registers.  Stages 2..6 run as a ROLLED loop: the straight-line
+// RHS + triangular solve are ~2.5 k instructions; unrolled five times the step body is ~190 KB of
+// SASS and the warps stall on instruction fetch (ncu: stall_no_instruction ~30 %).
 template <class WK>
 GYNC_HD static double gync_rodas4_step(WK& W, const double h, const double rtol, const double atol) {
   const double ih = GYNC_RCP(h);
@@ -126,76 +147,40 @@ GYNC_HD static double gync_rodas4_step(WK& W, const double h, const double rtol,
   GYNC_TICK(1)
   gync_lusolve(W.A, W.e);
   GYNC_TICK(2)
+#pragma unroll 1
+  for (int s = 0; s < 5; ++s) {
+    // park k_{s+1}; build the stage point
 #pragma unroll
-  for (int i = 0; i < GYNC_NY; ++i) { const double k1 = W.e[i]; W.k1[i] = k1; W.yn[i] = W.y[i] + RD_A21 * k1; }
-  GYNC_TICK(3)
-  gync_rhs(W.yn, W.q, W.e);
-  GYNC_TICK(4)
+    for (int i = 0; i < GYNC_NY; ++i) { W.k[s * GYNC_NY + i] = W.e[i]; W.yn[i] = W.y[i]; }
+#pragma unroll 1
+    for (int j = 0; j <= s; ++j) {
+      const double a = RD_TA[s][j];
 #pragma unroll
-  for (int i = 0; i < GYNC_NY; ++i) W.e[i] += (RD_C21 * ih) * W.k1[i];
-  GYNC_TICK(5)
-  gync_lusolve(W.A, W.e);
-  GYNC_TICK(2)
+      for (int i = 0; i < GYNC_NY; ++i) W.yn[i] = fma(a, (double)W.k[j * GYNC_NY + i], W.yn[i]);
+    }
+    GYNC_TICK(3)
+    gync_rhs(W.yn, W.q, W.e);
+    GYNC_TICK(4)
+#pragma unroll 1
+    for (int j = 0; j <= s; ++j) {
+      const double c = RD_TC[s][j] * ih;
 #pragma unroll
-  for (int i = 0; i < GYNC_NY; ++i) { const double k2 = W.e[i]; W.k2[i] = k2; W.yn[i] = W.y[i] + RD_A31 * W.k1[i] + RD_A32 * k2; }
-  GYNC_TICK(3)
-  gync_rhs(W.yn, W.q, W.e);
-  GYNC_TICK(4)
-#pragma unroll
-  for (int i = 0; i < GYNC_NY; ++i) W.e[i] += ih * (RD_C31 * W.k1[i] + RD_C32 * W.k2[i]);
-  GYNC_TICK(5)
-  gync_lusolve(W.A, W.e);
-  GYNC_TICK(2)
-#pragma unroll
-  for (int i = 0; i < GYNC_NY; ++i) {
-    const double k3 = W.e[i];
-    W.k3[i] = k3;
-    W.yn[i] = W.y[i] + RD_A41 * W.k1[i] + RD_A42 * W.k2[i] + RD_A43 * k3;
+      for (int i = 0; i < GYNC_NY; ++i) W.e[i] = fma(c, (double)W.k[j * GYNC_NY + i], W.e[i]);
+    }
+    GYNC_TICK(5)
+    gync_lusolve(W.A, W.e);
+    GYNC_TICK(2)
   }
-  GYNC_TICK(3)
-  gync_rhs(W.yn, W.q, W.e);
-  GYNC_TICK(4)
-#pragma unroll
-  for (int i = 0; i < GYNC_NY; ++i) W.e[i] += ih * (RD_C41 * W.k1[i] + RD_C42 * W.k2[i] + RD_C43 * W.k3[i]);
-  GYNC_TICK(5)
-  gync_lusolve(W.A, W.e);
-  GYNC_TICK(2)
-#pragma unroll
-  for (int i = 0; i < GYNC_NY; ++i) {
-    const double k4 = W.e[i];
-    W.k4[i] = k4;
-    W.yn[i] = W.y[i] + RD_A51 * W.k1[i] + RD_A52 * W.k2[i] + RD_A53 * W.k3[i] + RD_A54 * k4;
-  }
-  GYNC_TICK(3)
-  gync_rhs(W.yn, W.q, W.e);
-  GYNC_TICK(4)
-#pragma unroll
-  for (int i = 0; i < GYNC_NY; ++i)
-    W.e[i] += ih * (RD_C51 * W.k1[i] + RD_C52 * W.k2[i] + RD_C53 * W.k3[i] + RD_C54 * W.k4[i]);
-  GYNC_TICK(5)
-  gync_lusolve(W.A, W.e);
-  GYNC_TICK(2)
-#pragma unroll
-  for (int i = 0; i < GYNC_NY; ++i) { const double k5 = W.e[i]; W.k5[i] = k5; W.yn[i] += k5; }
-  GYNC_TICK(3)
-  gync_rhs(W.yn, W.q, W.e);
-  GYNC_TICK(4)
-#pragma unroll
-  for (int i = 0; i < GYNC_NY; ++i)
-    W.e[i] += ih * (RD_C61 * W.k1[i] + RD_C62 * W.k2[i] + RD_C63 * W.k3[i] + RD_C64 * W.k4[i] + RD_C65 * W.k5[i]);
-  GYNC_TICK(5)
-  gync_lusolve(W.A, W.e);
-  GYNC_TICK(2)
-  double s = 0.0;
+  double sum = 0.0;
 #pragma unroll
   for (int i = 0; i < GYNC_NY; ++i) {
     W.yn[i] += W.e[i];
     const double sc = atol + rtol * fmax(fabs(W.y[i]), fabs(W.yn[i]));
     const double r = W.e[i] * GYNC_RCP(sc);
-    s += r * r;
+    sum = fma(r, r, sum);
   }
   GYNC_TICK(6)
-  return sqrt(s * (1.0 / GYNC_NY));
+  return sqrt(sum * (1.0 / GYNC_NY));
 }
 
 // Step-size controller state (Hairer's RODAS controller with Gustafsson's predictive term).
