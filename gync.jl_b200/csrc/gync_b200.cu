@@ -73,76 +73,75 @@ extern "C" int gync_init(int device);
 // EM launch helpers (templates: outside extern "C")
 namespace {
 
-template <int MT>
+template <int MH, bool FULL>
 int em_persistent_launch(double* dw, const double* dL, int64_t K, int M, int niter, double* d_hist, cudaStream_t s) {
   int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gync_em_persistent_kernel<MT>, GYNC_EM_THREADS, 0));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gync_em_persistent_kernel<MH, FULL>, GYNC_EM_THREADS, 0));
   if (per_sm < 1) return fail(GYNC_ERR_CUDA, "EM kernel does not fit on an SM");
-  int64_t want = (K + GYNC_EM_THREADS - 1) / GYNC_EM_THREADS;
+  const int64_t rows_per_block = GYNC_EM_WARPS * 16;
+  int64_t want = (K + rows_per_block - 1) / rows_per_block;
   int nb = (int)std::min<int64_t>((int64_t)g_num_sms * per_sm, std::max<int64_t>(want, 1));
   double* partials = nullptr;
-  CK(cudaMallocAsync((void**)&partials, sizeof(double) * 2 * nb * MT, s));
+  CK(cudaMallocAsync((void**)&partials, sizeof(double) * 2 * nb * 2 * MH, s));
   void* args[] = {&dw, &dL, &K, &M, &niter, &partials, &d_hist};
-  CK(cudaLaunchCooperativeKernel((void*)gync_em_persistent_kernel<MT>, dim3(nb), dim3(GYNC_EM_THREADS), args, 0, s));
+  CK(cudaLaunchCooperativeKernel((void*)gync_em_persistent_kernel<MH, FULL>, dim3(nb), dim3(GYNC_EM_THREADS), args, 0, s));
   g_launches += 1;
   CK(cudaFreeAsync(partials, s));
   return GYNC_OK;
 }
 
-struct EmScratch {   // per-stream scratch for the sharded step kernels
+struct EmScratch {   // scratch for the sharded step kernels
   double* partials = nullptr;
-  int nb = 0, MT = 0;
+  size_t doubles = 0;
 } g_em_scratch;
 
-template <int MT>
 int em_grid(int64_t K) {
-  int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gync_em_step_kernel<MT>, GYNC_EM_THREADS, 0);
-  if (per_sm < 1) per_sm = 1;
-  int64_t want = (K + GYNC_EM_THREADS - 1) / GYNC_EM_THREADS;
-  return (int)std::min<int64_t>((int64_t)g_num_sms * per_sm, std::max<int64_t>(want, 1));
+  const int64_t rows_per_block = GYNC_EM_WARPS * 16;
+  int64_t want = (K + rows_per_block - 1) / rows_per_block;
+  return (int)std::min<int64_t>((int64_t)g_num_sms, std::max<int64_t>(want, 1));
 }
 
-int em_scratch(int nb, int MT) {
-  if (g_em_scratch.partials && g_em_scratch.nb >= nb && g_em_scratch.MT == MT) return GYNC_OK;
+int em_scratch(size_t doubles) {
+  if (g_em_scratch.partials && g_em_scratch.doubles >= doubles) return GYNC_OK;
   if (g_em_scratch.partials) cudaFree(g_em_scratch.partials);
   g_em_scratch.partials = nullptr;
-  CK(cudaMalloc((void**)&g_em_scratch.partials, sizeof(double) * nb * MT));
-  g_em_scratch.nb = nb;
-  g_em_scratch.MT = MT;
+  CK(cudaMalloc((void**)&g_em_scratch.partials, sizeof(double) * doubles));
+  g_em_scratch.doubles = doubles;
   return GYNC_OK;
 }
 
-template <int MT>
+template <int MH, bool FULL>
 int em_norms_launch(const double* dw, const double* dL, int64_t K, int M, double* d_out, cudaStream_t s) {
-  const int nb = em_grid<MT>(K);
-  if (int rc = em_scratch(nb, MT)) return rc;
-  gync_em_norms_kernel<MT><<<nb, GYNC_EM_THREADS, 0, s>>>(dw, dL, K, M, g_em_scratch.partials);
-  gync_em_finish_kernel<<<1, 64, 0, s>>>(g_em_scratch.partials, nb, MT, M, d_out);
+  const int nb = em_grid(K);
+  if (int rc = em_scratch((size_t)nb * 2 * MH)) return rc;
+  gync_em_norms_kernel<MH, FULL><<<nb, GYNC_EM_THREADS, 0, s>>>(dw, dL, K, M, g_em_scratch.partials);
+  gync_em_finish_kernel<MH><<<1, GYNC_EM_THREADS, 0, s>>>(g_em_scratch.partials, nb, M, d_out);
   g_launches += 2;
   CK(cudaGetLastError());
   return GYNC_OK;
 }
 
-template <int MT>
+template <int MH, bool FULL>
 int em_step_launch(double* dw, const double* dL, int64_t K, int M, const double* d_in, double* d_out, cudaStream_t s) {
-  const int nb = em_grid<MT>(K);
-  if (int rc = em_scratch(nb, MT)) return rc;
-  gync_em_step_kernel<MT><<<nb, GYNC_EM_THREADS, 0, s>>>(dw, dL, K, M, d_in, g_em_scratch.partials);
-  gync_em_finish_kernel<<<1, 64, 0, s>>>(g_em_scratch.partials, nb, MT, M, d_out);
+  const int nb = em_grid(K);
+  if (int rc = em_scratch((size_t)nb * 2 * MH)) return rc;
+  gync_em_step_kernel<MH, FULL><<<nb, GYNC_EM_THREADS, 0, s>>>(dw, dL, K, M, d_in, g_em_scratch.partials);
+  gync_em_finish_kernel<MH><<<1, GYNC_EM_THREADS, 0, s>>>(g_em_scratch.partials, nb, M, d_out);
   g_launches += 2;
   CK(cudaGetLastError());
   return GYNC_OK;
 }
 
+// columns are split over two threads per row: MH = columns per thread; FULL when M == 2*MH
 #define EM_DISPATCH(M, CALL)                                        \
   do {                                                              \
-    if ((M) <= 8) return CALL(8);                                   \
-    if ((M) <= 16) return CALL(16);                                 \
-    if ((M) <= 24) return CALL(24);                                 \
-    if ((M) <= 32) return CALL(32);                                 \
-    if ((M) <= 40) return CALL(40);                                 \
-    if ((M) <= 64) return CALL(64);                                 \
+    if ((M) == 40) return CALL(20, true);                           \
+    if ((M) <= 8) return CALL(4, false);                            \
+    if ((M) <= 16) return CALL(8, false);                           \
+    if ((M) <= 24) return CALL(12, false);                          \
+    if ((M) <= 32) return CALL(16, false);                          \
+    if ((M) <= 40) return CALL(20, false);                          \
+    if ((M) <= 64) return CALL(32, false);                          \
     return fail(GYNC_ERR_ARG, "EM: M > 64 patients not supported"); \
   } while (0)
 
@@ -334,7 +333,7 @@ int gync_em_iterate_dev(double* dw, const double* dL, int64_t K, int32_t M, int3
   if (int rc = ensure_init()) return rc;
   if (K == 0 || niter == 0) return GYNC_OK;
   cudaStream_t s = (cudaStream_t)stream;   // NULL = the legacy default stream, as torch uses
-#define CALL(MT) em_persistent_launch<MT>(dw, dL, K, M, niter, d_history, s)
+#define CALL(MH, F) em_persistent_launch<MH, F>(dw, dL, K, M, niter, d_history, s)
   EM_DISPATCH(M, CALL);
 #undef CALL
 }
@@ -343,7 +342,7 @@ int gync_em_norms_dev(const double* dw, const double* dL, int64_t K, int32_t M, 
   if (K < 0 || M < 1 || !d_norms_out) return fail(GYNC_ERR_ARG, "gync_em_norms: bad arguments");
   if (int rc = ensure_init()) return rc;
   cudaStream_t s = (cudaStream_t)stream;   // NULL = the legacy default stream, as torch uses
-#define CALL(MT) em_norms_launch<MT>(dw, dL, K, M, d_norms_out, s)
+#define CALL(MH, F) em_norms_launch<MH, F>(dw, dL, K, M, d_norms_out, s)
   EM_DISPATCH(M, CALL);
 #undef CALL
 }
@@ -353,7 +352,7 @@ int gync_em_step_dev(double* dw, const double* dL, int64_t K, int32_t M, const d
   if (K < 0 || M < 1 || !d_norms_in || !d_norms_out) return fail(GYNC_ERR_ARG, "gync_em_step: bad arguments");
   if (int rc = ensure_init()) return rc;
   cudaStream_t s = (cudaStream_t)stream;   // NULL = the legacy default stream, as torch uses
-#define CALL(MT) em_step_launch<MT>(dw, dL, K, M, d_norms_in, d_norms_out, s)
+#define CALL(MH, F) em_step_launch<MH, F>(dw, dL, K, M, d_norms_in, d_norms_out, s)
   EM_DISPATCH(M, CALL);
 #undef CALL
 }

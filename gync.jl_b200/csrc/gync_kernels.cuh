@@ -499,127 +499,183 @@ gync_solve_kernel(const double* __restrict__ X, const double* __restrict__ Y0, c
 // ------------------------------------------------------------------------------------------
 // K4: EM / self-consistency iteration  w_k <- w_k/M * sum_m L_km / (L'w)_m   (em.jl:27-41)
 //
-// Fused single-pass form: one read of L per iteration.  While row k's new weight is produced,
-// the NEXT iteration's denominators sum_k L_km w_k' are accumulated in registers; block partials
-// go to a double-buffered global scratch and every block re-reduces them in a fixed order after
-// one grid-wide barrier (deterministic, no atomics).  All `niter` iterations run inside one
-// cooperative launch.  HBM-bound: 8KM + 16K bytes per iteration.
-#define GYNC_EM_THREADS 256
+// Fused single-pass form: L is read ONCE per iteration.  While row k's new weight is produced,
+// the NEXT iteration's denominators sum_k L_km w_k' are accumulated in registers.  HBM-bound:
+// 8KM + 16K + 16M algorithmic bytes per iteration.
+//   * two threads per row, each owning half of the columns (MH = MT/2 values of L in flight per
+//     thread, 512 threads per SM: ~80 KB of loads in flight per SM to cover HBM latency);
+//     lane = 16*half + r, so for one column a half-warp reads 16 consecutive rows = one 128 B line;
+//   * the row sum needs one xor-16 shuffle; the per-thread accumulators are reduced over the 16
+//     row-lanes by shuffles, over the 16 warps through shared memory (fixed order);
+//   * block partials go to a double-buffered global scratch; after ONE grid-wide barrier every
+//     block re-reduces them in a fixed order (deterministic, no atomics), 12 blocks per thread
+//     group in parallel.  All `niter` iterations run inside one cooperative launch.
+#define GYNC_EM_THREADS 512
+#define GYNC_EM_WARPS (GYNC_EM_THREADS / 32)
 
-template <int MT>
-__device__ __forceinline__ void em_block_reduce(double (&acc)[MT], double* s_red /*[warps][MT]*/, double* out /*[MT]*/, int M) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+template <int MH>
+struct EmSmem {
+  double red[GYNC_EM_WARPS * 2 * MH];
+  double rinv[2 * MH];
+  double grp[(GYNC_EM_THREADS / (2 * MH) + 1) * 2 * MH];
+};
+
+// acc[j] (column half*MH + j) summed over the block -> out[m], m < M
+template <int MH>
+__device__ __forceinline__ void em_block_reduce(double (&acc)[MH], EmSmem<MH>& sm, double* out, int M) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = lane >> 4;
 #pragma unroll
-  for (int m = 0; m < MT; ++m) {
-    double v = acc[m];
+  for (int j = 0; j < MH; ++j) {
+    double v = acc[j];
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-    if (lane == 0) s_red[warp * MT + m] = v;
+    for (int off = 8; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if ((lane & 15) == 0) sm.red[warp * 2 * MH + half * MH + j] = v;
   }
   __syncthreads();
   if (threadIdx.x < M) {
     double v = 0.0;
-    for (int w = 0; w < GYNC_EM_THREADS / 32; ++w) v += s_red[w * MT + threadIdx.x];
+#pragma unroll
+    for (int w = 0; w < GYNC_EM_WARPS; ++w) v += sm.red[w * 2 * MH + threadIdx.x];
     out[threadIdx.x] = v;
   }
   __syncthreads();
 }
 
+// out[m] = sum_b partials[b][m] in a fixed order, using all threads of the block
+template <int MH>
+__device__ __forceinline__ void em_gather_partials(const double* __restrict__ partials, int nb, int M, EmSmem<MH>& sm,
+                                                   double* out_sm /* [2*MH] in shared memory */, bool reciprocal) {
+  constexpr int MT = 2 * MH, NG = GYNC_EM_THREADS / MT;
+  const int m = threadIdx.x % MT, g = threadIdx.x / MT;
+  if (g < NG) {
+    double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+    int b = g;
+    for (; b + 3 * NG < nb; b += 4 * NG) {      // independent loads in flight
+      v0 += __ldcg(partials + (size_t)b * MT + m);
+      v1 += __ldcg(partials + (size_t)(b + NG) * MT + m);
+      v2 += __ldcg(partials + (size_t)(b + 2 * NG) * MT + m);
+      v3 += __ldcg(partials + (size_t)(b + 3 * NG) * MT + m);
+    }
+    for (; b < nb; b += NG) v0 += __ldcg(partials + (size_t)b * MT + m);
+    sm.grp[g * MT + m] = (v0 + v1) + (v2 + v3);
+  }
+  __syncthreads();
+  if (threadIdx.x < MT) {
+    double v = 0.0;
+    for (int gg = 0; gg < NG; ++gg) v += sm.grp[gg * MT + threadIdx.x];
+    out_sm[threadIdx.x] = (threadIdx.x < M) ? (reciprocal ? 1.0 / v : v) : 0.0;   // unused columns: exact zeros
+  }
+  __syncthreads();
+}
+
 // partial denominators of this block's rows: out[m] = sum_k L[k,m] w[k]
-template <int MT>
+template <int MH, bool FULL>
 __device__ __forceinline__ void em_norms_pass(const double* __restrict__ w, const double* __restrict__ L,
-                                              int64_t K, int M, double* s_red, double* out) {
-  double acc[MT];
+                                              int64_t K, int M, EmSmem<MH>& sm, double* out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = lane >> 4, r = lane & 15;
+  double acc[MH];
 #pragma unroll
-  for (int m = 0; m < MT; ++m) acc[m] = 0.0;
-  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < K; k += (int64_t)gridDim.x * blockDim.x) {
+  for (int j = 0; j < MH; ++j) acc[j] = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * GYNC_EM_WARPS * 16;
+  for (int64_t k = ((int64_t)blockIdx.x * GYNC_EM_WARPS + warp) * 16 + r; k < K; k += stride) {
     const double wk = w[k];
+    const double* p = L + k + K * (int64_t)(half * MH);
 #pragma unroll
-    for (int m = 0; m < MT; ++m)
-      if (m < M) acc[m] = fma(__ldg(L + k + K * m), wk, acc[m]);
+    for (int j = 0; j < MH; ++j) {
+      if (FULL || half * MH + j < M) acc[j] = fma(__ldg(p), wk, acc[j]);
+      p += K;
+    }
   }
-  em_block_reduce<MT>(acc, s_red, out, M);
+  em_block_reduce<MH>(acc, sm, out, M);
 }
 
-// one EM step over this block's rows given s_rinv[m] = 1/norms[m]; accumulates next partials
-template <int MT>
+// one EM step over this block's rows given sm.rinv[m] = 1/norms[m]; accumulates next partials
+template <int MH, bool FULL>
 __device__ __forceinline__ void em_step_pass(double* __restrict__ w, const double* __restrict__ L, int64_t K, int M,
-                                             const double* s_rinv, double* s_red, double* out, double* hist) {
-  double acc[MT];
+                                             EmSmem<MH>& sm, double* out, double* hist) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = lane >> 4, r = lane & 15;
+  double acc[MH];
 #pragma unroll
-  for (int m = 0; m < MT; ++m) acc[m] = 0.0;
+  for (int j = 0; j < MH; ++j) acc[j] = 0.0;
+  const double* ri = sm.rinv + half * MH;      // reciprocal denominators (shared memory, broadcast reads)
   const double invM = 1.0 / (double)M;
-  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < K; k += (int64_t)gridDim.x * blockDim.x) {
-    double l[MT];
+  const int64_t stride = (int64_t)gridDim.x * GYNC_EM_WARPS * 16;
+  const int64_t k0 = ((int64_t)blockIdx.x * GYNC_EM_WARPS + warp) * 16;
+  for (int64_t kb = k0; kb < K; kb += stride) {          // warp-uniform loop (the shuffle needs all lanes)
+    const int64_t k = kb + r;
+    const bool valid = k < K;
+    double l[MH];
+    const double* p = L + (valid ? k : 0) + K * (int64_t)(half * MH);
 #pragma unroll
-    for (int m = 0; m < MT; ++m) l[m] = (m < M) ? __ldg(L + k + K * m) : 0.0;
-    double s = 0.0;
+    for (int j = 0; j < MH; ++j) {
+      l[j] = (valid && (FULL || half * MH + j < M)) ? __ldg(p) : 0.0;
+      p += K;
+    }
+    const double wk = valid ? w[k] : 0.0;
+    double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-    for (int m = 0; m < MT; ++m)
-      if (m < M) s = fma(l[m], s_rinv[m], s);
-    const double wn = w[k] * invM * s;
-    w[k] = wn;
-    if (hist) hist[k] = wn;
+    for (int j = 0; j + 1 < MH; j += 2) { s0 = fma(l[j], ri[j], s0); s1 = fma(l[j + 1], ri[j + 1], s1); }
+    if (MH & 1) s0 = fma(l[MH - 1], ri[MH - 1], s0);
+    double s = s0 + s1;
+    s += __shfl_xor_sync(0xffffffffu, s, 16);
+    const double wn = wk * invM * s;
+    if (valid && half == 0) {
+      w[k] = wn;
+      if (hist) hist[k] = wn;
+    }
 #pragma unroll
-    for (int m = 0; m < MT; ++m) acc[m] = fma(l[m], wn, acc[m]);
+    for (int j = 0; j < MH; ++j) acc[j] = fma(l[j], wn, acc[j]);
   }
-  em_block_reduce<MT>(acc, s_red, out, M);
+  em_block_reduce<MH>(acc, sm, out, M);
 }
 
-template <int MT>
-__global__ void __launch_bounds__(GYNC_EM_THREADS)
+template <int MH, bool FULL>
+__global__ void __launch_bounds__(GYNC_EM_THREADS, 1)
 gync_em_persistent_kernel(double* __restrict__ w, const double* __restrict__ L, int64_t K, int M, int niter,
-                          double* __restrict__ partials /* 2 x gridDim.x x MT */, double* __restrict__ history) {
+                          double* __restrict__ partials /* 2 x gridDim.x x 2MH */, double* __restrict__ history) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ double s_red[(GYNC_EM_THREADS / 32) * MT];
-  __shared__ double s_rinv[MT];
+  __shared__ EmSmem<MH> sm;
+  constexpr int MT = 2 * MH;
   const int nb = gridDim.x;
-  em_norms_pass<MT>(w, L, K, M, s_red, partials + (size_t)blockIdx.x * MT);
+  em_norms_pass<MH, FULL>(w, L, K, M, sm, partials + (size_t)blockIdx.x * MT);
   __threadfence();
   grid.sync();
   for (int it = 0; it < niter; ++it) {
     const double* pin = partials + (size_t)(it & 1) * nb * MT;
     double* pout = partials + (size_t)((it + 1) & 1) * nb * MT;
-    if (threadIdx.x < M) {
-      double v = 0.0;
-      for (int b = 0; b < nb; ++b) v += __ldcg(pin + (size_t)b * MT + threadIdx.x);
-      s_rinv[threadIdx.x] = 1.0 / v;
-    }
-    __syncthreads();
-    em_step_pass<MT>(w, L, K, M, s_rinv, s_red, pout + (size_t)blockIdx.x * MT,
-                     history ? history + (size_t)it * K : nullptr);
+    em_gather_partials<MH>(pin, nb, M, sm, sm.rinv, true);
+    em_step_pass<MH, FULL>(w, L, K, M, sm, pout + (size_t)blockIdx.x * MT, history ? history + (size_t)it * K : nullptr);
     __threadfence();
     grid.sync();
   }
 }
 
-// Sharded form: block partials -> scratch, then a one-block finishing kernel sums them.
-template <int MT>
-__global__ void __launch_bounds__(GYNC_EM_THREADS)
+// Sharded form (one process per GPU): block partials -> scratch, then a one-block finishing
+// kernel sums them; the caller allreduces the M denominators across ranks.
+template <int MH, bool FULL>
+__global__ void __launch_bounds__(GYNC_EM_THREADS, 1)
 gync_em_norms_kernel(const double* __restrict__ w, const double* __restrict__ L, int64_t K, int M,
                      double* __restrict__ partials) {
-  __shared__ double s_red[(GYNC_EM_THREADS / 32) * MT];
-  em_norms_pass<MT>(w, L, K, M, s_red, partials + (size_t)blockIdx.x * MT);
+  __shared__ EmSmem<MH> sm;
+  em_norms_pass<MH, FULL>(w, L, K, M, sm, partials + (size_t)blockIdx.x * 2 * MH);
 }
 
-template <int MT>
-__global__ void __launch_bounds__(GYNC_EM_THREADS)
+template <int MH, bool FULL>
+__global__ void __launch_bounds__(GYNC_EM_THREADS, 1)
 gync_em_step_kernel(double* __restrict__ w, const double* __restrict__ L, int64_t K, int M,
                     const double* __restrict__ norms_in, double* __restrict__ partials) {
-  __shared__ double s_red[(GYNC_EM_THREADS / 32) * MT];
-  __shared__ double s_rinv[MT];
-  if (threadIdx.x < M) s_rinv[threadIdx.x] = 1.0 / norms_in[threadIdx.x];
+  __shared__ EmSmem<MH> sm;
+  if (threadIdx.x < 2 * MH) sm.rinv[threadIdx.x] = (threadIdx.x < M) ? 1.0 / norms_in[threadIdx.x] : 0.0;
   __syncthreads();
-  em_step_pass<MT>(w, L, K, M, s_rinv, s_red, partials + (size_t)blockIdx.x * MT, nullptr);
+  em_step_pass<MH, FULL>(w, L, K, M, sm, partials + (size_t)blockIdx.x * 2 * MH, nullptr);
 }
 
-__global__ void gync_em_finish_kernel(const double* __restrict__ partials, int nb, int MT, int M, double* __restrict__ out) {
-  const int m = threadIdx.x;
-  if (m < M) {
-    double v = 0.0;
-    for (int b = 0; b < nb; ++b) v += partials[(size_t)b * MT + m];
-    out[m] = v;
-  }
+template <int MH>
+__global__ void __launch_bounds__(GYNC_EM_THREADS, 1)
+gync_em_finish_kernel(const double* __restrict__ partials, int nb, int M, double* __restrict__ out) {
+  __shared__ EmSmem<MH> sm;
+  em_gather_partials<MH>(partials, nb, M, sm, sm.rinv, false);
+  if (threadIdx.x < M) out[threadIdx.x] = sm.rinv[threadIdx.x];
 }
 
 // ------------------------------------------------------------------------------------------
