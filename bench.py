@@ -49,7 +49,7 @@ def near_set(n, seed=SEED):
 def workload_config(n_gpus):
     return {"workload": "batched GynCycle forward solve + log-likelihood, 1e5 synthetic parameter vectors (near set) x 1 "
                         "patient (Lausanne 1) per GPU", "n_samples_per_gpu": N_SAMPLES, "n_patients": 1,
-            "rtol": RTOL, "atol": ATOL, "solver": "RODAS4 adaptive, sparse LU (165 nnz)",
+            "rtol": RTOL, "atol": ATOL, "solver": "RODAS4 adaptive, sparse LU (165 nnz), state in smem+TMEM, 112 samples/SM",
             "l2_policy": "solver state lives in shared memory/registers; the 93 MB sample matrix is read once per step "
                          "(each step re-reads it from HBM/L2 — inputs are not larger than L2, a 256 MB buffer is written "
                          "between timed steps to flush it)",
@@ -232,7 +232,7 @@ def main():
     achieved = attempts * fl_step / (ms_dev * 1e-3) * 1e-12          # TFLOP/s on this rank's kernel
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
                 "frac": achieved / peak.value if peak.value else None, "traffic": None,
-                "kernel": "gync_loglik_kernel<64,32>", "kernel_ms": ms_dev,
+                "kernel": "gync_loglik_tm_kernel", "kernel_ms": ms_dev,
                 "how": f"{attempts} RODAS4 step attempts x {fl_step} FP64 flops per step (counted from the generated "
                        "code, DESIGN.md §5) / CUDA-event time; peak = FP64 FMA microbenchmark measured in this run "
                        "(MEASURED_PEAKS.json has no FP64 figure)",
@@ -339,7 +339,7 @@ def em_leg(lib, L, torch, dist, dev, stream, world, rank, barrier, max_over_rank
         by = 8 * K * M + 16 * K + 16 * M
         out["roofline"] = {"bound": "hbm", "achieved": out["cfg5_K1e6"]["algorithmic_GBps"], "peak": hbm, "unit": "GB/s",
                            "frac": out["cfg5_K1e6"]["frac_of_hbm"], "traffic": None,
-                           "kernel": "gync_em_persistent_kernel<40>", "peak_source": hbm_src,
+                           "kernel": "gync_em_persistent_kernel<20,true>", "peak_source": hbm_src,
                            "how": "8KM+16K+16M algorithmic bytes per iteration (L read once) / (CUDA-event time of one "
                                   "100-iteration cooperative launch / 100); K=1e6 x 40 = 320 MB > 126 MB L2"}
         return out
@@ -372,11 +372,35 @@ def em_leg(lib, L, torch, dist, dev, stream, world, rank, barrier, max_over_rank
     by = 8 * K * M + 16 * K + 16 * M
     wsum = w.sum()
     dist.all_reduce(wsum)
-    out["cfg5_K1e6_sharded"] = {"K_total": K * world, "K_per_gpu": K, "M": M, "us_per_iter": ms * 1e3, "iters_per_s": 1e3 / ms,
-                                "algorithmic_GBps_per_gpu": by / ms / 1e6, "frac_of_hbm": by / ms / 1e6 / hbm,
-                                "collective": "one NCCL allreduce(sum) of 40 f64 per iteration", "sum_w": float(wsum.item())}
-    out["roofline"] = {"bound": "hbm", "achieved": by / ms / 1e6, "peak": hbm, "unit": "GB/s", "frac": by / ms / 1e6 / hbm,
-                       "traffic": None, "kernel": "gync_em_step_kernel<40> + NCCL allreduce", "peak_source": hbm_src}
+    out["cfg5_K1e6_sharded_nccl"] = {"K_total": K * world, "K_per_gpu": K, "M": M, "us_per_iter": ms * 1e3, "iters_per_s": 1e3 / ms,
+                                     "algorithmic_GBps_per_gpu": by / ms / 1e6, "frac_of_hbm": by / ms / 1e6 / hbm,
+                                     "collective": "step kernel + one NCCL allreduce(sum) of 40 f64 per iteration",
+                                     "sum_w": float(wsum.item())}
+    # fused: EM step + exchange of the 40 denominators in ONE persistent kernel per rank over NVLink peer memory
+    from gync_b200.dist import FusedEM
+    w2 = torch.full((K,), 1.0 / (K * world), dtype=torch.float64, device=dev)
+    fem = FusedEM(w2, Lm, world, rank)
+    barrier()
+    fem.iterate(10)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fem.iterate(niter)
+    e1.record()
+    barrier()
+    msf = max_over_ranks(e0.elapsed_time(e1)) / niter
+    err = fem.error()
+    dw = (w2 - w).abs().max()
+    dist.all_reduce(dw, op=dist.ReduceOp.MAX)
+    fem.close()
+    out["cfg5_K1e6_sharded"] = {"K_total": K * world, "K_per_gpu": K, "M": M, "us_per_iter": msf * 1e3, "iters_per_s": 1e3 / msf,
+                                "algorithmic_GBps_per_gpu": by / msf / 1e6, "frac_of_hbm": by / msf / 1e6 / hbm,
+                                "collective": "fused: partial denominators stored into peer mailboxes over NVLink inside "
+                                              "the persistent kernel (no NCCL in the loop)",
+                                "peer_wait_timeout": int(err), "max_abs_diff_vs_nccl_path": float(dw.item())}
+    out["roofline"] = {"bound": "hbm", "achieved": by / msf / 1e6, "peak": hbm, "unit": "GB/s", "frac": by / msf / 1e6 / hbm,
+                       "traffic": None, "kernel": "gync_em_fused_kernel<20,true> (compute + peer-memory allreduce)",
+                       "peak_source": hbm_src}
     return out
 
 

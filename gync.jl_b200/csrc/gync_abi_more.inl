@@ -117,4 +117,119 @@ int gync_wc_normalize(const double* LL, const double* logprior, const int64_t* c
   return GYNC_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Fused multi-GPU EM: mailboxes in cudaMalloc'd memory exported with cudaIpc, so that each rank's
+// kernel can store its partial denominators directly into every peer's HBM over NVLink.
+struct gync_em_comm {
+  int world = 1, rank = 0, MT = 64;
+  double* mail = nullptr;                 // local mailbox [2][world][MT]
+  unsigned long long* flag = nullptr;     // local flags   [2][world]
+  void* peer_base[8] = {nullptr};         // opened peer allocations (nullptr for self)
+  GyncEmPeer peer;
+  unsigned long long seq = 0;
+  double* partials = nullptr;
+  double* gnorm = nullptr;
+  int* err = nullptr;
+  size_t flag_off = 0;
+};
+
+int gync_em_comm_create(int32_t world, int32_t rank, void* handle_out /* 64 bytes */, gync_em_comm** out) {
+  if (world < 1 || world > 8 || rank < 0 || rank >= world || !handle_out || !out)
+    return fail(GYNC_ERR_ARG, "gync_em_comm_create: bad arguments (world <= 8)");
+  if (int rc = ensure_init()) return rc;
+  gync_em_comm* c = new gync_em_comm();
+  c->world = world; c->rank = rank;
+  const size_t mail_bytes = sizeof(double) * 2 * world * c->MT;
+  c->flag_off = (mail_bytes + 255) / 256 * 256;
+  const size_t total = c->flag_off + sizeof(unsigned long long) * 2 * world;
+  void* base = nullptr;
+  CK(cudaMalloc(&base, total));
+  CK(cudaMemset(base, 0, total));
+  c->mail = (double*)base;
+  c->flag = (unsigned long long*)((char*)base + c->flag_off);
+  CK(cudaMalloc((void**)&c->partials, sizeof(double) * 1024 * c->MT));
+  CK(cudaMalloc((void**)&c->gnorm, sizeof(double) * 2 * c->MT));
+  CK(cudaMalloc((void**)&c->err, sizeof(int)));
+  CK(cudaMemset(c->err, 0, sizeof(int)));
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, base));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t size");
+  memcpy(handle_out, &h, 64);
+  c->peer.world = world; c->peer.rank = rank;
+  c->peer.mail[rank] = c->mail; c->peer.flag[rank] = c->flag;
+  CK(cudaDeviceSynchronize());
+  *out = c;
+  return GYNC_OK;
+}
+
+int gync_em_comm_connect(gync_em_comm* c, const void* all_handles /* world x 64 bytes, rank order */) {
+  if (!c || !all_handles) return fail(GYNC_ERR_ARG, "gync_em_comm_connect: NULL");
+  for (int p = 0; p < c->world; ++p) {
+    if (p == c->rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)all_handles + 64 * p, 64);
+    void* base = nullptr;
+    CK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    c->peer_base[p] = base;
+    c->peer.mail[p] = (double*)base;
+    c->peer.flag[p] = (unsigned long long*)((char*)base + c->flag_off);
+  }
+  return GYNC_OK;
+}
+
+void gync_em_comm_destroy(gync_em_comm* c) {
+  if (!c) return;
+  for (int p = 0; p < c->world; ++p) if (c->peer_base[p]) cudaIpcCloseMemHandle(c->peer_base[p]);
+  if (c->mail) cudaFree(c->mail);
+  if (c->partials) cudaFree(c->partials);
+  if (c->gnorm) cudaFree(c->gnorm);
+  if (c->err) cudaFree(c->err);
+  delete c;
+}
+
+}  // extern "C"
+
+namespace {
+template <int MH, bool FULL>
+int em_fused_launch(gync_em_comm* c, double* dw, const double* dL, int64_t K, int M, int niter, cudaStream_t s) {
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gync_em_fused_kernel<MH, FULL>, GYNC_EM_THREADS, 0));
+  if (per_sm < 1) return fail(GYNC_ERR_CUDA, "fused EM kernel does not fit on an SM");
+  const int64_t rows_per_block = GYNC_EM_WARPS * 16;
+  const int64_t want = (K + rows_per_block - 1) / rows_per_block;
+  int nb = (int)std::min<int64_t>(std::min<int64_t>((int64_t)g_num_sms * per_sm, 1024), std::max<int64_t>(want, 1));
+  // mailboxes are allocated 64 doubles wide per rank; the kernel indexes them with its own 2*MH stride
+  // (all ranks run the same instantiation, so the layout agrees)
+  GyncEmPeer peer = c->peer;
+  unsigned long long seq0 = c->seq;
+  double* partials = c->partials;
+  double* gnorm = c->gnorm;
+  int* err = c->err;
+  void* args[] = {&dw, &dL, &K, &M, &niter, &partials, &gnorm, &peer, &seq0, &err};
+  CK(cudaLaunchCooperativeKernel((void*)gync_em_fused_kernel<MH, FULL>, dim3(nb), dim3(GYNC_EM_THREADS), args, 0, s));
+  c->seq += (unsigned long long)niter + 1ull;
+  g_launches += 1;
+  return GYNC_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int gync_em_iterate_fused_dev(gync_em_comm* c, double* dw, const double* dL, int64_t K, int32_t M, int32_t niter,
+                              void* stream) {
+  if (!c || K < 0 || M < 1 || niter < 0 || (K > 0 && (!dw || !dL))) return fail(GYNC_ERR_ARG, "gync_em_iterate_fused: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+#define CALL(MH, F) em_fused_launch<MH, F>(c, dw, dL, K, M, niter, s)
+  EM_DISPATCH(M, CALL);
+#undef CALL
+}
+
+int gync_em_comm_error(gync_em_comm* c) {
+  if (!c) return -1;
+  int e = 0;
+  if (cudaMemcpy(&e, c->err, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+  return e;
+}
+
 }  // extern "C"

@@ -650,6 +650,74 @@ gync_em_persistent_kernel(double* __restrict__ w, const double* __restrict__ L, 
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// K4 across GPUs as ONE kernel: compute step + the allreduce of the M denominators fused over
+// NVLink peer memory.  Every rank runs this persistent cooperative kernel on its row shard.  Per
+// iteration: local fused pass -> grid barrier -> block 0 sums the block partials and STORES the M
+// partial denominators straight into every peer's mailbox (cudaIpc-mapped peer pointers, i.e.
+// st.global over NVLink/NVSwitch), publishes a sequence flag, spins on the flags of all peers,
+// adds the `world` contributions in rank order (bit-identical on every rank) -> grid barrier ->
+// next pass.  No NCCL call, no kernel boundary, no host round trip inside the iteration loop.
+struct GyncEmPeer {
+  double* mail[8];                 // mail[p]: rank p's mailbox [2 slots][world][MT] (peer pointer; mail[rank] local)
+  unsigned long long* flag[8];     // flag[p]: rank p's flags   [2 slots][world]
+  int world, rank;
+};
+
+template <int MH, bool FULL>
+__global__ void __launch_bounds__(GYNC_EM_THREADS, 1)
+gync_em_fused_kernel(double* __restrict__ w, const double* __restrict__ L, int64_t K, int M, int niter,
+                     double* __restrict__ partials /* gridDim.x x 2MH */, double* __restrict__ gnorm /* 2 x 2MH */,
+                     GyncEmPeer peer, unsigned long long seq0, int* __restrict__ err_flag) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ EmSmem<MH> sm;
+  constexpr int MT = 2 * MH;
+  const int nb = gridDim.x;
+  for (int it = -1; it < niter; ++it) {
+    // local pass: it == -1 computes the first denominators, afterwards one EM step each
+    if (it < 0) em_norms_pass<MH, FULL>(w, L, K, M, sm, partials + (size_t)blockIdx.x * MT);
+    else        em_step_pass<MH, FULL>(w, L, K, M, sm, partials + (size_t)blockIdx.x * MT, nullptr);
+    __threadfence();
+    grid.sync();
+    const unsigned long long seq = seq0 + (unsigned long long)(it + 1);
+    const int slot = (int)(seq & 1ull);
+    if (blockIdx.x == 0) {
+      em_gather_partials<MH>(partials, nb, M, sm, sm.rinv, false);          // this GPU's partial denominators
+      // push to every peer's mailbox (including our own), then publish the flag
+      for (int idx = threadIdx.x; idx < peer.world * MT; idx += GYNC_EM_THREADS) {
+        const int p = idx / MT, m = idx % MT;
+        peer.mail[p][((size_t)slot * peer.world + peer.rank) * MT + m] = sm.rinv[m];
+      }
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x < peer.world) {
+        volatile unsigned long long* f = peer.flag[threadIdx.x] + (size_t)slot * peer.world + peer.rank;
+        *f = seq;
+      }
+      // wait for all peers' contributions of this sequence number
+      if (threadIdx.x < peer.world) {
+        volatile unsigned long long* f = peer.flag[peer.rank] + (size_t)slot * peer.world + threadIdx.x;
+        long long spins = 0;
+        while (*f < seq) {
+          if (++spins > (1ll << 31)) { *err_flag = 1; break; }                 // never hang the GPU
+        }
+      }
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x < MT) {
+        double v = 0.0;
+        const volatile double* mb = peer.mail[peer.rank] + (size_t)slot * peer.world * MT;
+        for (int r = 0; r < peer.world; ++r) v += mb[(size_t)r * MT + threadIdx.x];   // rank order: identical everywhere
+        gnorm[slot * MT + threadIdx.x] = (threadIdx.x < M) ? 1.0 / v : 0.0;
+      }
+      __threadfence();
+    }
+    grid.sync();
+    if (threadIdx.x < MT) sm.rinv[threadIdx.x] = __ldcg(gnorm + slot * MT + threadIdx.x);
+    __syncthreads();
+  }
+}
+
 // Sharded form (one process per GPU): block partials -> scratch, then a one-block finishing
 // kernel sums them; the caller allreduces the M denominators across ranks.
 template <int MH, bool FULL>

@@ -65,3 +65,48 @@ class DeviceEM:
     def iterate(self, niter):
         import torch.distributed as dist
         return em_iterate_sharded(niter, self.norms, self.step, lambda x: dist.all_reduce(x))
+
+
+class FusedEM:
+    """Row shard of (w, L) on this rank's GPU, iterated by the FUSED kernel: EM step + allreduce of the M
+    denominators in one persistent cooperative launch per rank, partial sums exchanged through
+    cudaIpc-mapped peer mailboxes over NVLink (csrc/gync_kernels.cuh: gync_em_fused_kernel).
+    `torch.distributed` is used once, to exchange the 64-byte IPC handles."""
+
+    def __init__(self, w_local, L_local_colmajor, world=1, rank=0, all_gather_bytes=None):
+        import torch
+        from . import lib as _L
+        self.torch, self._L, self.lib = torch, _L, _L.load()
+        self.w, self.L = w_local, L_local_colmajor
+        self.M, self.K = self.L.shape
+        self.world, self.rank = world, rank
+        handle = (C.c_char * 64)()
+        self.comm = C.c_void_p()
+        _L.check(self.lib.gync_em_comm_create(world, rank, handle, C.byref(self.comm)))
+        if world > 1:
+            if all_gather_bytes is None:
+                import torch.distributed as dist
+
+                def all_gather_bytes(b):
+                    t = torch.frombuffer(bytearray(b), dtype=torch.uint8).to(w_local.device)
+                    out = [torch.empty_like(t) for _ in range(world)]
+                    dist.all_gather(out, t)
+                    return b"".join(bytes(o.cpu().numpy().tobytes()) for o in out)
+            allh = all_gather_bytes(bytes(handle))
+            assert len(allh) == 64 * world
+            self._handles = C.create_string_buffer(allh, 64 * world)
+            _L.check(self.lib.gync_em_comm_connect(self.comm, self._handles))
+
+    def iterate(self, niter):
+        """All ranks must call this with the same niter."""
+        self._L.check(self.lib.gync_em_iterate_fused_dev(self.comm, self.w.data_ptr(), self.L.data_ptr(), self.K, self.M,
+                                                         niter, self.torch.cuda.current_stream().cuda_stream))
+
+    def error(self):
+        return self.lib.gync_em_comm_error(self.comm)
+
+    def close(self):
+        if self.comm:
+            self.torch.cuda.synchronize()
+            self.lib.gync_em_comm_destroy(self.comm)
+            self.comm = None

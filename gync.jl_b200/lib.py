@@ -39,7 +39,8 @@ EXPORTS = [
     "gync_solve", "gync_forwardsol", "gync_loglik_batch", "gync_loglik_batch_dev",
     "gync_logprior_batch", "gync_mcmc_run", "gync_em_iterate", "gync_em_iterate_dev",
     "gync_em_norms_dev", "gync_em_step_dev", "gync_launch_count", "gync_wc_normalize", "gync_fp64_peak",
-    "gync_flops_per_step",
+    "gync_flops_per_step", "gync_em_comm_create", "gync_em_comm_connect", "gync_em_comm_destroy",
+    "gync_em_iterate_fused_dev", "gync_em_comm_error",
 ]
 
 _lib = None
@@ -79,6 +80,12 @@ def load():
                                       c_double_p, c_double_p]
     lib.gync_fp64_peak.argtypes = [c_double_p]
     lib.gync_flops_per_step.restype = C.c_double
+    lib.gync_em_comm_create.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.gync_em_comm_connect.argtypes = [C.c_void_p, C.c_void_p]
+    lib.gync_em_comm_destroy.argtypes = [C.c_void_p]
+    lib.gync_em_comm_destroy.restype = None
+    lib.gync_em_iterate_fused_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
+    lib.gync_em_comm_error.argtypes = [C.c_void_p]
     _lib = lib
     return lib
 

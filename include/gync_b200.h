@@ -116,6 +116,18 @@ int gync_em_iterate_dev(double* dw, const double* dL, int64_t K, int32_t M, int3
 int gync_em_norms_dev(const double* dw, const double* dL, int64_t K, int32_t M, double* d_norms_out, void* stream);
 int gync_em_step_dev(double* dw, const double* dL, int64_t K, int32_t M, const double* d_norms_in,
                      double* d_norms_out, void* stream);
+/* Fused multi-GPU EM (one process per GPU, <= 8 ranks of one NVLink domain): the step and the
+ * allreduce of the M denominators run as ONE persistent kernel per rank; partial denominators
+ * are stored straight into the peers' mailboxes over NVLink (cudaIpc-mapped), no NCCL inside the
+ * loop.  create -> exchange the 64-byte handles among ranks (any transport) -> connect.
+ * Every rank must call gync_em_iterate_fused_dev with the same M and niter. */
+typedef struct gync_em_comm gync_em_comm;
+int  gync_em_comm_create(int32_t world, int32_t rank, void* handle_out /* 64 bytes */, gync_em_comm** comm);
+int  gync_em_comm_connect(gync_em_comm* comm, const void* all_handles /* world x 64 bytes, rank order */);
+void gync_em_comm_destroy(gync_em_comm* comm);
+int  gync_em_iterate_fused_dev(gync_em_comm* comm, double* dw_local, const double* dL_local, int64_t K_local,
+                               int32_t M, int32_t niter, void* stream);
+int  gync_em_comm_error(gync_em_comm* comm);   /* 1 if a peer wait timed out */
 /* launches of our kernels since init (bench bookkeeping) */
 int64_t gync_launch_count(void);
 

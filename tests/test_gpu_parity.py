@@ -241,6 +241,30 @@ def test_em_sharded_step_kernels(gpu):
     assert relerr(got, ref) < RTOL_EM
 
 
+def test_em_fused_kernel_world1(gpu):
+    """The fused compute+exchange kernel with a single rank (mailbox = local memory): same numbers
+    as the oracle.  The multi-rank exchange is exercised by tools/multigpu_check.py under torchrun."""
+    import torch
+    import gync_oracle as o
+    from gync_b200.dist import FusedEM
+    rng = np.random.default_rng(12)
+    for K, M in ((20011, 40), (513, 7), (100_000, 33)):
+        L = rng.random((K, M))
+        L /= L.sum(0, keepdims=True)
+        w0 = rng.random(K)
+        w0 /= w0.sum()
+        em = FusedEM(torch.from_numpy(w0.copy()).cuda(), torch.from_numpy(np.ascontiguousarray(L.T)).cuda())
+        em.iterate(3)
+        em.iterate(2)                      # sequence numbers carry over between launches
+        torch.cuda.synchronize()
+        assert em.error() == 0
+        ref = w0.copy()
+        for _ in range(5):
+            ref = o.emiteration(ref, L)
+        assert relerr(em.w.cpu().numpy(), ref) < RTOL_EM
+        em.close()
+
+
 # ---------------------------------------------------------------------------------------- K3 / K5
 def test_mcmc_step_with_injected_randomness(gpu, gold):
     """Deterministic parity of the Metropolis step: same normals/uniforms into the
