@@ -127,7 +127,7 @@ struct gync_em_comm {
   unsigned long long* flag = nullptr;     // local flags   [2][world]
   void* peer_base[8] = {nullptr};         // opened peer allocations (nullptr for self)
   GyncEmPeer peer;
-  unsigned long long seq = 0;
+  unsigned long long seq = 1;          // flags start at 0: the first exchange must carry a larger number
   double* partials = nullptr;
   double* gnorm = nullptr;
   int* err = nullptr;
