@@ -41,7 +41,7 @@ parameternames = _C["parameternames"]
 #: parity is stated against the converged solution, so the default here is the
 #: tolerance at which log-likelihoods are within 1e-8 relative of it.
 DEFAULT_RTOL = 1e-8
-DEFAULT_ATOL = 1e-8
+DEFAULT_ATOL = 1e-10
 
 
 def uniformpropvar(relprop):

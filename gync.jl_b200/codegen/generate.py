@@ -158,10 +158,26 @@ def schedule(assigns, outputs, tmp_prefix):
     return list(reversed(keep))
 
 
+Q_LOOKAHEAD = 6     # statements of lookahead for parameter loads (software prefetch distance)
+
+
 def emit(stmts, cnt):
+    """Print the scheduled statements.  Every parameter q[k] is loaded ONCE into a named local, and
+    the loads are emitted a bounded number of statements ahead of their first use: the arrays may
+    live in shared memory behind volatile reads, which the compiler keeps glued to their use
+    (load-use distance 1 => the full shared-memory latency exposed per operation)."""
+    qsyms = {sym: name for sym, name in NAMES.items() if name.startswith("q[")}
+    local = {sym: sp.Symbol("q" + name[2:-1], real=True) for sym, name in qsyms.items()}
+    need = [[sym for sym in e.free_symbols if sym in qsyms] for _, e, _ in stmts]
+    loaded = set()
     lines = []
-    for l, e, d in stmts:
-        rhs = cprint(e, cnt)
+    for i, (l, e, d) in enumerate(stmts):
+        for j in range(i, min(i + Q_LOOKAHEAD, len(stmts))):
+            for sym in sorted(need[j], key=lambda v: int(qsyms[v][2:-1])):
+                if sym not in loaded:
+                    loaded.add(sym)
+                    lines.append(f"  const double {local[sym].name} = {qsyms[sym]};")
+        rhs = cprint(e.xreplace(local), cnt)
         lines.append(f"  {'const double ' if d else ''}{l} = {rhs};")
     return "\n".join(lines)
 
@@ -242,39 +258,60 @@ def main():
     lu_lines = []
     rows = {i: sorted([j for (a, j) in full if a == i], key=lambda j: rank[j]) for i in range(NY)}
     cols = {j: sorted([i for (i, b) in full if b == j], key=lambda i: rank[i]) for j in range(NY)}
+    LU_BATCH = 8
     for k in order:
         right = [j for j in rows[k] if rank[j] > rank[k]]
         below = [i for i in cols[k] if rank[i] > rank[k]]
         lu_lines.append(f"  {{ const double piv = GYNC_RCP(A[{pos[(k, k)]}]); A[{pos[(k, k)]}] = piv;")
         c_lu.rcp += 1
-        if below:   # read the pivot row once (the storage may be shared memory: every read is a real load)
+        if below:
             for j in right:
                 lu_lines.append(f"    const double u{j} = A[{pos[(k, j)]}];")
-        for i in below:
-            lu_lines.append(f"    {{ const double l = A[{pos[(i, k)]}] * piv; A[{pos[(i, k)]}] = l;")
-            c_lu.mul += 1
-            for j in right:
-                lu_lines.append(f"      A[{pos[(i, j)]}] -= l * u{j};")
+            for i in below:
+                lu_lines.append(f"    const double l{i} = A[{pos[(i, k)]}] * piv;")
                 c_lu.mul += 1
-                c_lu.add += 1
-            lu_lines.append("    }")
+            upd = [(i, j) for i in below for j in right]
+            for b0 in range(0, len(upd), LU_BATCH):       # loads of a batch first, then the FMAs, then the stores
+                batch = upd[b0:b0 + LU_BATCH]
+                for (i, j) in batch:
+                    lu_lines.append(f"    double t{i}_{j} = A[{pos[(i, j)]}];")
+                for (i, j) in batch:
+                    lu_lines.append(f"    t{i}_{j} -= l{i} * u{j};")
+                    c_lu.mul += 1
+                    c_lu.add += 1
+                for (i, j) in batch:
+                    lu_lines.append(f"    A[{pos[(i, j)]}] = t{i}_{j};")
+            for i in below:
+                lu_lines.append(f"    A[{pos[(i, k)]}] = l{i};")
         lu_lines.append("  }")
     src_lu = "\n".join(lu_lines)
 
     # ---- triangular solves
     c_sol = Counter()
-    sol_lines = []
+    SOL_BATCH = 8
+    ops = []      # (position in A, statement using the local name `a<n>`)
     for k in order:   # forward: L has unit diagonal, multipliers stored below the pivot
         for i in [i for i in cols[k] if rank[i] > rank[k]]:
-            sol_lines.append(f"  b[{i}] -= A[{pos[(i, k)]}] * b[{k}];")
+            ops.append((pos[(i, k)], f"b[{i}] -= {{a}} * b[{k}];"))
             c_sol.mul += 1
             c_sol.add += 1
     for k in reversed(order):
         right = [j for j in rows[k] if rank[j] > rank[k]]
-        acc = f"b[{k}]" + "".join(f" - A[{pos[(k, j)]}] * b[{j}]" for j in right)
+        for j in right:
+            ops.append((pos[(k, j)], f"b[{k}] -= {{a}} * b[{j}];"))
+        ops.append((pos[(k, k)], f"b[{k}] *= {{a}};"))
         c_sol.mul += len(right) + 1
         c_sol.add += len(right)
-        sol_lines.append(f"  b[{k}] = ({acc}) * A[{pos[(k, k)]}];")
+    sol_lines = []
+    batches = [ops[b0:b0 + SOL_BATCH] for b0 in range(0, len(ops), SOL_BATCH)]
+    def loads(bi):
+        return [f"  const double a{bi}_{n} = A[{p}];" for n, (p, _) in enumerate(batches[bi])]
+    sol_lines += loads(0)
+    for bi, batch in enumerate(batches):
+        if bi + 1 < len(batches):
+            sol_lines += loads(bi + 1)          # next batch's factors are in flight while this batch computes
+        for n, (_, stmt) in enumerate(batch):
+            sol_lines.append("  " + stmt.format(a=f"a{bi}_{n}"))
     src_sol = "\n".join(sol_lines)
 
     # ---- pack params

@@ -279,9 +279,13 @@ struct GyncWorkTm {
 // correction sum_j c_sj k_j, which is parked in the TMEM scratch vector while the RHS runs.
 __device__ __forceinline__ double gync_rodas4_step_tm(GyncWorkTm& W, const double h, const double rtol, const double atol) {
   const double ih = GYNC_RCP(h);
+  GYNC_TICK_INIT
   gync_rhs_w(W.y, W.q, ih * (1.0 / RD_G), W.e, W.A);
+  GYNC_TICK(0)
   gync_lu(W.A);
+  GYNC_TICK(1)
   gync_lusolve(W.A, W.e);
+  GYNC_TICK(2)
 #pragma unroll 1
   for (int s = 0; s < 5; ++s) {
     gync_tm_store_vec(W.tm + GYNC_TM_COL_K + 2 * GYNC_NY * s, W.e);      // park k_{s+1}
@@ -303,7 +307,9 @@ __device__ __forceinline__ double gync_rodas4_step_tm(GyncWorkTm& W, const doubl
       W.e[32] = fma(c, k32, W.e[32]);
     }
     gync_tm_store_vec(W.tm + GYNC_TM_COL_V, W.e);                          // park the correction
+    GYNC_TICK(3)
     gync_rhs(W.yn, W.q, W.e);
+    GYNC_TICK(4)
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
       double v[8];
@@ -312,7 +318,9 @@ __device__ __forceinline__ double gync_rodas4_step_tm(GyncWorkTm& W, const doubl
       for (int i = 0; i < 8; ++i) W.e[8 * ch + i] = fma(ih, v[i], W.e[8 * ch + i]);
     }
     W.e[32] = fma(ih, gync_tm_ld1(W.tm + GYNC_TM_COL_V + 64), W.e[32]);
+    GYNC_TICK(5)
     gync_lusolve(W.A, W.e);
+    GYNC_TICK(2)
   }
   double sum = 0.0;
 #pragma unroll
@@ -322,6 +330,7 @@ __device__ __forceinline__ double gync_rodas4_step_tm(GyncWorkTm& W, const doubl
     const double r = W.e[i] * GYNC_RCP(sc);
     sum = fma(r, r, sum);
   }
+  GYNC_TICK(6)
   return sqrt(sum * (1.0 / GYNC_NY));
 }
 

@@ -34,7 +34,7 @@ function check(rc::Cint)
 end
 
 # --- gync(y0,p,t;reltol,abstol)  (src/gync/gyncycle.jl:8-26) -------------------------------
-function gync(y0::Vector, p::Vector, t::Vector; reltol=1e-8, abstol=1e-8)
+function gync(y0::Vector, p::Vector, t::Vector; reltol=1e-8, abstol=1e-10)
   Y  = Array(Float64, length(t), length(y0))           # N = 1: exactly the reference's nT x 33 layout
   st = Cint[0]
   o  = Ref(SolverOpts(reltol, abstol))
@@ -45,7 +45,7 @@ function gync(y0::Vector, p::Vector, t::Vector; reltol=1e-8, abstol=1e-8)
 end
 
 # --- llh(c,x) (model.jl:128-155), llh(s::Sampling) (sampling.jl:32) --------------------------
-function loglikmatrix(X::Matrix{Float64}, datas::Vector{Matrix{Float64}}, sigmas::Vector{Float64}; reltol=1e-8, abstol=1e-8)
+function loglikmatrix(X::Matrix{Float64}, datas::Vector{Matrix{Float64}}, sigmas::Vector{Float64}; reltol=1e-8, abstol=1e-10)
   N, M = size(X, 1), length(datas)
   D  = cat(3, datas...)                                # 31 x 4 x M, NaN = missing
   LL = Array(Float64, N, M)
@@ -84,7 +84,7 @@ function sample!(s::Sampling, iters::Int)
   nacc  = Int64[0]
   state = reshape(copy(v.state), 1, 116)
   lf    = [v.logf]
-  o     = Ref(SolverOpts(1e-8, 1e-8))
+  o     = Ref(SolverOpts(1e-8, 1e-10))
   check(ccall((:gync_mcmc_run, LIBGYNC), Cint,
               (Ptr{Cdouble}, Ptr{Cdouble}, Int64, Ptr{Cdouble}, Cdouble, Ptr{Cdouble}, Cint, Ptr{Cdouble}, Ptr{Cint},
                Ptr{Cdouble}, Ptr{SolverOpts}, Int64, Cint, UInt64, UInt64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Int64}),

@@ -43,7 +43,7 @@ def rhs(y, p):
     return f
 
 
-def llh_batch(X, datas, sigmas, mode=1, rtol=1e-11, atol=1e-11, redundant=False, want_traj=False, want_work=False):
+def llh_batch(X, datas, sigmas, mode=1, rtol=1e-12, atol=1e-12, redundant=False, want_traj=False, want_work=False):
     """X (N,116); datas list of 31x4; -> LL (N,M) [, traj (N,62,4)] [, work (nfe,nje,nlu,nsteps)]."""
     X = np.asfortranarray(np.atleast_2d(X), dtype=np.float64)
     N = X.shape[0]
@@ -65,7 +65,7 @@ def llh_batch(X, datas, sigmas, mode=1, rtol=1e-11, atol=1e-11, redundant=False,
     return out[0] if len(out) == 1 else tuple(out)
 
 
-def gync(y0, p, t, mode=1, rtol=1e-11, atol=1e-11):
+def gync(y0, p, t, mode=1, rtol=1e-12, atol=1e-12):
     t = np.ascontiguousarray(t, dtype=np.float64)
     Y = np.empty((t.size, 33))
     lib().orc_gync(P(np.ascontiguousarray(y0, dtype=np.float64)), P(np.ascontiguousarray(p, dtype=np.float64)), P(t),

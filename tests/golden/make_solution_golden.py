@@ -55,7 +55,7 @@ if __name__ == "__main__":
     near[1, 115] = 28.0          # integer period: duplicated measurement times (model.jl:94,126)
     near[2, 115] = 30.5
     # converged reference solution -> y0 prior (model.jl:69, gyncycle.jl:30-38)
-    refsol = co.gync(o.REFY0, o.allparms(o.REFPARMS), np.arange(0.0, 31.0), mode=1, rtol=1e-11, atol=1e-11)
+    refsol = co.gync(o.REFY0, o.allparms(o.REFPARMS), np.arange(0.0, 31.0), mode=1, rtol=1e-12, atol=1e-12)
     refsol = o.referencesolution(refsol)
     means, stds = o.gmm_from_refsol(refsol)
     # "wide" set (eb/gync.jl:59): refparms .* 5u, y0 ~ GMM prior, T = 30
@@ -75,7 +75,7 @@ if __name__ == "__main__":
         d[np.isnan(la[m])] = np.nan
         datas.append(d)
     t0 = time.time()
-    LL, traj = co.llh_batch(X, datas, [sig] * 4, 1, 1e-11, 1e-11, want_traj=True)
+    LL, traj = co.llh_batch(X, datas, [sig] * 4, 1, 1e-12, 1e-12, want_traj=True)
     print("C oracle converged: %.1fs" % (time.time() - t0), "non-finite rows:", np.flatnonzero(~np.isfinite(LL[:, 0])))
     # independent cross-check with Radau on 5 samples
     chk = [0, 1, 2, 7, 19]

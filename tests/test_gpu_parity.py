@@ -54,7 +54,7 @@ def test_loglik_vs_c_oracle_fresh_samples(gpu):
     X[5, 115] = 27.0            # integer period -> duplicated times
     X[6, 115] = 31.75
     data = o.lausanne(2)
-    LLo, tro = co.llh_batch(X, [data], [0.15], 1, 1e-11, 1e-11, want_traj=True)
+    LLo, tro = co.llh_batch(X, [data], [0.15], 1, 1e-12, 1e-12, want_traj=True)
     LL, st, Ym = gpu.loglik_matrix(X, [data], [0.15], want_traj=True)
     assert np.all(st == 0) and np.all(np.isfinite(LLo))
     assert relerr(Ym, tro) < RTOL_TRAJ
@@ -113,14 +113,14 @@ def test_gync_and_forwardsol_generic_grid(gpu, gold):
     import gync_oracle as o
     t = np.arange(0.0, 31.0)
     Y = gpu.gync(o.REFY0, o.allparms(o.REFPARMS), t)
-    ref = co.gync(o.REFY0, o.allparms(o.REFPARMS), t, mode=1, rtol=1e-11, atol=1e-11)
+    ref = co.gync(o.REFY0, o.allparms(o.REFPARMS), t, mode=1, rtol=1e-12, atol=1e-12)
     big = np.abs(ref) > 1e-6 * np.abs(ref).max(0)
     assert np.array_equal(Y[0], o.REFY0)                       # t[0] is the initial time (cvode semantics)
     assert np.max(np.abs(Y - ref)[big] / np.abs(ref)[big]) < RTOL_TRAJ
     Yf = gpu.forwardsol(gold["X"][:4], np.array([1.0, 2.5, 2.5, 17.0, 40.0]))
     for i in range(4):
         parms, y0, _ = o.split(gold["X"][i])
-        ref = co.gync(y0, o.allparms(parms), np.array([1.0, 2.5, 17.0, 40.0]), mode=1, rtol=1e-11, atol=1e-11)
+        ref = co.gync(y0, o.allparms(parms), np.array([1.0, 2.5, 17.0, 40.0]), mode=1, rtol=1e-12, atol=1e-12)
         got = Yf[i][[0, 1, 3, 4]][:, o.MEASUREDINDS]
         assert relerr(got, ref[:, o.MEASUREDINDS]) < RTOL_TRAJ
         assert np.array_equal(Yf[i][1], Yf[i][2])
@@ -146,7 +146,7 @@ def test_full_size_properties(gpu, gold):
     assert np.array_equal(LL4[:, 0], LL1[sub, 0])              # column m is independent of the other patients
     import c_oracle as co
     pick = np.random.default_rng(6).choice(N, 16, replace=False)
-    LLo = co.llh_batch(X[pick], [data], [0.1], 1, 1e-11, 1e-11)
+    LLo = co.llh_batch(X[pick], [data], [0.1], 1, 1e-12, 1e-12)
     assert relerr(LL1[pick], LLo) < RTOL_LLH
 
 
@@ -288,7 +288,7 @@ def test_mcmc_step_with_injected_randomness(gpu, gold):
         lp = o.logprior(x, gold["gmm_means"], gold["gmm_stds"])
         if lp == -np.inf:
             return lp
-        return lp + co.llh_batch(x[None, :], [datas[m]], [0.1], 1, 1e-11, 1e-11)[0, 0] + xl.sum()
+        return lp + co.llh_batch(x[None, :], [datas[m]], [0.1], 1, 1e-12, 1e-12)[0, 0] + xl.sum()
 
     for use_chol in (False, True):
         state = L.fcol(np.tile(np.log(o.init_x()), (Cn, 1)))

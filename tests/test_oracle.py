@@ -70,7 +70,7 @@ def test_meastimes_and_duplicates():
 
 def test_c_oracle_converged_reproduces_golden(sol_gold):
     idx = [0, 1, 5, 34]
-    LL, tr = co.llh_batch(sol_gold["X"][idx], [sol_gold["data"][:, :, m] for m in range(4)], [0.1] * 4, 1, 1e-11, 1e-11,
+    LL, tr = co.llh_batch(sol_gold["X"][idx], [sol_gold["data"][:, :, m] for m in range(4)], [0.1] * 4, 1, 1e-12, 1e-12,
                           want_traj=True)
     assert relerr(LL, sol_gold["LL"][idx]) < 1e-10
     assert relerr(tr, sol_gold["traj"][idx]) < 1e-9

@@ -4,7 +4,7 @@
 #include <cstdio>
 #include "gync_kernels.cuh"
 int main() {
-  const int N = 64 * 148;
+  const int N = 112 * 148;
   double *X, *LL, *D, *S; double* isc; int* an; unsigned long long* cnt;
   cudaMallocManaged(&X, sizeof(double) * N * 116); cudaMallocManaged(&LL, sizeof(double) * N);
   cudaMallocManaged(&D, sizeof(double) * 124); cudaMallocManaged(&S, 8); cudaMallocManaged(&isc, 32); cudaMallocManaged(&an, 4);
@@ -16,11 +16,11 @@ int main() {
   for (int i = 0; i < 124; ++i) D[i] = 1.0; S[0] = 0.1;
   gync_prep_patients_kernel<<<1, 64>>>(D, S, 1, isc, an);
   GyncSolverOpts o = {1e-6, 1e-6, 0, 0, 100000};
-  cudaFuncSetAttribute(gync_loglik_kernel<64, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GyncWorkSm<64>::kSmemBytes);
-  gync_loglik_kernel<64, 32><<<148, 64, GyncWorkSm<64>::kSmemBytes>>>(X, N, D, isc, an, 1, o, LL, nullptr, nullptr, nullptr, cnt);
+  cudaFuncSetAttribute(gync_loglik_tm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GyncWorkTm::kSmemBytes);
+  gync_loglik_tm_kernel<<<148, 128, GyncWorkTm::kSmemBytes>>>(X, N, D, isc, an, 1, o, LL, nullptr, nullptr, nullptr, cnt);
   cudaError_t e = cudaDeviceSynchronize(); printf("%s LL0=%f\n", cudaGetErrorString(e), LL[0]);
   long long h[8]; cudaMemcpyFromSymbol(h, gync_phase_clk, sizeof(h));
-  const char* nm[] = {"rhs_w", "lu", "lusolve x6", "yn combos x5", "rhs x5", "e += combos x5", "norm", "outside step"};
+  const char* nm[] = {"rhs_w", "lu", "lusolve x6", "stage combos (TMEM) x5", "rhs x5", "e += v (TMEM) x5", "norm", "outside step"};
   long long tot = 0; for (int i = 0; i < 7; ++i) tot += h[i];
   for (int i = 0; i < 7; ++i) printf("%-40s %12lld  %.1f%%\n", nm[i], h[i], 100.0 * h[i] / tot);
   return 0;
