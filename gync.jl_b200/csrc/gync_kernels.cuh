@@ -223,6 +223,28 @@ struct GyncSmViewP {
   __device__ __forceinline__ GyncSmRefP operator[](int i) const { return GyncSmRefP{p + i * NSLOT, ok}; }
 };
 
+// Read-only view for phases that only READ an array (q in the RHS, A in the triangular solves):
+// plain `ld.shared.f64` through non-volatile asm on a laundered address.  The compiler cannot
+// forward earlier stores into them (the address is opaque after the barrier in gync_sm_ro) but
+// ptxas may schedule them freely inside the phase; volatile loads stay pinned in program order.
+// The view must be re-created inside every loop iteration that uses it, otherwise the loads are
+// loop-invariant and get hoisted out of the loop wholesale (258 live doubles -> spills).
+template <int NSLOT>
+struct GyncSmViewRO {
+  uint32_t sa;
+  __device__ __forceinline__ double operator[](int i) const {
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(sa + (uint32_t)(i * NSLOT * 8)));
+    return v;
+  }
+};
+template <int NSLOT>
+__device__ __forceinline__ GyncSmViewRO<NSLOT> gync_sm_ro(const double* p) {
+  uint32_t sa = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("" : "+r"(sa) :: "memory");       // earlier stores are emitted before; provenance forgotten
+  return GyncSmViewRO<NSLOT>{sa};
+}
+
 #define TM_R16(r) "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), \
                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
 #define TM_W16(r) "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), \
@@ -280,11 +302,12 @@ struct GyncWorkTm {
 __device__ __forceinline__ double gync_rodas4_step_tm(GyncWorkTm& W, const double h, const double rtol, const double atol) {
   const double ih = GYNC_RCP(h);
   GYNC_TICK_INIT
-  gync_rhs_w(W.y, W.q, ih * (1.0 / RD_G), W.e, W.A);
+  GYNC_TICK_INIT
+  gync_rhs_w(W.y, gync_sm_ro<GYNC_TM_NSLOT>(W.q.p), ih * (1.0 / RD_G), W.e, W.A);
   GYNC_TICK(0)
   gync_lu(W.A);
   GYNC_TICK(1)
-  gync_lusolve(W.A, W.e);
+  gync_lusolve(gync_sm_ro<GYNC_TM_NSLOT>(W.A.p), W.e);
   GYNC_TICK(2)
 #pragma unroll 1
   for (int s = 0; s < 5; ++s) {
@@ -308,7 +331,8 @@ __device__ __forceinline__ double gync_rodas4_step_tm(GyncWorkTm& W, const doubl
     }
     gync_tm_store_vec(W.tm + GYNC_TM_COL_V, W.e);                          // park the correction
     GYNC_TICK(3)
-    gync_rhs(W.yn, W.q, W.e);
+    GYNC_TICK(3)
+    gync_rhs(W.yn, gync_sm_ro<GYNC_TM_NSLOT>(W.q.p), W.e);
     GYNC_TICK(4)
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
@@ -319,7 +343,7 @@ __device__ __forceinline__ double gync_rodas4_step_tm(GyncWorkTm& W, const doubl
     }
     W.e[32] = fma(ih, gync_tm_ld1(W.tm + GYNC_TM_COL_V + 64), W.e[32]);
     GYNC_TICK(5)
-    gync_lusolve(W.A, W.e);
+    gync_lusolve(gync_sm_ro<GYNC_TM_NSLOT>(W.A.p), W.e);
     GYNC_TICK(2)
   }
   double sum = 0.0;
@@ -330,6 +354,7 @@ __device__ __forceinline__ double gync_rodas4_step_tm(GyncWorkTm& W, const doubl
     const double r = W.e[i] * GYNC_RCP(sc);
     sum = fma(r, r, sum);
   }
+  GYNC_TICK(6)
   GYNC_TICK(6)
   return sqrt(sum * (1.0 / GYNC_NY));
 }
