@@ -302,7 +302,6 @@ struct GyncWorkTm {
 __device__ __forceinline__ double gync_rodas4_step_tm(GyncWorkTm& W, const double h, const double rtol, const double atol) {
   const double ih = GYNC_RCP(h);
   GYNC_TICK_INIT
-  GYNC_TICK_INIT
   gync_rhs_w(W.y, gync_sm_ro<GYNC_TM_NSLOT>(W.q.p), ih * (1.0 / RD_G), W.e, W.A);
   GYNC_TICK(0)
   gync_lu(W.A);
@@ -331,7 +330,6 @@ __device__ __forceinline__ double gync_rodas4_step_tm(GyncWorkTm& W, const doubl
     }
     gync_tm_store_vec(W.tm + GYNC_TM_COL_V, W.e);                          // park the correction
     GYNC_TICK(3)
-    GYNC_TICK(3)
     gync_rhs(W.yn, gync_sm_ro<GYNC_TM_NSLOT>(W.q.p), W.e);
     GYNC_TICK(4)
 #pragma unroll
@@ -354,7 +352,6 @@ __device__ __forceinline__ double gync_rodas4_step_tm(GyncWorkTm& W, const doubl
     const double r = W.e[i] * GYNC_RCP(sc);
     sum = fma(r, r, sum);
   }
-  GYNC_TICK(6)
   GYNC_TICK(6)
   return sqrt(sum * (1.0 / GYNC_NY));
 }
