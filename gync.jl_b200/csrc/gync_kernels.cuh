@@ -91,7 +91,9 @@ struct GyncLlhSink {
   int64_t N;
   double* acc;                         // LL + n   (stride N over patients)
   double* ymeas;                       // Ymeas + n (N x 62 x 4) or nullptr
+  bool enabled = true;                 // mirror lanes of the TMEM kernel compute but do not write
   __device__ __forceinline__ void operator()(int period, int day, const double* y) {
+    if (!enabled) return;
     const double ym[GYNC_NMEAS] = {y[1], y[6], y[23], y[24]};   // measuredinds (model.jl:1)
     if (ymeas) {
 #pragma unroll
@@ -208,19 +210,15 @@ gync_loglik_kernel(const double* __restrict__ X, int64_t N, const double* __rest
 #define GYNC_TM_COL_K 0
 #define GYNC_TM_COL_V (5 * 2 * GYNC_NY)
 
-struct GyncSmRefP {
-  double* p;
-  bool ok;
-  __device__ __forceinline__ operator double() const { return *(volatile double*)p; }
-  __device__ __forceinline__ const GyncSmRefP& operator=(double v) const { if (ok) *p = v; return *this; }
-  __device__ __forceinline__ const GyncSmRefP& operator-=(double v) const { const double t = *(volatile double*)p - v; if (ok) *p = t; return *this; }
-  __device__ __forceinline__ const GyncSmRefP& operator+=(double v) const { const double t = *(volatile double*)p + v; if (ok) *p = t; return *this; }
-};
+// Lanes 28..31 of each warp have no shared-memory slot of their own.  They MIRROR lanes 24..27:
+// same sample index, same inputs, same instruction stream, hence bit-identical values — so they
+// may issue the same shared-memory stores to the same addresses (benign same-value races) and no
+// store needs a predicate (predicated stores turned into branches that chopped the straight-line
+// LU / Jacobian code into small basic blocks).  Only real lanes touch global memory.
 template <int NSLOT>
 struct GyncSmViewP {
   double* p;
-  bool ok;
-  __device__ __forceinline__ GyncSmRefP operator[](int i) const { return GyncSmRefP{p + i * NSLOT, ok}; }
+  __device__ __forceinline__ GyncSmRef operator[](int i) const { return GyncSmRef{p + i * NSLOT}; }
 };
 
 // Read-only view for phases that only READ an array (q in the RHS, A in the triangular solves):
@@ -374,33 +372,37 @@ gync_loglik_tm_kernel(const double* __restrict__ X, int64_t N, const double* __r
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = s_tmem;
 
-  const bool real = lane < GYNC_TM_LPW;                    // lanes 28..31 only keep the warp converged
+  const bool real = lane < GYNC_TM_LPW;                    // lanes 28..31 mirror lanes 24..27
+  const int src_lane = real ? lane : lane - 4;
   GyncWorkTm W;
-  const int slot = warp * GYNC_TM_LPW + (real ? lane : GYNC_TM_LPW - 1);
-  W.q.p = gync_sm + slot;  W.q.ok = real;
-  W.A.p = gync_sm + (size_t)GYNC_NQ * GYNC_TM_NSLOT + slot;  W.A.ok = real;
+  const int slot = warp * GYNC_TM_LPW + src_lane;
+  W.q.p = gync_sm + slot;
+  W.A.p = gync_sm + (size_t)GYNC_NQ * GYNC_TM_NSLOT + slot;
   W.tm = tmem_base + ((uint32_t)(warp * 32) << 16);
 #pragma unroll
   for (int i = 0; i < GYNC_NY; ++i) { W.y[i] = 1.0; W.yn[i] = 1.0; W.e[i] = 0.0; }
 
   const double big = 1.0e300, ninf = -INFINITY;
-  bool active = false, done = !real;
+  bool active = false, done = false;
   int64_t n = 0;
   double T = 0.0, t = 0.0, tn = 0.0;
   int i0 = 0, i1 = 0, budget = 0, st = GYNC_ST_OK;
   GyncCtrl c;
   gync_ctrl_init(c, 1e-3);
-  GyncLlhSink sink = {data, iscale, M, N, nullptr, nullptr};
-  if (!real) {   // benign dummy parameters (never stored: read-only alias of a real slot is fine)
-  }
+  GyncLlhSink sink = {data, iscale, M, N, nullptr, nullptr, real};
   for (;;) {
-    if (!active && !done) {
-      n = (int64_t)atomicAdd(counter, 1ull);
+    // fetch: real lanes draw an index, mirror lanes copy it (collectives stay outside divergent code)
+    const bool want = !active && !done;
+    long long drawn = -1;
+    if (want && real) drawn = (long long)atomicAdd(counter, 1ull);
+    drawn = __shfl_sync(0xffffffffu, drawn, src_lane);
+    if (want) {
+      n = (int64_t)drawn;
       if (n >= N) {
         done = true;
       } else {
         gync_load_sample(W, [&](int k) { return __ldg(X + n + N * k); }, c_refallparms, c_sampledinds, &T);
-        for (int m = 0; m < M; ++m) LL[n + N * m] = 0.0;
+        if (real) for (int m = 0; m < M; ++m) LL[n + N * m] = 0.0;
         sink.acc = LL + n;
         sink.ymeas = Ymeas ? Ymeas + n : nullptr;
         i0 = i1 = 0;
@@ -466,16 +468,18 @@ gync_loglik_tm_kernel(const double* __restrict__ X, int64_t N, const double* __r
         if (i0 >= GYNC_NDAYS && i1 >= GYNC_NDAYS) finished = true;
       }
       if (finished) {
-        for (int m = 0; m < M; ++m) {
-          const double a = LL[n + N * m];
-          LL[n + N * m] = (st != GYNC_ST_OK || allnan[m]) ? ninf : -0.5 * a;
+        if (real) {
+          for (int m = 0; m < M; ++m) {
+            const double a = LL[n + N * m];
+            LL[n + N * m] = (st != GYNC_ST_OK || allnan[m]) ? ninf : -0.5 * a;
+          }
+          if (st != GYNC_ST_OK && Ymeas)
+            for (int k = 0; k < GYNC_NT_MEAS * GYNC_NMEAS; ++k) Ymeas[n + N * k] = NAN;
+          if (status) status[n] = st;
+          if (nsteps) { nsteps[n] = c.nacc; nsteps[n + N] = c.nrej; }
         }
-        if (st != GYNC_ST_OK && Ymeas)
-          for (int k = 0; k < GYNC_NT_MEAS * GYNC_NMEAS; ++k) Ymeas[n + N * k] = NAN;
-        if (status) status[n] = st;
-        if (nsteps) { nsteps[n] = c.nacc; nsteps[n + N] = c.nrej; }
         active = false;
-        // keep the dummy state benign for the lock-step iterations that may follow
+        // keep the idle state benign for the lock-step iterations that may follow
 #pragma unroll
         for (int i = 0; i < GYNC_NY; ++i) if (!(W.y[i] * 0.0 == 0.0)) W.y[i] = 1.0;
       }
