@@ -36,7 +36,13 @@ int gync_mcmc_run(double* state, double* logf, int64_t C, const double* chol, do
   if (int rc = ensure_init()) return rc;
   if (C == 0) return GYNC_OK;
   const int64_t n_out = iters / thin;
-  DBuf dS, dLf, dCh, dD, dSig, dPat, dPr, dZ, dU, dOut, dAcc, dIsc, dNan;
+  // speculation depth: fill the solver kernel's sample slots (112 per SM) about twice per round
+  int K = (int)std::max<int64_t>(1, std::min<int64_t>(1024, (2 * (int64_t)g_num_sms * GYNC_TM_NSLOT) / C));
+  if (const char* v = getenv("GYNC_MCMC_SPEC")) K = std::max(1, std::min(4096, atoi(v)));
+  K = (int)std::min<int64_t>(K, std::max<int64_t>(iters, 1));
+  const int64_t N = C * K;
+  cudaStream_t s = g_stream;
+  DBuf dS, dLf, dCh, dD, dSig, dPat, dPr, dZ, dU, dOut, dAcc, dIsc, dNan, dIt, dXL, dX, dLpr, dLL, dPs, dMin;
   CK(dS.alloc(sizeof(double) * C * GYNC_NX));
   CK(dLf.alloc(sizeof(double) * C));
   CK(dD.alloc(sizeof(double) * 124 * M));
@@ -45,43 +51,74 @@ int gync_mcmc_run(double* state, double* logf, int64_t C, const double* chol, do
   CK(dIsc.alloc(sizeof(double) * 4 * M));
   CK(dNan.alloc(sizeof(int) * M));
   CK(dAcc.alloc(sizeof(long long) * C));
-  CK(cudaMemcpyAsync(dS.p, state, sizeof(double) * C * GYNC_NX, cudaMemcpyHostToDevice, g_stream));
-  CK(cudaMemcpyAsync(dLf.p, logf, sizeof(double) * C, cudaMemcpyHostToDevice, g_stream));
-  CK(cudaMemcpyAsync(dD.p, data, sizeof(double) * 124 * M, cudaMemcpyHostToDevice, g_stream));
-  CK(cudaMemcpyAsync(dSig.p, sigma_rho, sizeof(double) * M, cudaMemcpyHostToDevice, g_stream));
-  CK(cudaMemcpyAsync(dPr.p, prior, sizeof(gync_prior), cudaMemcpyHostToDevice, g_stream));
+  CK(dIt.alloc(sizeof(long long) * C));
+  CK(dXL.alloc(sizeof(double) * N * GYNC_NX));
+  CK(dX.alloc(sizeof(double) * N * GYNC_NX));
+  CK(dLpr.alloc(sizeof(double) * N));
+  CK(dLL.alloc(sizeof(double) * N));
+  CK(dPs.alloc(sizeof(int) * N));
+  CK(dMin.alloc(sizeof(long long)));
+  CK(cudaMemcpyAsync(dS.p, state, sizeof(double) * C * GYNC_NX, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(dLf.p, logf, sizeof(double) * C, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(dD.p, data, sizeof(double) * 124 * M, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(dSig.p, sigma_rho, sizeof(double) * M, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(dPr.p, prior, sizeof(gync_prior), cudaMemcpyHostToDevice, s));
+  CK(cudaMemsetAsync(dAcc.p, 0, sizeof(long long) * C, s));
+  CK(cudaMemsetAsync(dIt.p, 0, sizeof(long long) * C, s));
   if (chol) {
     CK(dCh.alloc(sizeof(double) * GYNC_NX * GYNC_NX));
-    CK(cudaMemcpyAsync(dCh.p, chol, sizeof(double) * GYNC_NX * GYNC_NX, cudaMemcpyHostToDevice, g_stream));
+    CK(cudaMemcpyAsync(dCh.p, chol, sizeof(double) * GYNC_NX * GYNC_NX, cudaMemcpyHostToDevice, s));
   }
   if (patient_of_chain) {
     CK(dPat.alloc(sizeof(int32_t) * C));
-    CK(cudaMemcpyAsync(dPat.p, patient_of_chain, sizeof(int32_t) * C, cudaMemcpyHostToDevice, g_stream));
+    CK(cudaMemcpyAsync(dPat.p, patient_of_chain, sizeof(int32_t) * C, cudaMemcpyHostToDevice, s));
   }
   if (inj_z) {
     CK(dZ.alloc(sizeof(double) * iters * GYNC_NX * C));
     CK(dU.alloc(sizeof(double) * iters * C));
-    CK(cudaMemcpyAsync(dZ.p, inj_z, sizeof(double) * iters * GYNC_NX * C, cudaMemcpyHostToDevice, g_stream));
-    CK(cudaMemcpyAsync(dU.p, inj_u, sizeof(double) * iters * C, cudaMemcpyHostToDevice, g_stream));
+    CK(cudaMemcpyAsync(dZ.p, inj_z, sizeof(double) * iters * GYNC_NX * C, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dU.p, inj_u, sizeof(double) * iters * C, cudaMemcpyHostToDevice, s));
   }
   if (samples_out && n_out > 0) CK(dOut.alloc(sizeof(double) * n_out * GYNC_NX * C));
-  gync_prep_patients_kernel<<<blocks_for(M, 64), 64, 0, g_stream>>>(dD.as<double>(), dSig.as<double>(), M, dIsc.as<double>(), dNan.as<int>());
-  // chains are latency-bound (one solve per iteration): spread them over the SMs, 32 per CTA
-  if (int rc = prep_solver_kernel(gync_mcmc_kernel<32>, GyncWorkSm<32>::kSmemBytes, 32)) return rc;
-  gync_mcmc_kernel<32><<<std::min<unsigned>(blocks_for(C, 32), 2 * g_num_sms), 32, GyncWorkSm<32>::kSmemBytes, g_stream>>>(
-      dS.as<double>(), dLf.as<double>(), C, chol ? dCh.as<double>() : nullptr, prop_sd, dD.as<double>(),
-      dIsc.as<double>(), dNan.as<int>(), patient_of_chain ? dPat.as<int>() : nullptr, dPr.as<GyncPriorDev>(),
-      to_opts(opts), iters, thin, seed, iter_offset, inj_z ? dZ.as<double>() : nullptr,
-      inj_u ? dU.as<double>() : nullptr, (samples_out && n_out > 0) ? dOut.as<double>() : nullptr,
-      dAcc.as<long long>());
-  g_launches += 2;
-  CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(state, dS.p, sizeof(double) * C * GYNC_NX, cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaMemcpyAsync(logf, dLf.p, sizeof(double) * C, cudaMemcpyDeviceToHost, g_stream));
+  gync_prep_patients_kernel<<<blocks_for(M, 64), 64, 0, s>>>(dD.as<double>(), dSig.as<double>(), M, dIsc.as<double>(), dNan.as<int>());
+  g_launches += 1;
+  const GyncSolverOpts so = to_opts(opts);
+  bool need_init = false;
+  for (int64_t c = 0; c < C; ++c) need_init |= !(logf[c] == logf[c]);
+  // round: propose K slots per chain -> batched likelihoods -> accept scan
+  auto round = [&](int mode, int Kr) -> int {
+    const int64_t Nr = C * Kr;
+    gync_mcmc_propose_kernel<<<blocks_for(Nr, 128), 128, 0, s>>>(
+        dS.as<double>(), dIt.as<long long>(), C, Kr, iters, mode, chol ? dCh.as<double>() : nullptr, prop_sd,
+        dPr.as<GyncPriorDev>(), seed, iter_offset, inj_z ? dZ.as<double>() : nullptr,
+        patient_of_chain ? dPat.as<int>() : nullptr, dXL.as<double>(), dX.as<double>(), dLpr.as<double>(), dPs.as<int>());
+    g_launches += 1;
+    CK(cudaGetLastError());
+    if (int rc = launch_loglik(dX.as<double>(), Nr, dD.as<double>(), dIsc.as<double>(), dNan.as<int>(), M, dPs.as<int>(), so,
+                               dLL.as<double>(), nullptr, nullptr, nullptr, s)) return rc;
+    long long big = (long long)iters;
+    CK(cudaMemcpyAsync(dMin.p, &big, sizeof(long long), cudaMemcpyHostToDevice, s));
+    gync_mcmc_accept_kernel<<<blocks_for(C, 128), 128, 0, s>>>(
+        dS.as<double>(), dLf.as<double>(), dIt.as<long long>(), C, Kr, iters, thin, mode, dXL.as<double>(), dLpr.as<double>(),
+        dLL.as<double>(), seed, iter_offset, inj_u ? dU.as<double>() : nullptr,
+        (samples_out && n_out > 0) ? dOut.as<double>() : nullptr, dAcc.as<long long>(), dMin.as<long long>());
+    g_launches += 1;
+    CK(cudaGetLastError());
+    return GYNC_OK;
+  };
+  if (need_init) if (int rc = round(1, 1)) return rc;
+  long long min_it = 0;
+  while (min_it < iters) {
+    if (int rc = round(0, K)) return rc;
+    CK(cudaMemcpyAsync(&min_it, dMin.p, sizeof(long long), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  CK(cudaMemcpyAsync(state, dS.p, sizeof(double) * C * GYNC_NX, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(logf, dLf.p, sizeof(double) * C, cudaMemcpyDeviceToHost, s));
   if (samples_out && n_out > 0)
-    CK(cudaMemcpyAsync(samples_out, dOut.p, sizeof(double) * n_out * GYNC_NX * C, cudaMemcpyDeviceToHost, g_stream));
-  if (naccept) CK(cudaMemcpyAsync(naccept, dAcc.p, sizeof(long long) * C, cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaStreamSynchronize(g_stream));
+    CK(cudaMemcpyAsync(samples_out, dOut.p, sizeof(double) * n_out * GYNC_NX * C, cudaMemcpyDeviceToHost, s));
+  if (naccept) CK(cudaMemcpyAsync(naccept, dAcc.p, sizeof(long long) * C, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
   return GYNC_OK;
 }
 

@@ -17,7 +17,6 @@ cudaStream_t g_stream = nullptr;
 int g_device = -1;
 int g_num_sms = 0;
 std::atomic<int64_t> g_launches{0};
-int g_llk_variant = 0;
 
 int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -69,6 +68,27 @@ int prep_solver_kernel(K kern, size_t smem, int block) {
 }  // namespace
 
 extern "C" int gync_init(int device);
+
+namespace {
+// One launch of the solver kernel: persistent lanes, one CTA (4 warps x 28 samples, state in shared
+// + tensor memory) per SM.  `pat` (nullable) gives every sample its own patient -> LL is N x 1.
+int launch_loglik(const double* dX, int64_t N, const double* d_data, const double* iscale, const int* allnan, int M,
+                  const int* pat, const GyncSolverOpts& so, double* dLL, double* dYmeas, int32_t* d_status,
+                  int32_t* d_nsteps, cudaStream_t s) {
+  unsigned long long* counter = nullptr;
+  CK(cudaMallocAsync((void**)&counter, sizeof(unsigned long long), s));
+  CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), s));
+  if (int rc = prep_solver_kernel(gync_loglik_tm_kernel, GyncWorkTm::kSmemBytes, 128)) return rc;
+  const int64_t want = (N + GYNC_TM_NSLOT - 1) / GYNC_TM_NSLOT;
+  const int nb = (int)std::min<int64_t>(want, (int64_t)g_num_sms);
+  gync_loglik_tm_kernel<<<nb, 128, GyncWorkTm::kSmemBytes, s>>>(dX, N, d_data, iscale, allnan, M, pat, so, dLL, dYmeas,
+                                                                d_status, d_nsteps, counter);
+  g_launches += 1;
+  CK(cudaGetLastError());
+  CK(cudaFreeAsync(counter, s));
+  return GYNC_OK;
+}
+}  // namespace
 
 // EM launch helpers (templates: outside extern "C")
 namespace {
@@ -188,7 +208,6 @@ int gync_init(int device) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   g_num_sms = prop.multiProcessorCount;
-  if (const char* v = getenv("GYNC_LLK_VARIANT")) g_llk_variant = atoi(v);
   g_device = device;
   return GYNC_OK;
 }
@@ -212,37 +231,8 @@ int gync_loglik_batch_dev(const double* dX, int64_t N, const double* d_data, int
   CK(cudaMallocAsync((void**)&iscale, sizeof(double) * 4 * M, s));
   CK(cudaMallocAsync((void**)&allnan, sizeof(int) * M, s));
   gync_prep_patients_kernel<<<blocks_for(M, 64), 64, 0, s>>>(d_data, d_sigma_rho, M, iscale, allnan);
-  const GyncSolverOpts so = to_opts(opts);
-  unsigned long long* counter = nullptr;
-  CK(cudaMallocAsync((void**)&counter, sizeof(unsigned long long), s));
-  CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), s));
-  // persistent lanes: one CTA of 64 sample slots per SM, spread over 32/LPW * 2 warps
-#define LLK(B, LPW)                                                                                             \
-  do {                                                                                                          \
-    if (int rc = prep_solver_kernel(gync_loglik_kernel<B, LPW>, GyncWorkSm<B>::kSmemBytes, B)) return rc;       \
-    const int64_t want = (N + B - 1) / B;                                                                       \
-    const int nb = (int)std::min<int64_t>(want, (int64_t)g_num_sms * (GYNC_SOLVE_BLOCK / B));                   \
-    gync_loglik_kernel<B, LPW><<<nb, B * (32 / LPW), GyncWorkSm<B>::kSmemBytes, s>>>(                           \
-        dX, N, d_data, iscale, allnan, M, so, dLL, dYmeas, d_status, d_nsteps, counter);                        \
-  } while (0)
-  switch (g_llk_variant) {   // tuning variants (env GYNC_LLK_VARIANT)
-    default: {               // production: stage vectors in tensor memory, 112 samples per SM
-      if (int rc = prep_solver_kernel(gync_loglik_tm_kernel, GyncWorkTm::kSmemBytes, 128)) return rc;
-      const int64_t want = (N + GYNC_TM_NSLOT - 1) / GYNC_TM_NSLOT;
-      const int nb = (int)std::min<int64_t>(want, (int64_t)g_num_sms);
-      gync_loglik_tm_kernel<<<nb, 128, GyncWorkTm::kSmemBytes, s>>>(dX, N, d_data, iscale, allnan, M, so, dLL, dYmeas,
-                                                                    d_status, d_nsteps, counter);
-    } break;
-    case 1: LLK(32, 32); break;
-    case 2: LLK(64, 16); break;
-    case 3: LLK(64, 8); break;
-    case 4: LLK(32, 16); break;
-    case 5: LLK(32, 8); break;
-    case 6: LLK(64, 32); break;   // all-shared-memory layout, 64 samples per SM
-  }
-#undef LLK
-  CK(cudaFreeAsync(counter, s));
-  g_launches += 2;
+  if (int rc = launch_loglik(dX, N, d_data, iscale, allnan, M, nullptr, to_opts(opts), dLL, dYmeas, d_status, d_nsteps, s)) return rc;
+  g_launches += 1;
   CK(cudaGetLastError());
   CK(cudaFreeAsync(iscale, s));
   CK(cudaFreeAsync(allnan, s));

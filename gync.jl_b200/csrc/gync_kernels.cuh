@@ -85,9 +85,9 @@ struct GyncWorkSm {
 // through the merged measurement grid one step attempt per loop trip, so lanes of a warp stay
 // busy although their samples need different numbers of (adaptive) steps.
 struct GyncLlhSink {
-  const double* __restrict__ data;     // 31 x 4 x M
+  const double* __restrict__ data;     // 31 x 4 x M  (offset to the first patient this sample is scored against)
   const double* __restrict__ iscale;   // 4 x M
-  int M;
+  int M;                               // number of patients scored (1 when every sample has its own patient)
   int64_t N;
   double* acc;                         // LL + n   (stride N over patients)
   double* ymeas;                       // Ymeas + n (N x 62 x 4) or nullptr
@@ -113,86 +113,6 @@ struct GyncLlhSink {
     }
   }
 };
-
-template <int BLOCK, int LPW>
-__global__ void __launch_bounds__(BLOCK * (32 / LPW), 1)
-gync_loglik_kernel(const double* __restrict__ X, int64_t N, const double* __restrict__ data,
-                   const double* __restrict__ iscale, const int* __restrict__ allnan, int M,
-                   GyncSolverOpts o, double* __restrict__ LL, double* __restrict__ Ymeas,
-                   int* __restrict__ status, int* __restrict__ nsteps, unsigned long long* __restrict__ counter) {
-  extern __shared__ double gync_sm[];
-  const int lane = threadIdx.x & 31;
-  if (lane >= LPW) return;
-  constexpr unsigned kMask = (LPW == 32) ? 0xffffffffu : ((1u << LPW) - 1u);
-  GyncWorkSm<BLOCK> W;
-  W.bind(gync_sm, (threadIdx.x >> 5) * LPW + lane);
-  const double big = 1.0e300, ninf = -INFINITY;
-  bool active = false, done = false;
-  int64_t n = 0;
-  double T = 0.0, t = 0.0, tn = 0.0;
-  int i0 = 0, i1 = 0, budget = 0, st = GYNC_ST_OK;
-  GyncCtrl c;
-  GyncLlhSink sink = {data, iscale, M, N, nullptr, nullptr};
-  for (;;) {
-    if (!active && !done) {
-      n = (int64_t)atomicAdd(counter, 1ull);
-      if (n >= N) {
-        done = true;
-      } else {
-        gync_load_sample(W, [&](int k) { return __ldg(X + n + N * k); }, c_refallparms, c_sampledinds, &T);
-        for (int m = 0; m < M; ++m) LL[n + N * m] = 0.0;
-        sink.acc = LL + n;
-        sink.ymeas = Ymeas ? Ymeas + n : nullptr;
-        i0 = i1 = 0;
-        budget = o.max_steps;
-        t = fmin(1.0, 1.0 + T);
-        tn = t;
-        st = (gync_all_finite(W.y, GYNC_NY) && gync_all_finite(W.q, GYNC_NQ) && (T * 0.0 == 0.0)) ? GYNC_ST_OK
-                                                                                                 : GYNC_ST_NONFINITE;
-        gync_ctrl_init(c, (st == GYNC_ST_OK) ? ((o.h0 > 0.0) ? o.h0 : gync_initial_step(W, o.rtol, o.atol)) : 1.0);
-        active = true;
-      }
-    }
-    if (__all_sync(kMask, done)) break;
-    if (active) {
-      bool finished = (st != GYNC_ST_OK);
-      if (!finished) {
-        if (tn > t) {
-          if (budget-- <= 0) {
-            st = GYNC_ST_MAXSTEPS;
-          } else {
-            const int r = gync_attempt(W, c, t, tn, o);
-            if (r < 0) st = -r;
-          }
-        }
-        if (st == GYNC_ST_OK && t >= tn) {
-          // serve every measurement time equal to t, then pick the next target
-          for (;;) {
-            const double tA = (i0 < GYNC_NDAYS) ? (double)(i0 + 1) : big;
-            const double tB = (i1 < GYNC_NDAYS) ? (double)(i1 + 1) + T : big;
-            tn = fmin(tA, tB);
-            if (tn > t) break;
-            if (tA == tn) { sink(0, i0, W.y); ++i0; }
-            if (tB == tn) { sink(1, i1, W.y); ++i1; }
-          }
-          if (i0 >= GYNC_NDAYS && i1 >= GYNC_NDAYS) finished = true;
-        }
-        if (st != GYNC_ST_OK) finished = true;
-      }
-      if (finished) {
-        for (int m = 0; m < M; ++m) {
-          const double a = LL[n + N * m];
-          LL[n + N * m] = (st != GYNC_ST_OK || allnan[m]) ? ninf : -0.5 * a;
-        }
-        if (st != GYNC_ST_OK && Ymeas)
-          for (int k = 0; k < GYNC_NT_MEAS * GYNC_NMEAS; ++k) Ymeas[n + N * k] = NAN;
-        if (status) status[n] = st;
-        if (nsteps) { nsteps[n] = c.nacc; nsteps[n + N] = c.nrej; }
-        active = false;
-      }
-    }
-  }
-}
 
 // ------------------------------------------------------------------------------------------
 // K1, TMEM variant: the five RODAS stage vectors live in TENSOR MEMORY.
@@ -357,6 +277,7 @@ __device__ __forceinline__ double gync_rodas4_step_tm(GyncWorkTm& W, const doubl
 __global__ void __launch_bounds__(128, 1)
 gync_loglik_tm_kernel(const double* __restrict__ X, int64_t N, const double* __restrict__ data,
                       const double* __restrict__ iscale, const int* __restrict__ allnan, int M,
+                      const int* __restrict__ pat /* nullable: patient of each sample -> LL is N x 1 */,
                       GyncSolverOpts o, double* __restrict__ LL, double* __restrict__ Ymeas,
                       int* __restrict__ status, int* __restrict__ nsteps, unsigned long long* __restrict__ counter) {
   extern __shared__ double gync_sm[];
@@ -386,7 +307,7 @@ gync_loglik_tm_kernel(const double* __restrict__ X, int64_t N, const double* __r
   bool active = false, done = false;
   int64_t n = 0;
   double T = 0.0, t = 0.0, tn = 0.0;
-  int i0 = 0, i1 = 0, budget = 0, st = GYNC_ST_OK;
+  int i0 = 0, i1 = 0, budget = 0, st = GYNC_ST_OK, mlo = 0, mcnt = M;
   GyncCtrl c;
   gync_ctrl_init(c, 1e-3);
   GyncLlhSink sink = {data, iscale, M, N, nullptr, nullptr, real};
@@ -402,7 +323,12 @@ gync_loglik_tm_kernel(const double* __restrict__ X, int64_t N, const double* __r
         done = true;
       } else {
         gync_load_sample(W, [&](int k) { return __ldg(X + n + N * k); }, c_refallparms, c_sampledinds, &T);
-        if (real) for (int m = 0; m < M; ++m) LL[n + N * m] = 0.0;
+        mlo = pat ? pat[n] : 0;
+        mcnt = pat ? 1 : M;
+        sink.data = data + (size_t)GYNC_NDAYS * GYNC_NMEAS * mlo;
+        sink.iscale = iscale + GYNC_NMEAS * mlo;
+        sink.M = mcnt;
+        if (real) for (int m = 0; m < mcnt; ++m) LL[n + N * m] = 0.0;
         sink.acc = LL + n;
         sink.ymeas = Ymeas ? Ymeas + n : nullptr;
         i0 = i1 = 0;
@@ -469,9 +395,9 @@ gync_loglik_tm_kernel(const double* __restrict__ X, int64_t N, const double* __r
       }
       if (finished) {
         if (real) {
-          for (int m = 0; m < M; ++m) {
+          for (int m = 0; m < mcnt; ++m) {
             const double a = LL[n + N * m];
-            LL[n + N * m] = (st != GYNC_ST_OK || allnan[m]) ? ninf : -0.5 * a;
+            LL[n + N * m] = (st != GYNC_ST_OK || allnan[mlo + m]) ? ninf : -0.5 * a;
           }
           if (st != GYNC_ST_OK && Ymeas)
             for (int k = 0; k < GYNC_NT_MEAS * GYNC_NMEAS; ++k) Ymeas[n + N * k] = NAN;

@@ -327,6 +327,13 @@ def test_sample_api_shapes_and_reproducibility(gpu):
     s2 = gpu.sample_bang(gpu.sample(c, 20, seed=3), 20)
     assert np.array_equal(s.samples, s2.samples)                                # counter-based RNG: resumable, reproducible
     assert 0 < s.variate.naccept <= 40 and np.all(s.samples > 0)
+    # speculative evaluation is EXACT: depth 1 (the sequential algorithm) and the default depth give the same chain
+    os.environ["GYNC_MCMC_SPEC"] = "1"
+    try:
+        s1 = gpu.sample_bang(gpu.sample(c, 20, seed=3), 20)
+    finally:
+        del os.environ["GYNC_MCMC_SPEC"]
+    assert np.array_equal(s1.samples, s.samples) and s1.variate.naccept == s.variate.naccept
     ss = gpu.sample_chains([gpu.new_sampling(gpu.Config(gpu.Lausanne(i)), seed=1) for i in (1, 2, 3)], 6)
     assert all(x.samples.shape == (6, 116) for x in ss)
     assert not np.array_equal(ss[0].samples, ss[1].samples)
