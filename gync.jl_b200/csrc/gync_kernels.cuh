@@ -163,6 +163,9 @@ __device__ __forceinline__ GyncSmViewRO<NSLOT> gync_sm_ro(const double* p) {
   return GyncSmViewRO<NSLOT>{sa};
 }
 
+template <int B>
+__device__ __forceinline__ GyncSmViewRO<B> gync_ro(const GyncSmView<B>& v) { return gync_sm_ro<B>(v.p); }
+
 #define TM_R16(r) "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), \
                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
 #define TM_W16(r) "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), \

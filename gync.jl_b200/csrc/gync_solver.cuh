@@ -131,6 +131,11 @@ GYNC_TABLE double RD_TC[5][5] = {{RD_C21, 0, 0, 0, 0},
                                  {RD_C51, RD_C52, RD_C53, RD_C54, 0},
                                  {RD_C61, RD_C62, RD_C63, RD_C64, RD_C65}};
 
+// Read-only access to an array for a phase that only reads it.  Plain arrays: the array itself.
+// The shared-memory views of the device overload this (gync_kernels.cuh) with a schedulable view.
+template <class T>
+GYNC_HD static const T& gync_ro(const T& a) { return a; }
+
 // One step attempt of size h from W.y; on return W.yn = y(t+h) candidate, returns the scaled
 // error norm (RMS over the 33 species of e_i / (atol + rtol*max(|y_i|,|yn_i|))).
 // Storage: W.q, W.A, W.k may be shared-memory views (every read a real load); W.y, W.yn and the
@@ -141,11 +146,11 @@ template <class WK>
 GYNC_HD static double gync_rodas4_step(WK& W, const double h, const double rtol, const double atol) {
   const double ih = GYNC_RCP(h);
   GYNC_TICK_INIT
-  gync_rhs_w(W.y, W.q, ih * (1.0 / RD_G), W.e, W.A);
+  gync_rhs_w(W.y, gync_ro(W.q), ih * (1.0 / RD_G), W.e, W.A);
   GYNC_TICK(0)
   gync_lu(W.A);
   GYNC_TICK(1)
-  gync_lusolve(W.A, W.e);
+  gync_lusolve(gync_ro(W.A), W.e);
   GYNC_TICK(2)
 #pragma unroll 1
   for (int s = 0; s < 5; ++s) {
@@ -159,7 +164,7 @@ GYNC_HD static double gync_rodas4_step(WK& W, const double h, const double rtol,
       for (int i = 0; i < GYNC_NY; ++i) W.yn[i] = fma(a, (double)W.k[j * GYNC_NY + i], W.yn[i]);
     }
     GYNC_TICK(3)
-    gync_rhs(W.yn, W.q, W.e);
+    gync_rhs(W.yn, gync_ro(W.q), W.e);
     GYNC_TICK(4)
 #pragma unroll 1
     for (int j = 0; j <= s; ++j) {
@@ -168,7 +173,7 @@ GYNC_HD static double gync_rodas4_step(WK& W, const double h, const double rtol,
       for (int i = 0; i < GYNC_NY; ++i) W.e[i] = fma(c, (double)W.k[j * GYNC_NY + i], W.e[i]);
     }
     GYNC_TICK(5)
-    gync_lusolve(W.A, W.e);
+    gync_lusolve(gync_ro(W.A), W.e);
     GYNC_TICK(2)
   }
   double sum = 0.0;
