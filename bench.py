@@ -231,7 +231,10 @@ def main():
     L.check(lib.gync_fp64_peak(C.byref(peak)))
     achieved = attempts * fl_step / (ms_dev * 1e-3) * 1e-12          # TFLOP/s on this rank's kernel
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
-                "frac": achieved / peak.value if peak.value else None, "traffic": None,
+                "frac": achieved / peak.value if peak.value else None,
+                # DRAM bytes per launch from the ncu --set full capture (profiles/r1_ncu_full_summary.txt:
+                # 15.6 MB read + 0.07 MB written for 16 576 samples = 946 B per sample; algorithmic 928 + 8 B)
+                "traffic": 946.0 * N_SAMPLES,
                 "kernel": "gync_loglik_tm_kernel", "kernel_ms": ms_dev,
                 "how": f"{attempts} RODAS4 step attempts x {fl_step} FP64 flops per step (counted from the generated "
                        "code, DESIGN.md §5) / CUDA-event time; peak = FP64 FMA microbenchmark measured in this run "
@@ -338,7 +341,9 @@ def em_leg(lib, L, torch, dist, dev, stream, world, rank, barrier, max_over_rank
         K = 1_000_000
         by = 8 * K * M + 16 * K + 16 * M
         out["roofline"] = {"bound": "hbm", "achieved": out["cfg5_K1e6"]["algorithmic_GBps"], "peak": hbm, "unit": "GB/s",
-                           "frac": out["cfg5_K1e6"]["frac_of_hbm"], "traffic": None,
+                           "frac": out["cfg5_K1e6"]["frac_of_hbm"],
+                           "traffic": 6.888e9 / 20 + 163.6e6 / 20,   # ncu: DRAM read+write of a 20-iteration launch / 20
+                           "algorithmic_bytes": by,
                            "kernel": "gync_em_persistent_kernel<20,true>", "peak_source": hbm_src,
                            "how": "8KM+16K+16M algorithmic bytes per iteration (L read once) / (CUDA-event time of one "
                                   "100-iteration cooperative launch / 100); K=1e6 x 40 = 320 MB > 126 MB L2"}

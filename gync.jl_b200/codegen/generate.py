@@ -19,6 +19,7 @@ Run:  python gync.jl_b200/codegen/generate.py      (the output is committed)
 from __future__ import annotations
 
 import os
+import re
 import sys
 from collections import OrderedDict
 
@@ -221,11 +222,25 @@ def main():
     assert all((i, i) in pattern for i in range(NY))
     order, full = markowitz(pattern, NY)
     rank = {k: r for r, k in enumerate(order)}
-    # storage order: by pivot rank of the row, then pivot rank of the column (row-major in pivot order)
-    lu_entries = sorted(full, key=lambda ij: (rank[ij[0]], rank[ij[1]]))
+    rows = {i: sorted([j for (a, j) in full if a == i], key=lambda j: rank[j]) for i in range(NY)}
+    cols = {j: sorted([i for (i, b) in full if b == j], key=lambda i: rank[i]) for j in range(NY)}
+    touched = set()
+    for k in order:
+        for i in [i for i in cols[k] if rank[i] > rank[k]]:
+            touched.add((i, k))
+            for j in [j for j in rows[k] if rank[j] > rank[k]]:
+                touched.add((i, j))
+    # storage order: by pivot rank of the row, then pivot rank of the column (row-major in pivot order);
+    # entries the factorisation never touches (unmodified U off-diagonals) go LAST (the "tail"), in
+    # backward-substitution use order, so that a layout may keep them in a second memory (TMEM on the device)
+    tail = [(k, j) for k in reversed(order) for j in rows[k] if rank[j] > rank[k] and (k, j) not in touched]
+    tail = tail[:(len(tail) // 8) * 8]
+    body = sorted([ij for ij in full if ij not in set(tail)], key=lambda ij: (rank[ij[0]], rank[ij[1]]))
+    lu_entries = body + tail
     pos = {ij: n for n, ij in enumerate(lu_entries)}
     nlu = len(lu_entries)
-
+    nbody = len(body)
+    assert all(ij in J for ij in tail)
     # parameter slots
     psyms = list(m.psyms.values())
     for k, s in enumerate(psyms):
@@ -248,9 +263,21 @@ def main():
     for ij in lu_entries:
         i, j = ij
         if ij in J:
-            outs.append((f"A[{pos[ij]}]", (fac if i == j else 0) - J[ij]))
+            lhs = f"A[{pos[ij]}]" if pos[ij] < nbody else f"const double at{pos[ij] - nbody}"
+            outs.append((lhs, (fac if i == j else 0) - J[ij]))
     st = schedule(defs + list(ddefs.items()), outs, "w")
     src_w = emit(st, c_w)
+    # each tail chunk is stored as soon as its 8 values exist (keeps the live range of the locals short)
+    wl = src_w.split("\n")
+    where = {}
+    for li, ln in enumerate(wl):
+        m_ = re.match(r"\s*const double at(\d+) = ", ln)
+        if m_:
+            where[int(m_.group(1))] = li
+    inserts = sorted(((max(where[8 * c8 + n] for n in range(8)), c8) for c8 in range(len(tail) // 8)), reverse=True)
+    for li, c8 in inserts:
+        wl.insert(li + 1, "  gync_tail_store8(A, %d, %s);" % (c8, ", ".join(f"at{8 * c8 + n}" for n in range(8))))
+    src_w = "\n".join(wl)
     zero_fill = "\n".join(f"  A[{pos[ij]}] = 0.0;" for ij in lu_entries if ij not in J)
 
     # ---- LU factorisation (right-looking, pivot order `order`)
@@ -259,14 +286,24 @@ def main():
     rows = {i: sorted([j for (a, j) in full if a == i], key=lambda j: rank[j]) for i in range(NY)}
     cols = {j: sorted([i for (i, b) in full if b == j], key=lambda i: rank[i]) for j in range(NY)}
     LU_BATCH = 8
+    lu_chunks = set()
     for k in order:
         right = [j for j in rows[k] if rank[j] > rank[k]]
         below = [i for i in cols[k] if rank[i] > rank[k]]
+        if below:      # pivot-row entries kept in the tail are read (never written) here: fetch their chunks first
+            for j in right:
+                if pos[(k, j)] >= nbody:
+                    c8 = (pos[(k, j)] - nbody) // 8
+                    if c8 not in lu_chunks:
+                        lu_chunks.add(c8)
+                        lu_lines.append(f"  double tl{c8}[8]; gync_tail_load8(A, {c8}, tl{c8});")
         lu_lines.append(f"  {{ const double piv = GYNC_RCP(A[{pos[(k, k)]}]); A[{pos[(k, k)]}] = piv;")
         c_lu.rcp += 1
         if below:
             for j in right:
-                lu_lines.append(f"    const double u{j} = A[{pos[(k, j)]}];")
+                p_ = pos[(k, j)]
+                src_ = f"A[{p_}]" if p_ < nbody else f"tl{(p_ - nbody) // 8}[{(p_ - nbody) % 8}]"
+                lu_lines.append(f"    const double u{j} = {src_};")
             for i in below:
                 lu_lines.append(f"    const double l{i} = A[{pos[(i, k)]}] * piv;")
                 c_lu.mul += 1
@@ -305,13 +342,21 @@ def main():
     sol_lines = []
     batches = [ops[b0:b0 + SOL_BATCH] for b0 in range(0, len(ops), SOL_BATCH)]
     def loads(bi):
-        return [f"  const double a{bi}_{n} = A[{p}];" for n, (p, _) in enumerate(batches[bi])]
+        return [f"  const double a{bi}_{n} = A[{p}];" for n, (p, _) in enumerate(batches[bi]) if p < nbody]
     sol_lines += loads(0)
+    chunks_loaded = set()
     for bi, batch in enumerate(batches):
         if bi + 1 < len(batches):
             sol_lines += loads(bi + 1)          # next batch's factors are in flight while this batch computes
-        for n, (_, stmt) in enumerate(batch):
-            sol_lines.append("  " + stmt.format(a=f"a{bi}_{n}"))
+        for n, (p, stmt) in enumerate(batch):
+            if p < nbody:
+                sol_lines.append("  " + stmt.format(a=f"a{bi}_{n}"))
+            else:
+                c8, off = divmod(p - nbody, 8)
+                if c8 not in chunks_loaded:
+                    chunks_loaded.add(c8)
+                    sol_lines.append(f"  double tl{c8}[8]; gync_tail_load8(A, {c8}, tl{c8});")
+                sol_lines.append("  " + stmt.format(a=f"tl{c8}[{off}]"))
     src_sol = "\n".join(sol_lines)
 
     # ---- pack params
@@ -347,6 +392,7 @@ def main():
 #define GYNC_NQ   {nq}      /* derived per-sample parameters */
 #define GYNC_NNZJ {len(J)}     /* structural nonzeros of the Jacobian */
 #define GYNC_NLU  {nlu}     /* nonzeros of L+U after fill (Markowitz order, diagonal pivots) */
+#define GYNC_NLU_BODY {nbody}   /* entries [0, BODY) are touched by the factorisation; [BODY, NLU) ("tail") only by gync_rhs_w and gync_lusolve */
 /* FP64 operation counts of the generated code (adds, muls, reciprocals, pows) */
 #define GYNC_OPS_RHS_FLOP  {c_rhs.flops()}
 #define GYNC_OPS_RHS_RCP   {c_rhs.rcp}
@@ -373,6 +419,18 @@ static const unsigned short GYNC_LU_DIAG[{NY}] = {{{", ".join(str(pos[(i, i)]) f
 #define GYNC_MEASMAG_LIST 120.0, 10.0, 400.0, 15.0
 /* 1-based reference parameter indices that the RHS reads ({len(used_p)} of 114) */
 static const unsigned char GYNC_USED_P[{len(used_p)}] = {{{", ".join(map(str, used_p))}}};
+
+/* tail of the LU storage in chunks of 8 (generic layouts keep it in the same array; the TMEM layout overloads these) */
+template <class AT>
+GYNC_HD static void gync_tail_store8(AT& A, const int c, const double v0, const double v1, const double v2, const double v3,
+                                     const double v4, const double v5, const double v6, const double v7) {{
+  A[GYNC_NLU_BODY + 8 * c + 0] = v0; A[GYNC_NLU_BODY + 8 * c + 1] = v1; A[GYNC_NLU_BODY + 8 * c + 2] = v2; A[GYNC_NLU_BODY + 8 * c + 3] = v3;
+  A[GYNC_NLU_BODY + 8 * c + 4] = v4; A[GYNC_NLU_BODY + 8 * c + 5] = v5; A[GYNC_NLU_BODY + 8 * c + 6] = v6; A[GYNC_NLU_BODY + 8 * c + 7] = v7;
+}}
+template <class AT>
+GYNC_HD static void gync_tail_load8(const AT& A, const int c, double (&v)[8]) {{
+  for (int i = 0; i < 8; ++i) v[i] = A[GYNC_NLU_BODY + 8 * c + i];
+}}
 
 /* q <- derived parameters from the 114 reference-ordered parameters */
 template <class PT, class QT>

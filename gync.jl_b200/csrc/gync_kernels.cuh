@@ -122,13 +122,16 @@ struct GyncLlhSink {
 // addressable scratch in the 32x32b access shape (thread i of warp w <-> TMEM lane 32(w%4)+i,
 // 512 columns x 32 bit each = 256 doubles per thread), with a 12-cycle load latency.  Moving
 // k1..k5 (330 columns) plus a 66-column scratch vector there leaves q + A = 2064 B per sample in
-// shared memory: 112 samples per SM as 4 warps x 28 lanes — one warp per SM sub-partition.
+// shared memory; with the 32 LU entries that the factorisation never touches (written once by the
+// Jacobian code, read once per triangular solve) also in TMEM it is 1808 B: 128 samples per SM as
+// 4 warps x 32 lanes — one full warp per SM sub-partition (396 + 64 = 460 of the 512 columns used).
 // tcgen05.ld/st are warp-collective (.sync.aligned), so every lane of a warp executes the step
-// (idle lanes on dummy state, their shared-memory stores predicated off).
-#define GYNC_TM_NSLOT 112
-#define GYNC_TM_LPW 28
+// (lanes without a sample run on their stale state).
+#define GYNC_TM_NSLOT 128
+#define GYNC_TM_LPW 32
 #define GYNC_TM_COL_K 0
 #define GYNC_TM_COL_V (5 * 2 * GYNC_NY)
+#define GYNC_TM_COL_TAIL (6 * 2 * GYNC_NY)   /* the 32 LU entries the factorisation never touches (GYNC_NLU_BODY..) */
 
 // Lanes 28..31 of each warp have no shared-memory slot of their own.  They MIRROR lanes 24..27:
 // same sample index, same inputs, same instruction stream, hence bit-identical values — so they
@@ -165,6 +168,23 @@ __device__ __forceinline__ GyncSmViewRO<NSLOT> gync_sm_ro(const double* p) {
 
 template <int B>
 __device__ __forceinline__ GyncSmViewRO<B> gync_ro(const GyncSmView<B>& v) { return gync_sm_ro<B>(v.p); }
+
+// LU storage of the TMEM layout: body [0, GYNC_NLU_BODY) in shared memory, tail in tensor memory.
+template <int NSLOT>
+struct GyncSmViewT {
+  double* p;
+  uint32_t tm;     // TMEM address of this warp's lane quadrant, column 0
+  __device__ __forceinline__ GyncSmRef operator[](int i) const { return GyncSmRef{p + i * NSLOT}; }
+};
+template <int NSLOT>
+struct GyncSmViewROT {
+  uint32_t sa, tm;
+  __device__ __forceinline__ double operator[](int i) const {
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(sa + (uint32_t)(i * NSLOT * 8)));
+    return v;
+  }
+};
 
 #define TM_R16(r) "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), \
                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
@@ -210,11 +230,34 @@ __device__ __forceinline__ void gync_tm_store_vec(uint32_t ta, const double* v) 
   gync_tm_wait_st();
 }
 
+// tail chunk c (8 doubles = 16 columns) of the LU storage: overloads of the generated code's hooks
+template <int NSLOT>
+__device__ __forceinline__ void gync_tail_store8(GyncSmViewT<NSLOT>& A, const int c, const double v0, const double v1,
+                                                 const double v2, const double v3, const double v4, const double v5,
+                                                 const double v6, const double v7) {
+  const double v[8] = {v0, v1, v2, v3, v4, v5, v6, v7};
+  gync_tm_st8(A.tm + GYNC_TM_COL_TAIL + 16 * c, v);
+  gync_tm_wait_st();     // chunks are emitted in the order their values become available, not by index
+}
+template <int NSLOT>
+__device__ __forceinline__ void gync_tail_load8(const GyncSmViewROT<NSLOT>& A, const int c, double (&v)[8]) {
+  gync_tm_ld8(A.tm + GYNC_TM_COL_TAIL + 16 * c, v);
+}
+template <int NSLOT>
+__device__ __forceinline__ void gync_tail_load8(const GyncSmViewT<NSLOT>& A, const int c, double (&v)[8]) {   // during the LU
+  gync_tm_ld8(A.tm + GYNC_TM_COL_TAIL + 16 * c, v);
+}
+template <int NSLOT>
+__device__ __forceinline__ GyncSmViewROT<NSLOT> gync_ro(const GyncSmViewT<NSLOT>& A) {
+  return GyncSmViewROT<NSLOT>{gync_sm_ro<NSLOT>(A.p).sa, A.tm};
+}
+
 struct GyncWorkTm {
-  GyncSmViewP<GYNC_TM_NSLOT> q, A;
+  GyncSmViewP<GYNC_TM_NSLOT> q;
+  GyncSmViewT<GYNC_TM_NSLOT> A;
   double y[GYNC_NY], yn[GYNC_NY], e[GYNC_NY];
   uint32_t tm;   // TMEM address of this warp's lane quadrant, column 0
-  static constexpr size_t kSmemBytes = sizeof(double) * (GYNC_NQ + GYNC_NLU) * GYNC_TM_NSLOT;
+  static constexpr size_t kSmemBytes = sizeof(double) * (GYNC_NQ + GYNC_NLU_BODY) * GYNC_TM_NSLOT;
 };
 
 // RODAS4 step with k in TMEM (same arithmetic as gync_rodas4_step up to the order of the stage
@@ -227,7 +270,7 @@ __device__ __forceinline__ double gync_rodas4_step_tm(GyncWorkTm& W, const doubl
   GYNC_TICK(0)
   gync_lu(W.A);
   GYNC_TICK(1)
-  gync_lusolve(gync_sm_ro<GYNC_TM_NSLOT>(W.A.p), W.e);
+  gync_lusolve(gync_ro(W.A), W.e);
   GYNC_TICK(2)
 #pragma unroll 1
   for (int s = 0; s < 5; ++s) {
@@ -262,7 +305,7 @@ __device__ __forceinline__ double gync_rodas4_step_tm(GyncWorkTm& W, const doubl
     }
     W.e[32] = fma(ih, gync_tm_ld1(W.tm + GYNC_TM_COL_V + 64), W.e[32]);
     GYNC_TICK(5)
-    gync_lusolve(gync_sm_ro<GYNC_TM_NSLOT>(W.A.p), W.e);
+    gync_lusolve(gync_ro(W.A), W.e);
     GYNC_TICK(2)
   }
   double sum = 0.0;
@@ -297,12 +340,13 @@ gync_loglik_tm_kernel(const double* __restrict__ X, int64_t N, const double* __r
   const uint32_t tmem_base = s_tmem;
 
   const bool real = lane < GYNC_TM_LPW;                    // lanes 28..31 mirror lanes 24..27
-  const int src_lane = real ? lane : lane - 4;
+  const int src_lane = real ? lane : lane - (32 - GYNC_TM_LPW);
   GyncWorkTm W;
   const int slot = warp * GYNC_TM_LPW + src_lane;
   W.q.p = gync_sm + slot;
   W.A.p = gync_sm + (size_t)GYNC_NQ * GYNC_TM_NSLOT + slot;
   W.tm = tmem_base + ((uint32_t)(warp * 32) << 16);
+  W.A.tm = W.tm;
 #pragma unroll
   for (int i = 0; i < GYNC_NY; ++i) { W.y[i] = 1.0; W.yn[i] = 1.0; W.e[i] = 0.0; }
 
