@@ -93,8 +93,37 @@ int launch_loglik(const double* dX, int64_t N, const double* d_data, const doubl
 // EM launch helpers (templates: outside extern "C")
 namespace {
 
+// L resident in shared memory (one pass over HBM for the whole call) when the rows fit: one CTA per SM.
+template <int MH, bool FULL>
+int em_resident_try(double* dw, const double* dL, int64_t K, int M, int niter, double* d_hist, cudaStream_t s, bool* done) {
+  *done = false;
+  if (getenv("GYNC_EM_NO_RESIDENT")) return GYNC_OK;
+  const int nb = g_num_sms;
+  const int64_t R = (K + nb - 1) / nb;
+  const size_t smem = sizeof(double) * (size_t)M * R + sizeof(EmSmem<MH>) + 16;
+  int max_optin = 0;
+  CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, g_device));
+  if (smem > (size_t)max_optin || niter < 2) return GYNC_OK;      // does not fit (or not worth the load): stream from HBM
+  CK(cudaFuncSetAttribute(gync_em_resident_kernel<MH, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gync_em_resident_kernel<MH, FULL>, GYNC_EM_THREADS, smem));
+  if (per_sm < 1) return GYNC_OK;
+  double* partials = nullptr;
+  CK(cudaMallocAsync((void**)&partials, sizeof(double) * 2 * nb * 2 * MH, s));
+  int Ri = (int)R;
+  void* args[] = {&dw, &dL, &K, &M, &niter, &Ri, &partials, &d_hist};
+  CK(cudaLaunchCooperativeKernel((void*)gync_em_resident_kernel<MH, FULL>, dim3(nb), dim3(GYNC_EM_THREADS), args, smem, s));
+  g_launches += 1;
+  CK(cudaFreeAsync(partials, s));
+  *done = true;
+  return GYNC_OK;
+}
+
 template <int MH, bool FULL>
 int em_persistent_launch(double* dw, const double* dL, int64_t K, int M, int niter, double* d_hist, cudaStream_t s) {
+  bool done = false;
+  if (int rc = em_resident_try<MH, FULL>(dw, dL, K, M, niter, d_hist, s, &done)) return rc;
+  if (done) return GYNC_OK;
   int per_sm = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gync_em_persistent_kernel<MH, FULL>, GYNC_EM_THREADS, 0));
   if (per_sm < 1) return fail(GYNC_ERR_CUDA, "EM kernel does not fit on an SM");

@@ -659,6 +659,66 @@ gync_em_persistent_kernel(double* __restrict__ w, const double* __restrict__ L, 
 }
 
 // ------------------------------------------------------------------------------------------
+// K4, resident variant: when this GPU's part of L fits in shared memory (K*M*8 B <= ~148 x 217 KB =
+// 32 MB, e.g. BASELINE cfg 3: 10^5 x 40) every CTA loads its rows ONCE and all iterations run out of
+// shared memory — HBM is out of the loop; an iteration costs one pass over 216 KB of shared memory
+// per SM plus the grid barrier and the partial gather.  Layout in shared memory: [column][row], so a
+// half-warp reads 16 consecutive rows of one column (conflict-free).
+template <int MH, bool FULL>
+__global__ void __launch_bounds__(GYNC_EM_THREADS, 1)
+gync_em_resident_kernel(double* __restrict__ w, const double* __restrict__ L, int64_t K, int M, int niter, int rows_per_block,
+                        double* __restrict__ partials /* 2 x gridDim.x x 2MH */, double* __restrict__ history) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ double em_dyn[];            // [M][rows_per_block] then EmSmem
+  constexpr int MT = 2 * MH;
+  const int R = rows_per_block;
+  double* sL = em_dyn;
+  EmSmem<MH>& sm = *reinterpret_cast<EmSmem<MH>*>(em_dyn + (size_t)M * R);
+  const int nb = gridDim.x;
+  const int64_t row0 = (int64_t)blockIdx.x * R;
+  const int nrows = (int)max((int64_t)0, min((int64_t)R, K - row0));
+  for (int m = 0; m < M; ++m)                    // coalesced: consecutive threads read consecutive rows of column m
+    for (int r = threadIdx.x; r < nrows; r += GYNC_EM_THREADS) sL[(size_t)m * R + r] = __ldg(L + row0 + r + K * (int64_t)m);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = lane >> 4, rl = lane & 15;
+  const double invM = 1.0 / (double)M;
+  for (int it = -1; it < niter; ++it) {
+    if (it >= 0) em_gather_partials<MH>(partials + (size_t)(it & 1) * nb * MT, nb, M, sm, sm.rinv, true);
+    double acc[MH];
+#pragma unroll
+    for (int j = 0; j < MH; ++j) acc[j] = 0.0;
+    const double* ri = sm.rinv + half * MH;
+    for (int rb = warp * 16; rb < nrows; rb += GYNC_EM_WARPS * 16) {     // warp-uniform (the shuffle needs all lanes)
+      const int r = rb + rl;
+      const bool valid = r < nrows;
+      const double* p = sL + (size_t)(half * MH) * R + (valid ? r : 0);
+      double l[MH];
+#pragma unroll
+      for (int j = 0; j < MH; ++j) l[j] = (valid && (FULL || half * MH + j < M)) ? p[(size_t)j * R] : 0.0;
+      double wk = valid ? w[row0 + r] : 0.0;
+      if (it >= 0) {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int j = 0; j + 1 < MH; j += 2) { s0 = fma(l[j], ri[j], s0); s1 = fma(l[j + 1], ri[j + 1], s1); }
+        if (MH & 1) s0 = fma(l[MH - 1], ri[MH - 1], s0);
+        double s = s0 + s1;
+        s += __shfl_xor_sync(0xffffffffu, s, 16);
+        wk = wk * invM * s;
+        if (valid && half == 0) {
+          w[row0 + r] = wk;
+          if (history) history[(size_t)it * K + row0 + r] = wk;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < MH; ++j) acc[j] = fma(l[j], wk, acc[j]);
+    }
+    em_block_reduce<MH>(acc, sm, partials + (size_t)((it + 1) & 1) * nb * MT + (size_t)blockIdx.x * MT, M);
+    __threadfence();
+    grid.sync();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // K4 across GPUs as ONE kernel: compute step + the allreduce of the M denominators fused over
 // NVLink peer memory.  Every rank runs this persistent cooperative kernel on its row shard.  Per
 // iteration: local fused pass -> grid barrier -> block 0 sums the block partials and STORES the M
