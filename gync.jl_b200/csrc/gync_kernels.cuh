@@ -556,16 +556,17 @@ __device__ __forceinline__ void em_gather_partials(const double* __restrict__ pa
   constexpr int MT = 2 * MH, NG = GYNC_EM_THREADS / MT;
   const int m = threadIdx.x % MT, g = threadIdx.x / MT;
   if (g < NG) {
-    double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
-    int b = g;
-    for (; b + 3 * NG < nb; b += 4 * NG) {      // independent loads in flight
-      v0 += __ldcg(partials + (size_t)b * MT + m);
-      v1 += __ldcg(partials + (size_t)(b + NG) * MT + m);
-      v2 += __ldcg(partials + (size_t)(b + 2 * NG) * MT + m);
-      v3 += __ldcg(partials + (size_t)(b + 3 * NG) * MT + m);
+    // up to 16 independent loads in flight per thread (fixed summation order)
+    double v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int b = g + u * NG;
+      v[u] = (b < nb) ? __ldcg(partials + (size_t)b * MT + m) : 0.0;
     }
-    for (; b < nb; b += NG) v0 += __ldcg(partials + (size_t)b * MT + m);
-    sm.grp[g * MT + m] = (v0 + v1) + (v2 + v3);
+    double acc = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+    acc += ((v[8] + v[9]) + (v[10] + v[11])) + ((v[12] + v[13]) + (v[14] + v[15]));
+    for (int b = g + 16 * NG; b < nb; b += NG) acc += __ldcg(partials + (size_t)b * MT + m);
+    sm.grp[g * MT + m] = acc;
   }
   __syncthreads();
   if (threadIdx.x < MT) {
@@ -646,14 +647,12 @@ gync_em_persistent_kernel(double* __restrict__ w, const double* __restrict__ L, 
   constexpr int MT = 2 * MH;
   const int nb = gridDim.x;
   em_norms_pass<MH, FULL>(w, L, K, M, sm, partials + (size_t)blockIdx.x * MT);
-  __threadfence();
-  grid.sync();
+  grid.sync();          // cooperative-groups grid barrier orders the partials written above
   for (int it = 0; it < niter; ++it) {
     const double* pin = partials + (size_t)(it & 1) * nb * MT;
     double* pout = partials + (size_t)((it + 1) & 1) * nb * MT;
     em_gather_partials<MH>(pin, nb, M, sm, sm.rinv, true);
     em_step_pass<MH, FULL>(w, L, K, M, sm, pout + (size_t)blockIdx.x * MT, history ? history + (size_t)it * K : nullptr);
-    __threadfence();
     grid.sync();
   }
 }
@@ -713,7 +712,6 @@ gync_em_resident_kernel(double* __restrict__ w, const double* __restrict__ L, in
       for (int j = 0; j < MH; ++j) acc[j] = fma(l[j], wk, acc[j]);
     }
     em_block_reduce<MH>(acc, sm, partials + (size_t)((it + 1) & 1) * nb * MT + (size_t)blockIdx.x * MT, M);
-    __threadfence();
     grid.sync();
   }
 }
