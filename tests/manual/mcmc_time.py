@@ -1,6 +1,6 @@
 import os, sys, time, json
 import numpy as np
-ROOT = "/root/repo" if os.path.exists("/root/repo/bench.py") else os.getcwd()
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import gync_b200 as g
 from gync_b200 import lib as L

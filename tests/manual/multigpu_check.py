@@ -1,10 +1,10 @@
 """Multi-GPU parity check (run under torchrun on a box with >= 2 GPUs):
-   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/multigpu_check.py
+   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/manual/multigpu_check.py
 Sharded EM through (a) step kernels + NCCL allreduce and (b) the fused peer-memory kernel must both equal the
 unsharded oracle to 1e-10; sharded likelihood batches must equal the single-GPU result bit for bit."""
 import os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import torch, torch.distributed as dist
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])

@@ -4,7 +4,7 @@
  (C) BASELINE configs[0]: sample(Config(), 1000) single chain;  configs[3] scaled: 4096 chains x 20 iterations"""
 import os, sys, time, json
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import gync_b200 as g
 from gync_b200 import lib as L

@@ -243,7 +243,7 @@ def test_em_sharded_step_kernels(gpu):
 
 def test_em_fused_kernel_world1(gpu):
     """The fused compute+exchange kernel with a single rank (mailbox = local memory): same numbers
-    as the oracle.  The multi-rank exchange is exercised by tools/multigpu_check.py under torchrun."""
+    as the oracle.  The multi-rank exchange is exercised by tests/manual/multigpu_check.py under torchrun."""
     import torch
     import gync_oracle as o
     from gync_b200.dist import FusedEM

@@ -2,15 +2,15 @@
 import ctypes as C, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, ROOT)
 import torch
 import gync_b200 as g
 from gync_b200 import lib as L
-import gync_oracle as o
 lib = L.load(); L.check(lib.gync_init(0))
 N = int(os.environ.get("N", 9472)); rtol = float(os.environ.get("RTOL", 1e-8)); atol = float(os.environ.get("ATOL", 1e-8))
 rng = np.random.default_rng(20160911 + 2)
-X = np.exp(np.log(o.init_x())[None, :] + 0.0998 * rng.standard_normal((N, 116)))
+x0 = np.concatenate([g.api.refparms, g.api.refy0, [28.0]])
+X = np.exp(np.log(x0)[None, :] + 0.0998 * rng.standard_normal((N, 116)))
 c = g.Config()
 dX = torch.from_numpy(np.asfortranarray(X).T.copy()).cuda()
 dD = torch.from_numpy(np.asfortranarray(c.data).T.copy()).cuda()
