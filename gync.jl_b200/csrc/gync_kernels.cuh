@@ -35,10 +35,11 @@ __global__ void gync_prep_patients_kernel(const double* __restrict__ data, const
 // LU factors A[165], five RODAS stage vectors, y/y_new/work vector) — four times what a thread
 // can hold in registers, and local-memory spills of that size miss L1 and serialise on L2
 // latency (measured: 14 k solves/s).  So the big arrays live in SHARED memory, interleaved
-// [element][thread] (a warp touches 32 consecutive doubles: conflict-free), with exactly
-// GYNC_SOLVE_BLOCK threads per SM and one CTA per SM (216.6 KB of the 227 KB), and the small
-// hot vectors (y, y_new, work) in registers.  The straight-line generated code indexes every
-// array with compile-time constants, so each access is one LDS/STS with an immediate offset.
+// [element][thread] (a warp touches 32 consecutive doubles: conflict-free), and the small hot
+// vectors (y, y_new, work) in registers.  The straight-line generated code indexes every array
+// with compile-time constants, so each access is one LDS/STS with an immediate offset.
+// GyncWorkSm keeps everything in shared memory (64 samples per CTA: 216.6 KB of the 227 KB) and is
+// used by the generic time-grid kernel; the likelihood kernel uses the TMEM layout further down.
 #ifndef GYNC_SOLVE_BLOCK
 #define GYNC_SOLVE_BLOCK 64
 #endif
@@ -60,11 +61,7 @@ struct GyncSmView {
   __device__ __forceinline__ GyncSmRef operator[](int i) const { return GyncSmRef{p + i * BLOCK}; }
 };
 
-// BLOCK = sample slots per CTA.  LPW = active lanes per warp: the solver is bound by per-warp
-// latency (dependent FP64 chains, shared-memory loads, instruction fetch of ~12 k straight-line
-// instructions per step), not by FP64 issue, and shared memory caps an SM at 64 samples — so
-// the 64 samples are spread over 32/LPW times as many warps, each running LPW lanes, to give
-// every SM sub-partition more warps to interleave.
+// BLOCK = sample slots per CTA (one thread each).
 template <int BLOCK>
 struct GyncWorkSm {
   GyncSmView<BLOCK> q, k, A;
@@ -133,11 +130,12 @@ struct GyncLlhSink {
 #define GYNC_TM_COL_V (5 * 2 * GYNC_NY)
 #define GYNC_TM_COL_TAIL (6 * 2 * GYNC_NY)   /* the 32 LU entries the factorisation never touches (GYNC_NLU_BODY..) */
 
-// Lanes 28..31 of each warp have no shared-memory slot of their own.  They MIRROR lanes 24..27:
-// same sample index, same inputs, same instruction stream, hence bit-identical values — so they
-// may issue the same shared-memory stores to the same addresses (benign same-value races) and no
-// store needs a predicate (predicated stores turned into branches that chopped the straight-line
-// LU / Jacobian code into small basic blocks).  Only real lanes touch global memory.
+// If GYNC_TM_LPW < 32 the upper lanes of each warp have no shared-memory slot of their own (an earlier
+// layout ran 28 samples per warp).  They then MIRROR the top real lanes: same sample index, same inputs,
+// same instruction stream, hence bit-identical values — so they may issue the same shared-memory stores
+// to the same addresses (benign same-value races) and no store needs a predicate (predicated stores
+// turned into branches that chopped the straight-line LU / Jacobian code into small basic blocks and
+// caused spills).  Only real lanes touch global memory.  With GYNC_TM_LPW == 32 every lane is real.
 template <int NSLOT>
 struct GyncSmViewP {
   double* p;
@@ -339,7 +337,7 @@ gync_loglik_tm_kernel(const double* __restrict__ X, int64_t N, const double* __r
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = s_tmem;
 
-  const bool real = lane < GYNC_TM_LPW;                    // lanes 28..31 mirror lanes 24..27
+  const bool real = lane < GYNC_TM_LPW;                    // lanes >= LPW (none at LPW = 32) mirror the top real lanes
   const int src_lane = real ? lane : lane - (32 - GYNC_TM_LPW);
   GyncWorkTm W;
   const int slot = warp * GYNC_TM_LPW + src_lane;
