@@ -122,38 +122,49 @@ int gync_mcmc_run(double* state, double* logf, int64_t C, const double* chol, do
   return GYNC_OK;
 }
 
+int gync_wc_normalize_dev(double* dLL_inout, const double* d_logprior, const int64_t* d_counts, int64_t K, int32_t M,
+                          double* d_weights, double* d_density, void* stream) {
+  if (K < 1 || M < 1 || !dLL_inout || !d_logprior || !d_counts || !d_weights || !d_density)
+    return fail(GYNC_ERR_ARG, "gync_wc_normalize: bad arguments");
+  if (int rc = ensure_init()) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nb = g_num_sms * 4;
+  double* scratch = nullptr;      // colsum[M] | scal[2] | partial[nb]
+  CK(cudaMallocAsync((void**)&scratch, sizeof(double) * (M + 2 + nb), s));
+  double* dCs = scratch;
+  double* dSc = scratch + M;
+  double* dPart = scratch + M + 2;
+  gync_wc_colpass_kernel<<<M + 2, GYNC_WC_THREADS, 0, s>>>(dLL_inout, d_logprior, (const long long*)d_counts, K, M, dLL_inout, dCs, dSc);
+  gync_wc_rowpass_kernel<<<nb, 256, 0, s>>>(dLL_inout, d_logprior, (const long long*)d_counts, K, M, dCs, dSc, d_weights, d_density, dPart);
+  gync_wc_scale_kernel<<<nb, 256, 0, s>>>(d_density, K, dPart, nb);
+  g_launches += 3;
+  CK(cudaGetLastError());
+  CK(cudaFreeAsync(scratch, s));
+  return GYNC_OK;
+}
+
 int gync_wc_normalize(const double* LL, const double* logprior, const int64_t* counts, int64_t K, int32_t M,
                       double* L, double* weights, double* density) {
   if (K < 1 || M < 1 || !LL || !logprior || !counts || !L || !weights || !density)
     return fail(GYNC_ERR_ARG, "gync_wc_normalize: bad arguments");
   if (int rc = ensure_init()) return rc;
-  DBuf dLL, dLp, dCn, dW, dDn, dCs, dSc, dPart;
-  const int nb = g_num_sms * 4;
+  DBuf dLL, dLp, dCn, dW, dDn;
   CK(dLL.alloc(sizeof(double) * K * M));
   CK(dLp.alloc(sizeof(double) * K));
   CK(dCn.alloc(sizeof(long long) * K));
   CK(dW.alloc(sizeof(double) * K));
   CK(dDn.alloc(sizeof(double) * K));
-  CK(dCs.alloc(sizeof(double) * M));
-  CK(dSc.alloc(sizeof(double) * 2));
-  CK(dPart.alloc(sizeof(double) * nb));
   CK(cudaMemcpyAsync(dLL.p, LL, sizeof(double) * K * M, cudaMemcpyHostToDevice, g_stream));
   CK(cudaMemcpyAsync(dLp.p, logprior, sizeof(double) * K, cudaMemcpyHostToDevice, g_stream));
   CK(cudaMemcpyAsync(dCn.p, counts, sizeof(long long) * K, cudaMemcpyHostToDevice, g_stream));
-  gync_wc_colpass_kernel<<<M + 2, GYNC_WC_THREADS, 0, g_stream>>>(dLL.as<double>(), dLp.as<double>(), dCn.as<long long>(), K, M,
-                                                                  dLL.as<double>(), dCs.as<double>(), dSc.as<double>());
-  gync_wc_rowpass_kernel<<<nb, 256, 0, g_stream>>>(dLL.as<double>(), dLp.as<double>(), dCn.as<long long>(), K, M, dCs.as<double>(),
-                                                   dSc.as<double>(), dW.as<double>(), dDn.as<double>(), dPart.as<double>());
-  gync_wc_scale_kernel<<<nb, 256, 0, g_stream>>>(dDn.as<double>(), K, dPart.as<double>(), nb);
-  g_launches += 3;
-  CK(cudaGetLastError());
+  if (int rc = gync_wc_normalize_dev(dLL.as<double>(), dLp.as<double>(), dCn.as<int64_t>(), K, M, dW.as<double>(),
+                                     dDn.as<double>(), g_stream)) return rc;
   CK(cudaMemcpyAsync(L, dLL.p, sizeof(double) * K * M, cudaMemcpyDeviceToHost, g_stream));
   CK(cudaMemcpyAsync(weights, dW.p, sizeof(double) * K, cudaMemcpyDeviceToHost, g_stream));
   CK(cudaMemcpyAsync(density, dDn.p, sizeof(double) * K, cudaMemcpyDeviceToHost, g_stream));
   CK(cudaStreamSynchronize(g_stream));
   return GYNC_OK;
 }
-
 
 // ------------------------------------------------------------------------------------------
 // Fused multi-GPU EM: mailboxes in cudaMalloc'd memory exported with cudaIpc, so that each rank's

@@ -40,7 +40,7 @@ EXPORTS = [
     "gync_logprior_batch", "gync_mcmc_run", "gync_em_iterate", "gync_em_iterate_dev",
     "gync_em_norms_dev", "gync_em_step_dev", "gync_launch_count", "gync_wc_normalize", "gync_fp64_peak",
     "gync_flops_per_step", "gync_em_comm_create", "gync_em_comm_connect", "gync_em_comm_destroy",
-    "gync_em_iterate_fused_dev", "gync_em_comm_error",
+    "gync_em_iterate_fused_dev", "gync_em_comm_error", "gync_wc_normalize_dev",
 ]
 
 _lib = None
@@ -79,6 +79,7 @@ def load():
     lib.gync_wc_normalize.argtypes = [c_double_p, c_double_p, c_int64_p, C.c_int64, C.c_int32, c_double_p,
                                       c_double_p, c_double_p]
     lib.gync_fp64_peak.argtypes = [c_double_p]
+    lib.gync_wc_normalize_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.gync_flops_per_step.restype = C.c_double
     lib.gync_em_comm_create.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]
     lib.gync_em_comm_connect.argtypes = [C.c_void_p, C.c_void_p]

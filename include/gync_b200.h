@@ -136,6 +136,9 @@ int64_t gync_launch_count(void);
  * logprior: K, counts: K (int64) -> weights = counts/sum, density = rowmean(L).*exp(lp-max), normalised. */
 int gync_wc_normalize(const double* LL, const double* logprior, const int64_t* counts, int64_t K, int32_t M,
                       double* L, double* weights, double* density);
+/* device-resident form: dLL is normalised in place (LL -> L), so K1 -> K5 -> K4 never leave HBM */
+int gync_wc_normalize_dev(double* dLL_inout, const double* d_logprior, const int64_t* d_counts, int64_t K, int32_t M,
+                          double* d_weights, double* d_density, void* stream);
 
 /* FP64 flops of one RODAS4 step attempt (counted from the generated code; roofline bookkeeping). */
 double gync_flops_per_step(void);
