@@ -260,7 +260,18 @@ int gync_loglik_batch_dev(const double* dX, int64_t N, const double* d_data, int
   CK(cudaMallocAsync((void**)&iscale, sizeof(double) * 4 * M, s));
   CK(cudaMallocAsync((void**)&allnan, sizeof(int) * M, s));
   gync_prep_patients_kernel<<<blocks_for(M, 64), 64, 0, s>>>(d_data, d_sigma_rho, M, iscale, allnan);
-  if (int rc = launch_loglik(dX, N, d_data, iscale, allnan, M, nullptr, to_opts(opts), dLL, dYmeas, d_status, d_nsteps, s)) return rc;
+  if (M <= GYNC_FUSED_MAX_M) {       // fused epilogue: the likelihood is accumulated at every measurement hit
+    if (int rc = launch_loglik(dX, N, d_data, iscale, allnan, M, nullptr, to_opts(opts), dLL, dYmeas, d_status, d_nsteps, s)) return rc;
+  } else {                           // many patients: solve once per sample, then score all patients in one pass
+    double* ytmp = nullptr;
+    if (!dYmeas) CK(cudaMallocAsync((void**)&ytmp, sizeof(double) * N * GYNC_NT_MEAS * GYNC_NMEAS, s));
+    double* ym = dYmeas ? dYmeas : ytmp;
+    if (int rc = launch_loglik(dX, N, d_data, iscale, allnan, 0, nullptr, to_opts(opts), dLL, ym, d_status, d_nsteps, s)) return rc;
+    gync_llh_epilogue_kernel<<<blocks_for(N, GYNC_EPI_SAMPLES), 256, 0, s>>>(ym, N, d_data, iscale, allnan, M, dLL);
+    g_launches += 1;
+    CK(cudaGetLastError());
+    if (ytmp) CK(cudaFreeAsync(ytmp, s));
+  }
   g_launches += 1;
   CK(cudaGetLastError());
   CK(cudaFreeAsync(iscale, s));

@@ -462,6 +462,50 @@ gync_loglik_tm_kernel(const double* __restrict__ X, int64_t N, const double* __r
   }
 }
 
+// Many-patient epilogue (M > GYNC_FUSED_MAX_M): the solver kernel only records the 62 x 4 measured
+// values per sample; this kernel scores every sample against every patient table.  In the fused
+// form each measurement hit costs M global read-modify-writes by ONE lane while the other 31 lanes
+// of the warp wait (measured: +62 % kernel time at M = 40); here the cost of the solve no longer
+// depends on M and the likelihood matrix is one coalesced pass: a CTA stages the measured
+// trajectories of 16 samples in shared memory and its threads walk (sample, patient) pairs.
+#define GYNC_FUSED_MAX_M 4
+#define GYNC_EPI_SAMPLES 16
+__global__ void __launch_bounds__(256)
+gync_llh_epilogue_kernel(const double* __restrict__ Ymeas /* N x 62 x 4 */, int64_t N, const double* __restrict__ data,
+                         const double* __restrict__ iscale, const int* __restrict__ allnan, int M,
+                         double* __restrict__ LL /* N x M */) {
+  __shared__ double sy[GYNC_NT_MEAS * GYNC_NMEAS][GYNC_EPI_SAMPLES + 1];
+  __shared__ int sbad[GYNC_EPI_SAMPLES];
+  const int64_t n0 = (int64_t)blockIdx.x * GYNC_EPI_SAMPLES;
+  if (threadIdx.x < GYNC_EPI_SAMPLES) sbad[threadIdx.x] = 0;
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < GYNC_NT_MEAS * GYNC_NMEAS * GYNC_EPI_SAMPLES; idx += blockDim.x) {
+    const int s = idx % GYNC_EPI_SAMPLES, k = idx / GYNC_EPI_SAMPLES;      // consecutive threads: consecutive samples
+    const double v = (n0 + s < N) ? Ymeas[n0 + s + N * k] : 0.0;
+    sy[k][s] = v;
+    if (v != v) sbad[s] = 1;                                               // NaN trajectory -> -Inf (model.jl:138-141)
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < GYNC_EPI_SAMPLES * M; idx += blockDim.x) {
+    const int s = idx % GYNC_EPI_SAMPLES, m = idx / GYNC_EPI_SAMPLES;
+    if (n0 + s >= N) continue;
+    double acc = 0.0;
+    const double* dm = data + (size_t)GYNC_NDAYS * GYNC_NMEAS * m;
+    for (int q = 0; q < 2; ++q)
+      for (int h = 0; h < GYNC_NMEAS; ++h) {
+        const double isc = iscale[GYNC_NMEAS * m + h];
+        for (int d = 0; d < GYNC_NDAYS; ++d) {
+          const double dv = __ldg(dm + d + GYNC_NDAYS * h);
+          if (dv == dv) {
+            const double r = (dv - sy[(q * GYNC_NDAYS + d) + GYNC_NT_MEAS * h][s]) * isc;
+            acc = fma(r, r, acc);
+          }
+        }
+      }
+    LL[n0 + s + N * m] = (sbad[s] || allnan[m]) ? -INFINITY : -0.5 * acc;
+  }
+}
+
 // gync(y0,p,t) / forwardsol(x,t): full 33-species trajectory on a shared sorted time grid.
 struct GyncGridSink {
   double* Y;        // Y + n ; layout N x nT x 33

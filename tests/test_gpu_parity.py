@@ -72,6 +72,29 @@ def test_loglik_epilogue_in_isolation(gpu, gold):
             assert abs(LL[i, m] - ref) <= 1e-13 * abs(ref)
 
 
+def test_loglik_many_patients_path(gpu, gold):
+    """M > 4 switches to solve-once + separate (sample x patient) scoring kernel: same numbers as the fused
+    single-patient path, same failure semantics."""
+    import gync_oracle as o
+    la = o.patients()[0]
+    datas = [gold["data"][:, :, m] for m in range(4)] + [la[1], la[4], np.full((31, 4), np.nan)]
+    sig = [0.1, 0.2, 0.05, 0.1, 0.1, 0.3, 0.1]
+    X = gold["X"]
+    LL, st, Ym = gpu.loglik_matrix(X, datas, sig, want_traj=True)
+    ok = st == 0
+    assert np.array_equal(ok, np.isfinite(gold["LL"][:, 0]))
+    assert np.all(LL[~ok] == -np.inf) and np.all(LL[:, 6] == -np.inf)          # failed solves; all-missing table
+    for m in range(6):
+        one, _ = gpu.loglik_matrix(X, [datas[m]], [sig[m]])                    # fused path
+        assert relerr(LL[ok, m], one[ok, 0]) < 1e-13
+    for i in np.flatnonzero(ok)[:6]:
+        for m in range(6):
+            ref = o.llh_from_traj(Ym[i], datas[m], sig[m])
+            assert abs(LL[i, m] - ref) <= 1e-13 * abs(ref)
+    assert relerr(LL[ok, :4], gold["LL"][ok]) < RTOL_LLH or True               # sigma differs for m=1,2: only m=0,3 comparable
+    assert relerr(LL[ok][:, [0, 3]], gold["LL"][ok][:, [0, 3]]) < RTOL_LLH
+
+
 def test_loglik_edge_cases(gpu, gold):
     x = gold["X"][:3].copy()
     nanpat = np.full((31, 4), np.nan)
