@@ -129,7 +129,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb, ms = cpu_reference_leg(args.steps, args.warmup, budget_s=30.0)
+    cb, ms = cpu_reference_leg(args.steps, args.warmup, budget_s=float(os.environ.get("GYNC_BENCH_CPU_BUDGET", 30.0)))
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args.gpus),

@@ -36,6 +36,15 @@ int ensure_init() {
   return gync_init(0);
 }
 
+// RAII stream-ordered temporary (freed on every exit path)
+struct ABuf {
+  void* p = nullptr;
+  cudaStream_t s = nullptr;
+  ~ABuf() { if (p) cudaFreeAsync(p, s); }
+  cudaError_t alloc(size_t bytes, cudaStream_t st) { s = st; return cudaMallocAsync(&p, bytes ? bytes : 8, st); }
+  template <class T> T* as() { return static_cast<T*>(p); }
+};
+
 // RAII device buffer
 struct DBuf {
   void* p = nullptr;
@@ -75,8 +84,9 @@ namespace {
 int launch_loglik(const double* dX, int64_t N, const double* d_data, const double* iscale, const int* allnan, int M,
                   const int* pat, const GyncSolverOpts& so, double* dLL, double* dYmeas, int32_t* d_status,
                   int32_t* d_nsteps, cudaStream_t s) {
-  unsigned long long* counter = nullptr;
-  CK(cudaMallocAsync((void**)&counter, sizeof(unsigned long long), s));
+  ABuf cnt;
+  CK(cnt.alloc(sizeof(unsigned long long), s));
+  unsigned long long* counter = cnt.as<unsigned long long>();
   CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), s));
   if (int rc = prep_solver_kernel(gync_loglik_tm_kernel, GyncWorkTm::kSmemBytes, 128)) return rc;
   const int64_t want = (N + GYNC_TM_NSLOT - 1) / GYNC_TM_NSLOT;
@@ -85,7 +95,6 @@ int launch_loglik(const double* dX, int64_t N, const double* d_data, const doubl
                                                                 d_status, d_nsteps, counter);
   g_launches += 1;
   CK(cudaGetLastError());
-  CK(cudaFreeAsync(counter, s));
   return GYNC_OK;
 }
 }  // namespace
@@ -242,6 +251,7 @@ int gync_init(int device) {
 }
 
 void gync_shutdown(void) {
+  if (g_em_scratch.partials) { cudaFree(g_em_scratch.partials); g_em_scratch.partials = nullptr; g_em_scratch.doubles = 0; }
   if (g_stream) { cudaStreamDestroy(g_stream); g_stream = nullptr; }
   g_device = -1;
 }
@@ -255,27 +265,24 @@ int gync_loglik_batch_dev(const double* dX, int64_t N, const double* d_data, int
   if (int rc = ensure_init()) return rc;
   if (N == 0) return GYNC_OK;
   cudaStream_t s = (cudaStream_t)stream;   // NULL = the legacy default stream, as torch uses
-  double* iscale = nullptr;
-  int* allnan = nullptr;
-  CK(cudaMallocAsync((void**)&iscale, sizeof(double) * 4 * M, s));
-  CK(cudaMallocAsync((void**)&allnan, sizeof(int) * M, s));
+  ABuf bIsc, bNan, bY;
+  CK(bIsc.alloc(sizeof(double) * 4 * M, s));
+  CK(bNan.alloc(sizeof(int) * M, s));
+  double* iscale = bIsc.as<double>();
+  int* allnan = bNan.as<int>();
   gync_prep_patients_kernel<<<blocks_for(M, 64), 64, 0, s>>>(d_data, d_sigma_rho, M, iscale, allnan);
-  if (M <= GYNC_FUSED_MAX_M) {       // fused epilogue: the likelihood is accumulated at every measurement hit
-    if (int rc = launch_loglik(dX, N, d_data, iscale, allnan, M, nullptr, to_opts(opts), dLL, dYmeas, d_status, d_nsteps, s)) return rc;
-  } else {                           // many patients: solve once per sample, then score all patients in one pass
-    double* ytmp = nullptr;
-    if (!dYmeas) CK(cudaMallocAsync((void**)&ytmp, sizeof(double) * N * GYNC_NT_MEAS * GYNC_NMEAS, s));
-    double* ym = dYmeas ? dYmeas : ytmp;
-    if (int rc = launch_loglik(dX, N, d_data, iscale, allnan, 0, nullptr, to_opts(opts), dLL, ym, d_status, d_nsteps, s)) return rc;
-    gync_llh_epilogue_kernel<<<blocks_for(N, GYNC_EPI_SAMPLES), 256, 0, s>>>(ym, N, d_data, iscale, allnan, M, dLL);
-    g_launches += 1;
-    CK(cudaGetLastError());
-    if (ytmp) CK(cudaFreeAsync(ytmp, s));
-  }
   g_launches += 1;
   CK(cudaGetLastError());
-  CK(cudaFreeAsync(iscale, s));
-  CK(cudaFreeAsync(allnan, s));
+  if (M <= GYNC_FUSED_MAX_M) {       // fused epilogue: the likelihood is accumulated at every measurement hit
+    return launch_loglik(dX, N, d_data, iscale, allnan, M, nullptr, to_opts(opts), dLL, dYmeas, d_status, d_nsteps, s);
+  }
+  // many patients: solve once per sample, then score all (sample, patient) pairs in one pass
+  if (!dYmeas) CK(bY.alloc(sizeof(double) * N * GYNC_NT_MEAS * GYNC_NMEAS, s));
+  double* ym = dYmeas ? dYmeas : bY.as<double>();
+  if (int rc = launch_loglik(dX, N, d_data, iscale, allnan, 0, nullptr, to_opts(opts), dLL, ym, d_status, d_nsteps, s)) return rc;
+  gync_llh_epilogue_kernel<<<blocks_for(N, GYNC_EPI_SAMPLES), 256, 0, s>>>(ym, N, d_data, iscale, allnan, M, dLL);
+  g_launches += 1;
+  CK(cudaGetLastError());
   return GYNC_OK;
 }
 

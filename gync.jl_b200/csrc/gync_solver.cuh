@@ -45,14 +45,6 @@ __device__ __forceinline__ double gync_rcp_dev(double x) {
 #define GYNC_ST_HMIN        2   /* step size underflow */
 #define GYNC_ST_NONFINITE   4   /* non-finite input or state (e.g. negative base of the real power) */
 
-#ifndef GYNC_CONSTANT
-#  ifdef __CUDA_ARCH__
-#    define GYNC_CONSTANT __constant__
-#  else
-#    define GYNC_CONSTANT static const
-#  endif
-#endif
-
 struct GyncSolverOpts {
   double rtol, atol;
   double h0;          // initial step; <=0: automatic

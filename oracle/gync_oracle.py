@@ -190,35 +190,6 @@ def meastimes(days, periods, T):
     return np.concatenate([np.arange(1, days + 1) + T * q for q in range(periods)]).astype(np.float64)
 
 
-def gync(y0, p, t, rtol=1e-4, atol=1e-4, method="BDF"):
-    """gync(y0,p,t;reltol,abstol)  (gyncycle.jl:8-26).
-
-    t sorted; t[0] is the INITIAL time and row 0 is y0 (Sundials.cvode semantics,
-    gyncycle.jl:15).  Any failure -> all-NaN matrix (gyncycle.jl:18-19).
-    Integrator: scipy (CVODE is not available here); `method` in {"BDF","Radau","LSODA"}.
-    """
-    from scipy.integrate import solve_ivp
-    y0 = np.asarray(y0, dtype=np.float64)
-    t = np.asarray(t, dtype=np.float64)
-    nan = np.full((t.size, 33), np.nan)
-    if not np.all(np.isfinite(y0)) or not np.all(np.isfinite(p)):
-        return nan
-    fun = _fast_rhs(p)
-    try:
-        with np.errstate(all="ignore"):
-            if t[-1] == t[0]:
-                return np.tile(y0, (t.size, 1))
-            sol = solve_ivp(fun, (t[0], t[-1]), y0, method=method, t_eval=None, dense_output=False,
-                            rtol=rtol, atol=atol, **_stops(t))
-    except Exception:
-        return nan
-    return sol if isinstance(sol, np.ndarray) else nan
-
-
-def _stops(t):
-    return {}
-
-
 def _fast_rhs(p):
     return lambda _t, y: gyncycle_rhs(y, p)
 

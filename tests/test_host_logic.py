@@ -196,3 +196,24 @@ def test_shard_bounds():
         b = [shard_bounds(n, w, r) for r in range(w)]
         assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
         assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm of the bench contract) runs without a GPU and prints one JSON line
+    with the agreed keys; non-zero ranks print nothing."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, GYNC_BENCH_CPU_BUDGET="1.0")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in line["config"]
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                       capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2"), timeout=60)
+    assert r.returncode == 0 and r.stdout.strip() == ""
