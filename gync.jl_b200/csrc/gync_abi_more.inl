@@ -280,4 +280,52 @@ int gync_em_comm_error(gync_em_comm* c) {
   return e;
 }
 
+
+// Single-process multi-GPU EM (gync_init_multi): rows of (w, L) are sharded over the devices and every device runs
+// the fused step+exchange kernel; the mailboxes are wired with plain peer pointers (same process, peer access on).
+int gync_em_iterate_multi(double* w, const double* L, int64_t K, int32_t M, int32_t niter) {
+  const int nd = (int)g_devs.size();
+  if (nd < 2) return fail(GYNC_ERR_ARG, "gync_em_iterate_multi: call gync_init_multi with >= 2 devices first");
+  if (K < nd || M < 1 || niter < 0 || !w || !L) return fail(GYNC_ERR_ARG, "gync_em_iterate_multi: bad arguments");
+  struct Part { int64_t lo = 0, n = 0; DBuf dw, dL; gync_em_comm* comm = nullptr; };
+  std::vector<Part> parts(nd);
+  char handle[64];
+  int rc = GYNC_OK;
+  for (int i = 0; i < nd && !rc; ++i) {
+    Part& p = parts[i];
+    p.lo = K * i / nd;
+    p.n = K * (i + 1) / nd - p.lo;
+    if ((rc = use_device(i))) break;
+    if ((rc = gync_em_comm_create(nd, i, handle, &p.comm))) break;
+    if (p.dw.alloc(sizeof(double) * p.n) != cudaSuccess || p.dL.alloc(sizeof(double) * p.n * M) != cudaSuccess) { rc = fail(GYNC_ERR_NOMEM, "gync_em_iterate_multi: out of device memory"); break; }
+    cudaMemcpyAsync(p.dw.p, w + p.lo, sizeof(double) * p.n, cudaMemcpyHostToDevice, g_stream);
+    cudaMemcpy2DAsync(p.dL.p, sizeof(double) * p.n, L + p.lo, sizeof(double) * K, sizeof(double) * p.n, M, cudaMemcpyHostToDevice, g_stream);
+  }
+  if (!rc) {
+    for (int i = 0; i < nd; ++i)                   // wire the mailboxes: direct peer pointers
+      for (int j = 0; j < nd; ++j) {
+        parts[i].comm->peer.mail[j] = parts[j].comm->mail;
+        parts[i].comm->peer.flag[j] = parts[j].comm->flag;
+      }
+    for (int i = 0; i < nd && !rc; ++i) {          // all launches are asynchronous: the kernels meet on the GPUs
+      if ((rc = use_device(i))) break;
+      rc = gync_em_iterate_fused_dev(parts[i].comm, parts[i].dw.as<double>(), parts[i].dL.as<double>(), parts[i].n, M, niter, g_stream);
+    }
+    for (int i = 0; i < nd && !rc; ++i) {
+      if ((rc = use_device(i))) break;
+      cudaMemcpyAsync(w + parts[i].lo, parts[i].dw.p, sizeof(double) * parts[i].n, cudaMemcpyDeviceToHost, g_stream);
+      if (cudaStreamSynchronize(g_stream) != cudaSuccess) rc = fail(GYNC_ERR_CUDA, "gync_em_iterate_multi: kernel failed");
+      else if (gync_em_comm_error(parts[i].comm)) rc = fail(GYNC_ERR_CUDA, "gync_em_iterate_multi: peer wait timed out");
+    }
+  }
+  for (int i = 0; i < nd; ++i) {
+    use_device(i);
+    cudaStreamSynchronize(g_stream);
+    if (parts[i].comm) gync_em_comm_destroy(parts[i].comm);
+    parts[i] = Part();
+  }
+  use_device(0);
+  return rc;
+}
+
 }  // extern "C"

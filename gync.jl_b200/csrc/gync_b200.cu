@@ -10,6 +10,9 @@
 #include "gync_mcmc.cuh"
 #include "../../include/gync_b200.h"
 
+extern "C" int gync_init(int device);
+extern "C" void gync_shutdown(void);
+
 namespace {
 
 thread_local std::string g_err;
@@ -17,6 +20,15 @@ cudaStream_t g_stream = nullptr;
 int g_device = -1;
 int g_num_sms = 0;
 std::atomic<int64_t> g_launches{0};
+
+// Devices this process drives (gync_init: one; gync_init_multi: several).  The g_* variables above always
+// describe the device that is current; use_device() switches them.
+struct DevCtx {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  int num_sms = 0;
+};
+std::vector<DevCtx> g_devs;
 
 int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -34,6 +46,15 @@ int fail(int code, const std::string& msg) {
 int ensure_init() {
   if (g_device >= 0) return GYNC_OK;
   return gync_init(0);
+}
+
+int use_device(int i) {
+  if (i < 0 || i >= (int)g_devs.size()) return fail(GYNC_ERR_ARG, "device slot out of range");
+  CK(cudaSetDevice(g_devs[i].device));
+  g_device = g_devs[i].device;
+  g_stream = g_devs[i].stream;
+  g_num_sms = g_devs[i].num_sms;
+  return GYNC_OK;
 }
 
 // RAII stream-ordered temporary (freed on every exit path)
@@ -148,9 +169,10 @@ int em_persistent_launch(double* dw, const double* dL, int64_t K, int M, int nit
   return GYNC_OK;
 }
 
-struct EmScratch {   // scratch for the sharded step kernels
+struct EmScratch {   // scratch for the sharded step kernels (on the device that was current when allocated)
   double* partials = nullptr;
   size_t doubles = 0;
+  int device = -1;
 } g_em_scratch;
 
 int em_grid(int64_t K) {
@@ -160,11 +182,16 @@ int em_grid(int64_t K) {
 }
 
 int em_scratch(size_t doubles) {
-  if (g_em_scratch.partials && g_em_scratch.doubles >= doubles) return GYNC_OK;
-  if (g_em_scratch.partials) cudaFree(g_em_scratch.partials);
+  if (g_em_scratch.partials && g_em_scratch.doubles >= doubles && g_em_scratch.device == g_device) return GYNC_OK;
+  if (g_em_scratch.partials) {
+    cudaSetDevice(g_em_scratch.device);
+    cudaFree(g_em_scratch.partials);
+    cudaSetDevice(g_device);
+  }
   g_em_scratch.partials = nullptr;
   CK(cudaMalloc((void**)&g_em_scratch.partials, sizeof(double) * doubles));
   g_em_scratch.doubles = doubles;
+  g_em_scratch.device = g_device;
   return GYNC_OK;
 }
 
@@ -233,6 +260,34 @@ void gync_dims(int32_t* ny, int32_t* np, int32_t* nx, int32_t* nq, int32_t* nlu)
   if (nlu) *nlu = GYNC_NLU;
 }
 
+int gync_ndev(void) { return (int)g_devs.size(); }
+
+int gync_init_multi(int32_t ndev, const int32_t* devices) {
+  if (ndev < 1 || ndev > 8) return fail(GYNC_ERR_ARG, "gync_init_multi: 1..8 devices");
+  gync_shutdown();
+  std::vector<DevCtx> devs;
+  for (int i = 0; i < ndev; ++i) {
+    const int d = devices ? devices[i] : i;
+    if (int rc = gync_init(d)) return rc;          // creates the stream of device d
+    devs.push_back({g_device, g_stream, g_num_sms});
+    g_stream = nullptr;                            // keep it alive: owned by the table now
+    g_devs.clear();
+  }
+  for (int i = 0; i < ndev; ++i)                   // NVLink peer access for the fused EM exchange
+    for (int j = 0; j < ndev; ++j)
+      if (i != j) {
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can, devs[i].device, devs[j].device));
+        if (!can) return fail(GYNC_ERR_CUDA, "gync_init_multi: devices without peer access");
+        CK(cudaSetDevice(devs[i].device));
+        cudaError_t e = cudaDeviceEnablePeerAccess(devs[j].device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+        (void)cudaGetLastError();
+      }
+  g_devs = devs;
+  return use_device(0);
+}
+
 int gync_init(int device) {
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
@@ -247,11 +302,19 @@ int gync_init(int device) {
   CK(cudaGetDeviceProperties(&prop, device));
   g_num_sms = prop.multiProcessorCount;
   g_device = device;
+  g_devs.assign(1, DevCtx{g_device, g_stream, g_num_sms});
   return GYNC_OK;
 }
 
 void gync_shutdown(void) {
-  if (g_em_scratch.partials) { cudaFree(g_em_scratch.partials); g_em_scratch.partials = nullptr; g_em_scratch.doubles = 0; }
+  if (g_em_scratch.partials) {
+    if (g_em_scratch.device >= 0) cudaSetDevice(g_em_scratch.device);
+    cudaFree(g_em_scratch.partials);
+    g_em_scratch = EmScratch();
+  }
+  for (DevCtx& d : g_devs)
+    if (d.stream) { cudaSetDevice(d.device); cudaStreamDestroy(d.stream); if (d.stream == g_stream) g_stream = nullptr; }
+  g_devs.clear();
   if (g_stream) { cudaStreamDestroy(g_stream); g_stream = nullptr; }
   g_device = -1;
 }
@@ -286,6 +349,55 @@ int gync_loglik_batch_dev(const double* dX, int64_t N, const double* d_data, int
   return GYNC_OK;
 }
 
+// Several devices in one process (gync_init_multi): contiguous blocks of samples per device, no
+// data-path collective.  Column-major slices are moved with 2-D copies; all devices run concurrently.
+static int loglik_batch_multi(const double* X, int64_t N, const double* data, int32_t M, const double* sigma_rho,
+                              const gync_solver_opts* opts, double* LL, double* Ymeas, int32_t* status, int32_t* nsteps) {
+  const int nd = (int)g_devs.size();
+  struct Part { int64_t lo = 0, n = 0; DBuf dX, dD, dS, dLL, dY, dSt, dNs; };
+  std::vector<Part> parts(nd);
+  for (int i = 0; i < nd; ++i) {
+    Part& p = parts[i];
+    p.lo = N * i / nd;
+    p.n = N * (i + 1) / nd - p.lo;
+    if (p.n == 0) continue;
+    if (int rc = use_device(i)) return rc;
+    CK(p.dX.alloc(sizeof(double) * p.n * GYNC_NX));
+    CK(p.dD.alloc(sizeof(double) * 124 * M));
+    CK(p.dS.alloc(sizeof(double) * M));
+    CK(p.dLL.alloc(sizeof(double) * p.n * M));
+    if (Ymeas) CK(p.dY.alloc(sizeof(double) * p.n * GYNC_NT_MEAS * GYNC_NMEAS));
+    CK(p.dSt.alloc(sizeof(int32_t) * p.n));
+    if (nsteps) CK(p.dNs.alloc(sizeof(int32_t) * p.n * 2));
+    CK(cudaMemcpy2DAsync(p.dX.p, sizeof(double) * p.n, X + p.lo, sizeof(double) * N, sizeof(double) * p.n, GYNC_NX,
+                         cudaMemcpyHostToDevice, g_stream));
+    CK(cudaMemcpyAsync(p.dD.p, data, sizeof(double) * 124 * M, cudaMemcpyHostToDevice, g_stream));
+    CK(cudaMemcpyAsync(p.dS.p, sigma_rho, sizeof(double) * M, cudaMemcpyHostToDevice, g_stream));
+    if (int rc = gync_loglik_batch_dev(p.dX.as<double>(), p.n, p.dD.as<double>(), M, p.dS.as<double>(), opts, p.dLL.as<double>(),
+                                       Ymeas ? p.dY.as<double>() : nullptr, p.dSt.as<int32_t>(),
+                                       nsteps ? p.dNs.as<int32_t>() : nullptr, g_stream)) return rc;
+  }
+  for (int i = 0; i < nd; ++i) {
+    Part& p = parts[i];
+    if (p.n == 0) continue;
+    if (int rc = use_device(i)) return rc;
+    CK(cudaMemcpy2DAsync(LL + p.lo, sizeof(double) * N, p.dLL.p, sizeof(double) * p.n, sizeof(double) * p.n, M,
+                         cudaMemcpyDeviceToHost, g_stream));
+    if (Ymeas) CK(cudaMemcpy2DAsync(Ymeas + p.lo, sizeof(double) * N, p.dY.p, sizeof(double) * p.n, sizeof(double) * p.n,
+                                    GYNC_NT_MEAS * GYNC_NMEAS, cudaMemcpyDeviceToHost, g_stream));
+    if (status) CK(cudaMemcpyAsync(status + p.lo, p.dSt.p, sizeof(int32_t) * p.n, cudaMemcpyDeviceToHost, g_stream));
+    if (nsteps) CK(cudaMemcpy2DAsync(nsteps + p.lo, sizeof(int32_t) * N, p.dNs.p, sizeof(int32_t) * p.n, sizeof(int32_t) * p.n, 2,
+                                     cudaMemcpyDeviceToHost, g_stream));
+  }
+  for (int i = 0; i < nd; ++i) {
+    if (parts[i].n == 0) continue;
+    if (int rc = use_device(i)) return rc;
+    CK(cudaStreamSynchronize(g_stream));
+    parts[i] = Part();           // free on the owning device
+  }
+  return use_device(0);
+}
+
 int gync_loglik_batch(const double* X, int64_t N, const double* data, int32_t M, const double* sigma_rho,
                       const gync_solver_opts* opts, double* LL, double* Ymeas, int32_t* status,
                       int32_t* nsteps) {
@@ -293,6 +405,8 @@ int gync_loglik_batch(const double* X, int64_t N, const double* data, int32_t M,
     return fail(GYNC_ERR_ARG, "gync_loglik_batch: bad arguments");
   if (int rc = ensure_init()) return rc;
   if (N == 0) return GYNC_OK;
+  if (g_devs.size() > 1 && N >= (int64_t)g_devs.size() * 256)
+    return loglik_batch_multi(X, N, data, M, sigma_rho, opts, LL, Ymeas, status, nsteps);
   DBuf dX, dD, dS, dLL, dY, dSt, dNs;
   CK(dX.alloc(sizeof(double) * N * GYNC_NX));
   CK(dD.alloc(sizeof(double) * 124 * M));
@@ -394,10 +508,14 @@ int gync_em_step_dev(double* dw, const double* dL, int64_t K, int32_t M, const d
 #undef CALL
 }
 
+extern "C" int gync_em_iterate_multi(double* w, const double* L, int64_t K, int32_t M, int32_t niter);
+
 int gync_em_iterate(double* w, const double* L, int64_t K, int32_t M, int32_t niter, double* history) {
   if (K < 0 || M < 1 || niter < 0 || (K > 0 && (!w || !L))) return fail(GYNC_ERR_ARG, "gync_em_iterate: bad arguments");
   if (int rc = ensure_init()) return rc;
   if (K == 0 || niter == 0) return GYNC_OK;
+  if (g_devs.size() > 1 && !history && K >= (int64_t)g_devs.size() * 4096 && M <= 64)
+    return gync_em_iterate_multi(w, L, K, M, niter);
   DBuf dw, dL, dH;
   CK(dw.alloc(sizeof(double) * K));
   CK(dL.alloc(sizeof(double) * K * M));

@@ -40,7 +40,8 @@ EXPORTS = [
     "gync_logprior_batch", "gync_mcmc_run", "gync_em_iterate", "gync_em_iterate_dev",
     "gync_em_norms_dev", "gync_em_step_dev", "gync_launch_count", "gync_wc_normalize", "gync_fp64_peak",
     "gync_flops_per_step", "gync_em_comm_create", "gync_em_comm_connect", "gync_em_comm_destroy",
-    "gync_em_iterate_fused_dev", "gync_em_comm_error", "gync_wc_normalize_dev",
+    "gync_em_iterate_fused_dev", "gync_em_comm_error", "gync_wc_normalize_dev", "gync_init_multi", "gync_ndev",
+    "gync_em_iterate_multi",
 ]
 
 _lib = None
@@ -58,6 +59,8 @@ def load():
     lib.gync_last_error.restype = C.c_char_p
     lib.gync_launch_count.restype = C.c_int64
     lib.gync_init.argtypes = [C.c_int]
+    lib.gync_init_multi.argtypes = [C.c_int32, c_int32_p]
+    lib.gync_em_iterate_multi.argtypes = [c_double_p, c_double_p, C.c_int64, C.c_int32, C.c_int32]
     lib.gync_dims.argtypes = [c_int32_p] * 5
     lib.gync_solve.argtypes = [c_double_p, c_double_p, C.c_int64, c_double_p, C.c_int32, C.POINTER(SolverOpts),
                                c_double_p, c_int32_p]

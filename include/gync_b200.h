@@ -36,6 +36,11 @@ extern "C" {
 
 /* ---- lifecycle ------------------------------------------------------------------------ */
 int  gync_init(int device);              /* select device, create the library stream */
+/* Drive several GPUs of one NVLink domain from ONE process (the Julia host is a single process): the host-buffer
+ * entry points gync_loglik_batch and gync_em_iterate then shard samples / rows over the devices (the EM through the
+ * fused peer-memory kernel).  devices == NULL means 0..ndev-1. */
+int  gync_init_multi(int32_t ndev, const int32_t* devices);
+int  gync_ndev(void);
 void gync_shutdown(void);
 const char* gync_last_error(void);
 int  gync_abi_version(void);
@@ -110,6 +115,7 @@ int gync_mcmc_run(double* state, double* logf, int64_t C, const double* chol, do
 int gync_em_iterate(double* w, const double* L, int64_t K, int32_t M, int32_t niter, double* history);
 int gync_em_iterate_dev(double* dw, const double* dL, int64_t K, int32_t M, int32_t niter,
                         double* d_history, void* stream);
+int gync_em_iterate_multi(double* w, const double* L, int64_t K, int32_t M, int32_t niter);   /* needs gync_init_multi */
 /* Sharded form (one process per GPU): one EM step on the local rows given the GLOBAL
  * denominators d_norms_in (M); writes this shard's partial denominators of the NEXT iteration
  * to d_norms_out (M) for the caller's allreduce.  em_norms_dev computes the first partials. */
