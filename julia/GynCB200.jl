@@ -10,6 +10,13 @@
 
 const LIBGYNC = get(ENV, "GYNC_B200_LIB", "libgync_b200.so")
 
+# Julia is one process: drive all GPUs of the node from it (samples / EM rows are sharded inside the library).
+function b200init(ndev::Int=1)
+  rc = ndev > 1 ? ccall((:gync_init_multi, LIBGYNC), Cint, (Cint, Ptr{Cint}), ndev, C_NULL) :
+                  ccall((:gync_init, LIBGYNC), Cint, (Cint,), 0)
+  rc == 0 || error("gync_b200: ", bytestring(ccall((:gync_last_error, LIBGYNC), Ptr{UInt8}, ())))
+end
+
 immutable SolverOpts          # gync_solver_opts
   rtol::Cdouble
   atol::Cdouble
