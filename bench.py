@@ -391,7 +391,7 @@ def em_leg(lib, L, torch, dist, dev, stream, world, rank, barrier, max_over_rank
                            "frac": out["cfg5_K1e6"]["frac_of_hbm"],
                            "traffic": 6.888e9 / 20 + 163.6e6 / 20,   # ncu: DRAM read+write of a 20-iteration launch / 20
                            "algorithmic_bytes": by,
-                           "kernel": "gync_em_persistent_kernel<20,true>", "peak_source": hbm_src,
+                           "kernel": "gync_em_kernel<20,true,false> (streaming)", "peak_source": hbm_src,
                            "how": "8KM+16K+16M algorithmic bytes per iteration (L read once) / (CUDA-event time of one "
                                   "100-iteration cooperative launch / 100); K=1e6 x 40 = 320 MB > 126 MB L2"}
         return out
@@ -451,7 +451,7 @@ def em_leg(lib, L, torch, dist, dev, stream, world, rank, barrier, max_over_rank
                                               "the persistent kernel (no NCCL in the loop)",
                                 "peer_wait_timeout": int(err), "max_abs_diff_vs_nccl_path": float(dw.item())}
     out["roofline"] = {"bound": "hbm", "achieved": by / msf / 1e6, "peak": hbm, "unit": "GB/s", "frac": by / msf / 1e6 / hbm,
-                       "traffic": None, "kernel": "gync_em_fused_kernel<20,true> (compute + peer-memory allreduce)",
+                       "traffic": None, "kernel": "gync_em_kernel<20,true,*> with peers (compute + peer-memory allreduce)",
                        "peak_source": hbm_src}
     return out
 

@@ -175,10 +175,7 @@ struct gync_em_comm {
   unsigned long long* flag = nullptr;     // local flags   [2][world]
   void* peer_base[8] = {nullptr};         // opened peer allocations (nullptr for self)
   GyncEmPeer peer;
-  unsigned long long seq = 1;          // flags start at 0: the first exchange must carry a larger number
-  double* partials = nullptr;
-  double* gnorm = nullptr;
-  int* err = nullptr;
+  EmLaunchState st;                       // sequence numbers start at 1: mailbox flags start at 0
   size_t flag_off = 0;
 };
 
@@ -196,10 +193,7 @@ int gync_em_comm_create(int32_t world, int32_t rank, void* handle_out /* 64 byte
   CK(cudaMemset(base, 0, total));
   c->mail = (double*)base;
   c->flag = (unsigned long long*)((char*)base + c->flag_off);
-  CK(cudaMalloc((void**)&c->partials, sizeof(double) * 1024 * c->MT));
-  CK(cudaMalloc((void**)&c->gnorm, sizeof(double) * 2 * c->MT));
-  CK(cudaMalloc((void**)&c->err, sizeof(int)));
-  CK(cudaMemset(c->err, 0, sizeof(int)));
+  if (int rc = c->st.alloc()) return rc;
   cudaIpcMemHandle_t h;
   CK(cudaIpcGetMemHandle(&h, base));
   static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t size");
@@ -230,37 +224,11 @@ void gync_em_comm_destroy(gync_em_comm* c) {
   if (!c) return;
   for (int p = 0; p < c->world; ++p) if (c->peer_base[p]) cudaIpcCloseMemHandle(c->peer_base[p]);
   if (c->mail) cudaFree(c->mail);
-  if (c->partials) cudaFree(c->partials);
-  if (c->gnorm) cudaFree(c->gnorm);
-  if (c->err) cudaFree(c->err);
+  c->st.release();
   delete c;
 }
 
 }  // extern "C"
-
-namespace {
-template <int MH, bool FULL>
-int em_fused_launch(gync_em_comm* c, double* dw, const double* dL, int64_t K, int M, int niter, cudaStream_t s) {
-  int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gync_em_fused_kernel<MH, FULL>, GYNC_EM_THREADS, 0));
-  if (per_sm < 1) return fail(GYNC_ERR_CUDA, "fused EM kernel does not fit on an SM");
-  const int64_t rows_per_block = GYNC_EM_WARPS * 16;
-  const int64_t want = (K + rows_per_block - 1) / rows_per_block;
-  int nb = (int)std::min<int64_t>(std::min<int64_t>((int64_t)g_num_sms * per_sm, 1024), std::max<int64_t>(want, 1));
-  // mailboxes are allocated 64 doubles wide per rank; the kernel indexes them with its own 2*MH stride
-  // (all ranks run the same instantiation, so the layout agrees)
-  GyncEmPeer peer = c->peer;
-  unsigned long long seq0 = c->seq;
-  double* partials = c->partials;
-  double* gnorm = c->gnorm;
-  int* err = c->err;
-  void* args[] = {&dw, &dL, &K, &M, &niter, &partials, &gnorm, &peer, &seq0, &err};
-  CK(cudaLaunchCooperativeKernel((void*)gync_em_fused_kernel<MH, FULL>, dim3(nb), dim3(GYNC_EM_THREADS), args, 0, s));
-  c->seq += (unsigned long long)niter + 1ull;
-  g_launches += 1;
-  return GYNC_OK;
-}
-}  // namespace
 
 extern "C" {
 
@@ -268,7 +236,7 @@ int gync_em_iterate_fused_dev(gync_em_comm* c, double* dw, const double* dL, int
                               void* stream) {
   if (!c || K < 0 || M < 1 || niter < 0 || (K > 0 && (!dw || !dL))) return fail(GYNC_ERR_ARG, "gync_em_iterate_fused: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
-#define CALL(MH, F) em_fused_launch<MH, F>(c, dw, dL, K, M, niter, s)
+#define CALL(MH, F) em_launch<MH, F>(c->st, c->peer, dw, dL, K, M, niter, nullptr, s)
   EM_DISPATCH(M, CALL);
 #undef CALL
 }
@@ -276,7 +244,7 @@ int gync_em_iterate_fused_dev(gync_em_comm* c, double* dw, const double* dL, int
 int gync_em_comm_error(gync_em_comm* c) {
   if (!c) return -1;
   int e = 0;
-  if (cudaMemcpy(&e, c->err, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+  if (cudaMemcpy(&e, c->st.err, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
   return e;
 }
 

@@ -123,50 +123,88 @@ int launch_loglik(const double* dX, int64_t N, const double* d_data, const doubl
 // EM launch helpers (templates: outside extern "C")
 namespace {
 
-// L resident in shared memory (one pass over HBM for the whole call) when the rows fit: one CTA per SM.
-template <int MH, bool FULL>
-int em_resident_try(double* dw, const double* dL, int64_t K, int M, int niter, double* d_hist, cudaStream_t s, bool* done) {
+// Unified EM launch: one cooperative launch of gync_em_kernel for all iterations; L resident in shared
+// memory when this GPU's rows fit.  `peer` describes the other ranks (world 1: none).
+struct EmLaunchState {          // synchronisation words + scratch of one (device, communicator)
+  unsigned long long* sync_words = nullptr;    // [0] arrive, [1] ready
+  double* partials = nullptr;                  // 1024 x 64
+  double* gnorm = nullptr;                     // 2 x 64
+  int* err = nullptr;
+  unsigned long long seq = 1, arrive0 = 0;
+  int device = -1;
+  int alloc() {
+    CK(cudaMalloc((void**)&sync_words, 2 * sizeof(unsigned long long)));
+    CK(cudaMemset(sync_words, 0, 2 * sizeof(unsigned long long)));
+    CK(cudaMalloc((void**)&partials, sizeof(double) * 1024 * 64));
+    CK(cudaMalloc((void**)&gnorm, sizeof(double) * 2 * 64));
+    CK(cudaMalloc((void**)&err, sizeof(int)));
+    CK(cudaMemset(err, 0, sizeof(int)));
+    CK(cudaGetDevice(&device));
+    return GYNC_OK;
+  }
+  void release() {
+    if (device >= 0) { int cur; cudaGetDevice(&cur); cudaSetDevice(device);
+      cudaFree(sync_words); cudaFree(partials); cudaFree(gnorm); cudaFree(err); cudaSetDevice(cur); }
+    *this = EmLaunchState();
+  }
+};
+EmLaunchState g_em_local[8];    // single-GPU calls: one per device slot
+
+template <int MH, bool FULL, bool RESIDENT>
+int em_launch_variant(EmLaunchState& st, const GyncEmPeer& peer, double* dw, const double* dL, int64_t K, int M, int niter,
+                      double* d_hist, cudaStream_t s, bool* done) {
   *done = false;
-  if (getenv("GYNC_EM_NO_RESIDENT")) return GYNC_OK;
-  const int nb = g_num_sms;
-  const int64_t R = (K + nb - 1) / nb;
-  const size_t smem = sizeof(double) * (size_t)M * R + sizeof(EmSmem<MH>) + 16;
-  int max_optin = 0;
-  CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, g_device));
-  if (smem > (size_t)max_optin || niter < 2) return GYNC_OK;      // does not fit (or not worth the load): stream from HBM
-  CK(cudaFuncSetAttribute(gync_em_resident_kernel<MH, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t rows_per_pass = GYNC_EM_WARPS * 16;
+  int nb;
+  int64_t R = 0;
+  size_t smem = sizeof(EmSmem<MH>) + 16;
+  if (RESIDENT) {
+    nb = g_num_sms;
+    R = (K + nb - 1) / nb;
+    smem += sizeof(double) * (size_t)M * R;
+    int max_optin = 0;
+    CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, g_device));
+    if (smem > (size_t)max_optin || R > 3 * rows_per_pass) return GYNC_OK;   // rows do not fit: caller streams instead
+  } else {
+    nb = (int)std::min<int64_t>(g_num_sms, std::max<int64_t>((K + rows_per_pass - 1) / rows_per_pass, 1));
+  }
+  CK(cudaFuncSetAttribute(gync_em_kernel<MH, FULL, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gync_em_resident_kernel<MH, FULL>, GYNC_EM_THREADS, smem));
-  if (per_sm < 1) return GYNC_OK;
-  double* partials = nullptr;
-  CK(cudaMallocAsync((void**)&partials, sizeof(double) * 2 * nb * 2 * MH, s));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gync_em_kernel<MH, FULL, RESIDENT>, GYNC_EM_THREADS, smem));
+  if (per_sm < 1) return RESIDENT ? GYNC_OK : fail(GYNC_ERR_CUDA, "EM kernel does not fit on an SM");
+  GyncEmSync sync = {st.sync_words, st.sync_words + 1, st.seq, st.arrive0};
+  GyncEmPeer pr = peer;
   int Ri = (int)R;
-  void* args[] = {&dw, &dL, &K, &M, &niter, &Ri, &partials, &d_hist};
-  CK(cudaLaunchCooperativeKernel((void*)gync_em_resident_kernel<MH, FULL>, dim3(nb), dim3(GYNC_EM_THREADS), args, smem, s));
+  void* args[] = {&dw, &dL, &K, &M, &niter, &Ri, &st.partials, &st.gnorm, &sync, &pr, &st.err, &d_hist};
+  CK(cudaLaunchCooperativeKernel((void*)gync_em_kernel<MH, FULL, RESIDENT>, dim3(nb), dim3(GYNC_EM_THREADS), args, smem, s));
+  st.seq += (unsigned long long)niter + 1ull;
+  st.arrive0 += (unsigned long long)nb * ((unsigned long long)niter + 1ull);
   g_launches += 1;
-  CK(cudaFreeAsync(partials, s));
   *done = true;
   return GYNC_OK;
 }
 
 template <int MH, bool FULL>
-int em_persistent_launch(double* dw, const double* dL, int64_t K, int M, int niter, double* d_hist, cudaStream_t s) {
+int em_launch(EmLaunchState& st, const GyncEmPeer& peer, double* dw, const double* dL, int64_t K, int M, int niter,
+              double* d_hist, cudaStream_t s) {
   bool done = false;
-  if (int rc = em_resident_try<MH, FULL>(dw, dL, K, M, niter, d_hist, s, &done)) return rc;
-  if (done) return GYNC_OK;
-  int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gync_em_persistent_kernel<MH, FULL>, GYNC_EM_THREADS, 0));
-  if (per_sm < 1) return fail(GYNC_ERR_CUDA, "EM kernel does not fit on an SM");
-  const int64_t rows_per_block = GYNC_EM_WARPS * 16;
-  int64_t want = (K + rows_per_block - 1) / rows_per_block;
-  int nb = (int)std::min<int64_t>((int64_t)g_num_sms * per_sm, std::max<int64_t>(want, 1));
-  double* partials = nullptr;
-  CK(cudaMallocAsync((void**)&partials, sizeof(double) * 2 * nb * 2 * MH, s));
-  void* args[] = {&dw, &dL, &K, &M, &niter, &partials, &d_hist};
-  CK(cudaLaunchCooperativeKernel((void*)gync_em_persistent_kernel<MH, FULL>, dim3(nb), dim3(GYNC_EM_THREADS), args, 0, s));
-  g_launches += 1;
-  CK(cudaFreeAsync(partials, s));
-  return GYNC_OK;
+  if (niter >= 2 && !getenv("GYNC_EM_NO_RESIDENT")) {
+    if (int rc = em_launch_variant<MH, FULL, true>(st, peer, dw, dL, K, M, niter, d_hist, s, &done)) return rc;
+    if (done) return GYNC_OK;
+  }
+  return em_launch_variant<MH, FULL, false>(st, peer, dw, dL, K, M, niter, d_hist, s, &done);
+}
+
+template <int MH, bool FULL>
+int em_persistent_launch(double* dw, const double* dL, int64_t K, int M, int niter, double* d_hist, cudaStream_t s) {
+  int slot = 0;
+  for (size_t i = 0; i < g_devs.size(); ++i) if (g_devs[i].device == g_device) slot = (int)i;
+  EmLaunchState& st = g_em_local[slot];
+  if (st.device != g_device) { st.release(); if (int rc = st.alloc()) return rc; }
+  GyncEmPeer peer;
+  memset(&peer, 0, sizeof(peer));
+  peer.world = 1;
+  return em_launch<MH, FULL>(st, peer, dw, dL, K, M, niter, d_hist, s);
 }
 
 struct EmScratch {   // scratch for the sharded step kernels (on the device that was current when allocated)
@@ -307,6 +345,7 @@ int gync_init(int device) {
 }
 
 void gync_shutdown(void) {
+  for (EmLaunchState& st : g_em_local) st.release();
   if (g_em_scratch.partials) {
     if (g_em_scratch.device >= 0) cudaSetDevice(g_em_scratch.device);
     cudaFree(g_em_scratch.partials);

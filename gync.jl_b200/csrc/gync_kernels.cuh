@@ -680,84 +680,6 @@ __device__ __forceinline__ void em_step_pass(double* __restrict__ w, const doubl
   em_block_reduce<MH>(acc, sm, out, M);
 }
 
-template <int MH, bool FULL>
-__global__ void __launch_bounds__(GYNC_EM_THREADS, 1)
-gync_em_persistent_kernel(double* __restrict__ w, const double* __restrict__ L, int64_t K, int M, int niter,
-                          double* __restrict__ partials /* 2 x gridDim.x x 2MH */, double* __restrict__ history) {
-  cg::grid_group grid = cg::this_grid();
-  __shared__ EmSmem<MH> sm;
-  constexpr int MT = 2 * MH;
-  const int nb = gridDim.x;
-  em_norms_pass<MH, FULL>(w, L, K, M, sm, partials + (size_t)blockIdx.x * MT);
-  grid.sync();          // cooperative-groups grid barrier orders the partials written above
-  for (int it = 0; it < niter; ++it) {
-    const double* pin = partials + (size_t)(it & 1) * nb * MT;
-    double* pout = partials + (size_t)((it + 1) & 1) * nb * MT;
-    em_gather_partials<MH>(pin, nb, M, sm, sm.rinv, true);
-    em_step_pass<MH, FULL>(w, L, K, M, sm, pout + (size_t)blockIdx.x * MT, history ? history + (size_t)it * K : nullptr);
-    grid.sync();
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// K4, resident variant: when this GPU's part of L fits in shared memory (K*M*8 B <= ~148 x 217 KB =
-// 32 MB, e.g. BASELINE cfg 3: 10^5 x 40) every CTA loads its rows ONCE and all iterations run out of
-// shared memory — HBM is out of the loop; an iteration costs one pass over 216 KB of shared memory
-// per SM plus the grid barrier and the partial gather.  Layout in shared memory: [column][row], so a
-// half-warp reads 16 consecutive rows of one column (conflict-free).
-template <int MH, bool FULL>
-__global__ void __launch_bounds__(GYNC_EM_THREADS, 1)
-gync_em_resident_kernel(double* __restrict__ w, const double* __restrict__ L, int64_t K, int M, int niter, int rows_per_block,
-                        double* __restrict__ partials /* 2 x gridDim.x x 2MH */, double* __restrict__ history) {
-  cg::grid_group grid = cg::this_grid();
-  extern __shared__ double em_dyn[];            // [M][rows_per_block] then EmSmem
-  constexpr int MT = 2 * MH;
-  const int R = rows_per_block;
-  double* sL = em_dyn;
-  EmSmem<MH>& sm = *reinterpret_cast<EmSmem<MH>*>(em_dyn + (size_t)M * R);
-  const int nb = gridDim.x;
-  const int64_t row0 = (int64_t)blockIdx.x * R;
-  const int nrows = (int)max((int64_t)0, min((int64_t)R, K - row0));
-  for (int m = 0; m < M; ++m)                    // coalesced: consecutive threads read consecutive rows of column m
-    for (int r = threadIdx.x; r < nrows; r += GYNC_EM_THREADS) sL[(size_t)m * R + r] = __ldg(L + row0 + r + K * (int64_t)m);
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = lane >> 4, rl = lane & 15;
-  const double invM = 1.0 / (double)M;
-  for (int it = -1; it < niter; ++it) {
-    if (it >= 0) em_gather_partials<MH>(partials + (size_t)(it & 1) * nb * MT, nb, M, sm, sm.rinv, true);
-    double acc[MH];
-#pragma unroll
-    for (int j = 0; j < MH; ++j) acc[j] = 0.0;
-    const double* ri = sm.rinv + half * MH;
-    for (int rb = warp * 16; rb < nrows; rb += GYNC_EM_WARPS * 16) {     // warp-uniform (the shuffle needs all lanes)
-      const int r = rb + rl;
-      const bool valid = r < nrows;
-      const double* p = sL + (size_t)(half * MH) * R + (valid ? r : 0);
-      double l[MH];
-#pragma unroll
-      for (int j = 0; j < MH; ++j) l[j] = (valid && (FULL || half * MH + j < M)) ? p[(size_t)j * R] : 0.0;
-      double wk = valid ? w[row0 + r] : 0.0;
-      if (it >= 0) {
-        double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-        for (int j = 0; j + 1 < MH; j += 2) { s0 = fma(l[j], ri[j], s0); s1 = fma(l[j + 1], ri[j + 1], s1); }
-        if (MH & 1) s0 = fma(l[MH - 1], ri[MH - 1], s0);
-        double s = s0 + s1;
-        s += __shfl_xor_sync(0xffffffffu, s, 16);
-        wk = wk * invM * s;
-        if (valid && half == 0) {
-          w[row0 + r] = wk;
-          if (history) history[(size_t)it * K + row0 + r] = wk;
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < MH; ++j) acc[j] = fma(l[j], wk, acc[j]);
-    }
-    em_block_reduce<MH>(acc, sm, partials + (size_t)((it + 1) & 1) * nb * MT + (size_t)blockIdx.x * MT, M);
-    grid.sync();
-  }
-}
-
 // ------------------------------------------------------------------------------------------
 // K4 across GPUs as ONE kernel: compute step + the allreduce of the M denominators fused over
 // NVLink peer memory.  Every rank runs this persistent cooperative kernel on its row shard.  Per
@@ -772,55 +694,162 @@ struct GyncEmPeer {
   int world, rank;
 };
 
-template <int MH, bool FULL>
+// ------------------------------------------------------------------------------------------
+// K4, unified persistent kernel (single GPU and fused multi-GPU), flag-based synchronisation.
+//
+// A grid-wide barrier is more than this loop needs: only ONE block has to see all partials, and the
+// other blocks only have to learn the new denominators.  So per iteration every block does its pass,
+// writes its partials and ARRIVES (one atomic); block 0 waits for the arrivals, sums the partials in a
+// fixed order, exchanges with the peer GPUs if there are any (mailboxes over NVLink, rank order), and
+// publishes 1/denominators plus a sequence flag; all blocks poll that flag.  Compared with two
+// cooperative-groups grid barriers plus 148 redundant gathers this removes ~5 us per iteration.
+// RESIDENT: this GPU's rows of L are loaded into shared memory once (when they fit).
+struct GyncEmSync {
+  unsigned long long* arrive;   // monotonically increasing arrival counter (device memory)
+  unsigned long long* ready;    // sequence number of the denominators currently published in gnorm
+  unsigned long long seq0;      // first sequence number of this launch (ready < seq0 on entry)
+  unsigned long long arrive0;   // value of *arrive when this launch starts
+};
+
+template <int MH, bool FULL, bool RESIDENT>
 __global__ void __launch_bounds__(GYNC_EM_THREADS, 1)
-gync_em_fused_kernel(double* __restrict__ w, const double* __restrict__ L, int64_t K, int M, int niter,
-                     double* __restrict__ partials /* gridDim.x x 2MH */, double* __restrict__ gnorm /* 2 x 2MH */,
-                     GyncEmPeer peer, unsigned long long seq0, int* __restrict__ err_flag) {
-  cg::grid_group grid = cg::this_grid();
-  __shared__ EmSmem<MH> sm;
+gync_em_kernel(double* __restrict__ w, const double* __restrict__ L, int64_t K, int M, int niter, int rows_per_block,
+               double* __restrict__ partials /* 2 x gridDim.x x 2MH */, double* __restrict__ gnorm /* 2 x 2MH */,
+               GyncEmSync sync, GyncEmPeer peer, int* __restrict__ err_flag, double* __restrict__ history) {
+  extern __shared__ double em_dyn[];            // RESIDENT: [M][rows_per_block] then EmSmem ; else EmSmem only
   constexpr int MT = 2 * MH;
+  const int R = rows_per_block;
+  double* sL = em_dyn;
+  EmSmem<MH>& sm = *reinterpret_cast<EmSmem<MH>*>(em_dyn + (RESIDENT ? (size_t)M * R : 0));
   const int nb = gridDim.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = lane >> 4, rl = lane & 15;
+  const int64_t row0 = (int64_t)blockIdx.x * R;
+  const int nrows = RESIDENT ? (int)max((int64_t)0, min((int64_t)R, K - row0)) : 0;
+  if (RESIDENT) {
+    for (int m = 0; m < M; ++m)
+      for (int r = threadIdx.x; r < nrows; r += GYNC_EM_THREADS) sL[(size_t)m * R + r] = __ldg(L + row0 + r + K * (int64_t)m);
+    __syncthreads();
+  }
+  const double invM = 1.0 / (double)M;
+  // RESIDENT: rows_per_block <= kSweeps * 256 (the host checks it); each thread keeps its rows' weights in registers
+  constexpr int kSweeps = 3;
+  double wreg[kSweeps];
+#pragma unroll
+  for (int sw = 0; sw < kSweeps; ++sw) {
+    const int r = warp * 16 + sw * GYNC_EM_WARPS * 16 + rl;
+    wreg[sw] = (RESIDENT && r < nrows) ? w[row0 + r] : 0.0;
+  }
   for (int it = -1; it < niter; ++it) {
-    // local pass: it == -1 computes the first denominators, afterwards one EM step each
-    if (it < 0) em_norms_pass<MH, FULL>(w, L, K, M, sm, partials + (size_t)blockIdx.x * MT);
-    else        em_step_pass<MH, FULL>(w, L, K, M, sm, partials + (size_t)blockIdx.x * MT, nullptr);
-    __threadfence();
-    grid.sync();
-    const unsigned long long seq = seq0 + (unsigned long long)(it + 1);
-    const int slot = (int)(seq & 1ull);
-    if (blockIdx.x == 0) {
-      em_gather_partials<MH>(partials, nb, M, sm, sm.rinv, false);          // this GPU's partial denominators
-      // push to every peer's mailbox (including our own), then publish the flag
-      for (int idx = threadIdx.x; idx < peer.world * MT; idx += GYNC_EM_THREADS) {
-        const int p = idx / MT, m = idx % MT;
-        peer.mail[p][((size_t)slot * peer.world + peer.rank) * MT + m] = sm.rinv[m];
-      }
-      __threadfence_system();
-      __syncthreads();
-      if (threadIdx.x < peer.world) {
-        volatile unsigned long long* f = peer.flag[threadIdx.x] + (size_t)slot * peer.world + peer.rank;
-        *f = seq;
-      }
-      // wait for all peers' contributions of this sequence number
-      if (threadIdx.x < peer.world) {
-        volatile unsigned long long* f = peer.flag[peer.rank] + (size_t)slot * peer.world + threadIdx.x;
-        long long spins = 0;
-        while (*f < seq) {
-          if (++spins > (1ll << 31)) { *err_flag = 1; break; }                 // never hang the GPU
+    double* pbuf = partials + (size_t)((it + 1) & 1) * nb * MT;      // double-buffered block partials
+    // ---- local pass (it == -1: first denominators only)
+    if (RESIDENT) {
+      double acc[MH];
+#pragma unroll
+      for (int j = 0; j < MH; ++j) acc[j] = 0.0;
+      const double* ri = sm.rinv + half * MH;
+#pragma unroll
+      for (int sw = 0; sw < kSweeps; ++sw) {      // a thread owns the same <= kSweeps rows in every iteration: w stays in registers
+        const int rb = warp * 16 + sw * GYNC_EM_WARPS * 16;
+        if (rb < nrows) {                          // warp-uniform
+          const int r = rb + rl;
+          const bool valid = r < nrows;
+          const double* p = sL + (size_t)(half * MH) * R + (valid ? r : 0);
+          double l[MH];
+#pragma unroll
+          for (int j = 0; j < MH; ++j) l[j] = (valid && (FULL || half * MH + j < M)) ? p[(size_t)j * R] : 0.0;
+          double wk = wreg[sw];
+          if (it >= 0) {
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int j = 0; j + 1 < MH; j += 2) { s0 = fma(l[j], ri[j], s0); s1 = fma(l[j + 1], ri[j + 1], s1); }
+            if (MH & 1) s0 = fma(l[MH - 1], ri[MH - 1], s0);
+            double s = s0 + s1;
+            s += __shfl_xor_sync(0xffffffffu, s, 16);
+            wk = wk * invM * s;
+            wreg[sw] = wk;
+            if (valid && half == 0) {
+              w[row0 + r] = wk;
+              if (history) history[(size_t)it * K + row0 + r] = wk;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < MH; ++j) acc[j] = fma(l[j], wk, acc[j]);
         }
       }
-      __threadfence_system();
-      __syncthreads();
-      if (threadIdx.x < MT) {
-        double v = 0.0;
-        const volatile double* mb = peer.mail[peer.rank] + (size_t)slot * peer.world * MT;
-        for (int r = 0; r < peer.world; ++r) v += mb[(size_t)r * MT + threadIdx.x];   // rank order: identical everywhere
-        gnorm[slot * MT + threadIdx.x] = (threadIdx.x < M) ? 1.0 / v : 0.0;
+      em_block_reduce<MH>(acc, sm, pbuf + (size_t)blockIdx.x * MT, M);
+    } else if (it < 0) {
+      em_norms_pass<MH, FULL>(w, L, K, M, sm, pbuf + (size_t)blockIdx.x * MT);
+    } else {
+      em_step_pass<MH, FULL>(w, L, K, M, sm, pbuf + (size_t)blockIdx.x * MT, history ? history + (size_t)it * K : nullptr);
+    }
+    // ---- arrive
+    const unsigned long long seq = sync.seq0 + (unsigned long long)(it + 1);
+    const int slot = (int)(seq & 1ull);
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(sync.arrive, 1ull);
+    }
+    if (peer.world == 1) {
+      // single GPU: every block waits for all arrivals and gathers the partials itself (same fixed order
+      // everywhere) — two L2 round trips shorter than publish-and-poll through block 0
+      if (threadIdx.x == 0) {
+        const unsigned long long want = sync.arrive0 + (unsigned long long)nb * (unsigned long long)(it + 2);
+        volatile unsigned long long* a = sync.arrive;
+        long long spins = 0;
+        while (*a < want) { if (++spins > (1ll << 31)) { *err_flag = 1; break; } }
+        __threadfence();
       }
+      __syncthreads();
+      em_gather_partials<MH>(partials + (size_t)((it + 1) & 1) * nb * MT, nb, M, sm, sm.rinv, true);
+      continue;
+    }
+    if (blockIdx.x == 0) {
+      if (threadIdx.x == 0) {
+        const unsigned long long want = sync.arrive0 + (unsigned long long)nb * (unsigned long long)(it + 2);
+        volatile unsigned long long* a = sync.arrive;
+        long long spins = 0;
+        while (*a < want) { if (++spins > (1ll << 31)) { *err_flag = 1; break; } }
+        __threadfence();
+      }
+      __syncthreads();
+      em_gather_partials<MH>(pbuf, nb, M, sm, sm.rinv, false);                // this GPU's denominators (fixed order)
+      if (peer.world > 1) {
+        for (int idx = threadIdx.x; idx < peer.world * MT; idx += GYNC_EM_THREADS) {
+          const int p = idx / MT, m = idx % MT;
+          peer.mail[p][((size_t)slot * peer.world + peer.rank) * MT + m] = sm.rinv[m];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < peer.world) {
+          volatile unsigned long long* f = peer.flag[threadIdx.x] + (size_t)slot * peer.world + peer.rank;
+          *f = seq;
+          volatile unsigned long long* g = peer.flag[peer.rank] + (size_t)slot * peer.world + threadIdx.x;
+          long long spins = 0;
+          while (*g < seq) { if (++spins > (1ll << 31)) { *err_flag = 1; break; } }
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < MT) {
+          double v = 0.0;
+          const volatile double* mb = peer.mail[peer.rank] + (size_t)slot * peer.world * MT;
+          for (int r = 0; r < peer.world; ++r) v += mb[(size_t)r * MT + threadIdx.x];     // rank order: identical everywhere
+          sm.rinv[threadIdx.x] = v;
+        }
+        __syncthreads();
+      }
+      if (threadIdx.x < MT) gnorm[slot * MT + threadIdx.x] = (threadIdx.x < M) ? 1.0 / sm.rinv[threadIdx.x] : 0.0;
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) { volatile unsigned long long* rd = sync.ready; *rd = seq; }
+    }
+    // ---- everybody: wait for the published denominators
+    if (threadIdx.x == 0) {
+      volatile unsigned long long* rd = sync.ready;
+      long long spins = 0;
+      while (*rd < seq) { if (++spins > (1ll << 31)) { *err_flag = 1; break; } }
       __threadfence();
     }
-    grid.sync();
+    __syncthreads();
     if (threadIdx.x < MT) sm.rinv[threadIdx.x] = __ldcg(gnorm + slot * MT + threadIdx.x);
     __syncthreads();
   }

@@ -70,7 +70,7 @@ class DeviceEM:
 class FusedEM:
     """Row shard of (w, L) on this rank's GPU, iterated by the FUSED kernel: EM step + allreduce of the M
     denominators in one persistent cooperative launch per rank, partial sums exchanged through
-    cudaIpc-mapped peer mailboxes over NVLink (csrc/gync_kernels.cuh: gync_em_fused_kernel).
+    cudaIpc-mapped peer mailboxes over NVLink (csrc/gync_kernels.cuh: gync_em_kernel with peers).
     `torch.distributed` is used once, to exchange the 64-byte IPC handles."""
 
     def __init__(self, w_local, L_local_colmajor, world=1, rank=0, all_gather_bytes=None):
