@@ -255,13 +255,16 @@ def main():
     step_e2e()
     barrier()
     t0 = time.perf_counter()
+    e2e_steps = []
     for _ in range(args.steps):
+        t1 = time.perf_counter()
         step_e2e()
+        e2e_steps.append((time.perf_counter() - t1) * 1e3)
     barrier()
     ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
     e2e = {"value": world * N_SAMPLES / (ms_e2e * 1e-3), "unit": UNIT,
            "h2d_bytes_per_step": int(N_SAMPLES * 116 * 8 + 124 * 8 + 8), "d2h_bytes_per_step": int(N_SAMPLES * 12),
-           "ms_per_step": ms_e2e, "llh_checksum": float(np.nansum(LLh[np.isfinite(LLh)]))}
+           "ms_per_step": ms_e2e, "ms_each_step_rank0": e2e_steps, "llh_checksum": float(np.nansum(LLh[np.isfinite(LLh)]))}
 
     # ---- cfg 3 pipeline (device-resident): 1e5 x 40 likelihood matrix -> WeightedChain normalisation -> 100 EM steps
     cfg3 = None
