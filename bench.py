@@ -147,6 +147,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-em", action="store_true", help="skip the EM leg")
+    ap.add_argument("--no-eb", action="store_true", help="skip the empirical-Bayes (likelihoodmat / regulariser) leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -276,6 +277,11 @@ def main():
     if not args.no_em:
         em = em_leg(lib, L, torch, dist, dev, stream, world, rank, barrier, max_over_ranks)
 
+    # ---- §8f rows 2-3: alternative likelihood-matrix builder + regulariser gradients (device-resident)
+    ebr = None
+    if world == 1 and not args.no_eb:
+        ebr = eb_leg(lib, L, torch, dev, stream)
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
@@ -286,6 +292,8 @@ def main():
         if em:
             line["em"] = em
             line["roofline_em"] = em.get("roofline")
+        if ebr:
+            line["eb"] = ebr
         if world == 1 and not args.no_cpu:
             cb, _ = cpu_reference_leg(2, 1)
             line["cpu_baseline"] = cb
@@ -333,6 +341,80 @@ def cfg3_leg(lib, L, torch, dev, stream, dX, Xh, op, M=40, niter=100):
             "sample_patient_evals_per_s": K * M / t_ll * 1e3, "normalize_ms": t_nm, "em_iters": niter, "em_ms": t_em,
             "sum_w": float(dW.sum().item()), "colsum_min": float(dLL.sum(1).min().item()),
             "note": "one forward solve per sample serves all 40 patients (the reference re-solves per patient)"}
+
+
+def eb_leg(lib, L, torch, dev, stream, K=10_000, M=40, D=124):
+    """likelihoodmat_nanfast (eb/likelihoodmat.jl:34) at the cfg-3 shape (1e5 x 40, 124 = 31 days x 4 hormones) and as the
+    K x K z-matrix of hz (regularizers.jl:26); then the regulariser gradients on the resident matrices:
+    dhzdiscr = two HBM passes over the Z x K matrix (800 MB at K = 1e4), dlogl on K x M, and one projected ascent step."""
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(99)
+    sig = torch.tensor(np.tile(np.array([12.0, 1.0, 40.0, 1.5]), (31, 1)).ravel(order="F"), device=dev)
+
+    def timed(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        best = None
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        return best
+
+    out = {}
+    # (1) 1e5 samples (sample-major trajectories, no NaN) x 40 patients (40 % missing)
+    I, J = 100_000, M
+    A = torch.randn(D, I, dtype=torch.float64, device=dev, generator=gen)              # row-major D x I: stride_k = I, stride_i = 1
+    B = torch.randn(J, D, dtype=torch.float64, device=dev, generator=gen)              # column-major D x J
+    B[torch.rand(J, D, device=dev, generator=gen) < 0.4] = float("nan")
+    Lm = torch.empty(J, I, dtype=torch.float64, device=dev)
+    ms = timed(lambda: L.check(lib.gync_likelihoodmat_dev(A.data_ptr(), I, I, 1, B.data_ptr(), J, 1, D, D, sig.data_ptr(), 1,
+                                                          Lm.data_ptr(), stream)))
+    out["likelihoodmat_1e5x40"] = {"ms": ms, "pairs_per_s": I * J / ms * 1e3, "fp64_instr_per_pair_k": 5,
+                                   "TFLOPs_fp64_instr": 5 * I * J * D / ms * 1e-9,
+                                   "algorithmic_GBps": (8 * D * (I + J) + 2 * 8 * I * J) / ms / 1e6}
+    del A, B, Lm
+    # (2) the z-matrix of hz: K x K, no NaN (zs = ys + noise)
+    Y = torch.randn(D, K, dtype=torch.float64, device=dev, generator=gen) * 0.3
+    Zs = Y + torch.randn(D, K, dtype=torch.float64, device=dev, generator=gen) * 0.1
+    Lz = torch.empty(K, K, dtype=torch.float64, device=dev)
+    ms = timed(lambda: L.check(lib.gync_likelihoodmat_dev(Zs.data_ptr(), K, K, 1, Y.data_ptr(), K, K, 1, D, sig.data_ptr(), 1,
+                                                          Lz.data_ptr(), stream)))
+    out["likelihoodmat_1e4x1e4"] = {"ms": ms, "pairs_per_s": K * K / ms * 1e3, "fp64_instr_per_pair_k": 3,
+                                    "TFLOPs_fp64_instr": 3 * K * K * D / ms * 1e-9,
+                                    "algorithmic_GBps": (2 * 8 * D * K + 2 * 8 * K * K) / ms / 1e6}
+    # (3) gradients on resident matrices
+    Ld = torch.rand(M, K, dtype=torch.float64, device=dev, generator=gen)
+    h = C.c_void_p()
+    L.check(lib.gync_ebmodel_from_matrices(L.dptr(np.asfortranarray(Ld.cpu().numpy().T)), K, M,
+                                           L.dptr(np.asfortranarray(Lz.cpu().numpy().T)), K, C.byref(h)))
+    del Lz, Y, Zs
+    w = torch.full((K,), 1.0 / K, dtype=torch.float64, device=dev)
+    reps = 10
+    ms = timed(lambda: L.check(lib.gync_ebmodel_grad_dev(h, w.data_ptr(), 1, reps, stream))) / reps
+    by = 2 * 8 * K * K + 8 * 8 * K
+    out["dhzdiscr_1e4x1e4"] = {"us": ms * 1e3, "algorithmic_bytes": by, "algorithmic_GBps": by / ms / 1e6,
+                               "frac_of_hbm": by / ms / 1e6 / hbm, "launches_per_gradient": 5,
+                               "note": "rho = Lz w, then Lz' (wz ./ rho): the matrix (800 MB > L2) is read twice"}
+    ms = timed(lambda: L.check(lib.gync_ebmodel_grad_dev(h, w.data_ptr(), 2, reps, stream))) / reps
+    out["dlogl_1e4x40"] = {"us": ms * 1e3, "launches_per_gradient": 4}
+    wh = np.full(K, 1.0 / K)
+    t0 = time.perf_counter()
+    L.check(lib.gync_ebmodel_mple(h, L.dptr(wh), 0.5, 1e-6, 20, 0, None))
+    out["mple_20_steps_host_call_ms"] = (time.perf_counter() - t0) * 1e3
+    out["mple_sum_w"] = float(wh.sum())
+    lib.gync_ebmodel_destroy(h)
+    return out
 
 
 def flops_per_step(lib):

@@ -1,0 +1,495 @@
+// C ABI, part 3: empirical-Bayes callers of the likelihood matrix:
+// likelihoodmat_nanfast, LikelihoodModel + logl/dlogl/hz/dhz, projectsimplex, gradient ascent (mple), gyncmodel's phi.
+// (included at the end of gync_b200.cu)
+#include "gync_eb.cuh"
+
+namespace {
+
+int lmat_launch(const double* dA, int64_t I, int64_t sa_k, int64_t sa_i, const double* dB, int64_t J, int64_t sb_k,
+                int64_t sb_j, int D, const double* d_sig, int renorm, double* dL, cudaStream_t s) {
+  if (I == 0 || J == 0) return GYNC_OK;
+  const int64_t gx = (I + GYNC_LM_T - 1) / GYNC_LM_T, gy = (J + GYNC_LM_T - 1) / GYNC_LM_T;
+  if (gy > 65535) return fail(GYNC_ERR_ARG, "likelihoodmat: more than 4.19 M columns");
+  const int64_t nblk = gx * gy;
+  ABuf red;
+  CK(red.alloc(sizeof(double) * (2 * nblk + 2), s));
+  double* bmin = red.as<double>();
+  double* bmax = bmin + nblk;
+  double* scal = bmax + nblk;
+  CK(cudaFuncSetAttribute(gync_lmat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GyncLmSmem)));
+  gync_lmat_kernel<<<dim3((unsigned)gx, (unsigned)gy), GYNC_LM_THREADS, sizeof(GyncLmSmem), s>>>(
+      dA, I, sa_k, sa_i, dB, J, sb_k, sb_j, D, d_sig, renorm, dL, bmin, bmax);
+  g_launches += 1;
+  if (renorm) {
+    gync_lmat_minmax_kernel<<<1, 1024, 0, s>>>(bmin, bmax, nblk, scal);
+    const int64_t n = I * J;
+    const unsigned nb = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)g_num_sms * 16);
+    gync_lmat_exp_kernel<<<nb, 256, 0, s>>>(dL, n, scal);
+    g_launches += 2;
+  }
+  CK(cudaGetLastError());
+  return GYNC_OK;
+}
+
+// y = A x (row sums): partials in `part`, number of partials returned
+int mv_n_launch(const double* A, int64_t R, int64_t C, const double* x, double* part, int* nparts, cudaStream_t s) {
+  const int64_t chunks = (C + GYNC_MV_CCHUNK - 1) / GYNC_MV_CCHUNK;
+  if (chunks > 65535) return fail(GYNC_ERR_ARG, "matvec: too many columns");
+  gync_gemv_n_kernel<<<dim3(blocks_for(R, GYNC_MV_THREADS), (unsigned)chunks), GYNC_MV_THREADS, 0, s>>>(A, R, C, R, x, part);
+  g_launches += 1;
+  *nparts = (int)chunks;
+  CK(cudaGetLastError());
+  return GYNC_OK;
+}
+
+int mv_t_rchunk(int64_t R, int64_t C) {
+  // enough CTAs to fill the GPU four times over when the matrix allows it
+  const int64_t colblocks = (C + GYNC_MV_TCOLS - 1) / GYNC_MV_TCOLS;
+  const int64_t want_rb = std::max<int64_t>(1, (4 * (int64_t)g_num_sms + colblocks - 1) / colblocks);
+  int64_t rc = (R + want_rb - 1) / want_rb;
+  rc = (rc + 255) / 256 * 256;
+  return (int)std::min<int64_t>(GYNC_MV_RCHUNK, std::max<int64_t>(256, rc));
+}
+
+// y = A' x (column sums)
+int mv_t_launch(const double* A, int64_t R, int64_t C, const double* x, double* part, int* nparts, cudaStream_t s) {
+  const int rchunk = mv_t_rchunk(R, C);
+  const int64_t rb = (R + rchunk - 1) / rchunk, cb = (C + GYNC_MV_TCOLS - 1) / GYNC_MV_TCOLS;
+  if (cb > 65535) return fail(GYNC_ERR_ARG, "matvec: too many columns");
+  gync_gemv_t_kernel<<<dim3((unsigned)rb, (unsigned)cb), GYNC_MV_THREADS, 0, s>>>(A, R, C, R, x, rchunk, part);
+  g_launches += 1;
+  *nparts = (int)rb;
+  CK(cudaGetLastError());
+  return GYNC_OK;
+}
+
+int mv_finish(const double* part, int nparts, int64_t n, int epi, double* out, double* out2, const double* rho, int zmult,
+              int* nan_flag, cudaStream_t s) {
+  gync_mv_finish_kernel<<<blocks_for(n, 256), 256, 0, s>>>(part, nparts, n, epi, out, out2, rho, zmult, nan_flag);
+  g_launches += 1;
+  CK(cudaGetLastError());
+  return GYNC_OK;
+}
+
+size_t mv_part_doubles(int64_t R, int64_t C) {
+  const int64_t n_parts = (C + GYNC_MV_CCHUNK - 1) / GYNC_MV_CCHUNK;
+  const int64_t t_parts = (R + 255) / 256;     // upper bound: the smallest row chunk is 256
+  return (size_t)std::max<int64_t>(n_parts * R, t_parts * C);
+}
+
+}  // namespace
+
+// LikelihoodModel (eb/likelihoodmodel.jl:3-14) with both likelihood matrices resident in HBM:
+//   Ld = likelihoodmat(ys, datas, measerr)      K x M   (its transpose is what logl/dlogl use, regularizers.jl:3,8)
+//   Lz = likelihoodmat(zs, ys, zsampledistr)    Z x K   (hz/dhz, regularizers.jl:26,60)
+struct gync_ebmodel {
+  int device = -1;
+  int64_t K = 0, M = 0, Z = 0;
+  int zmult = 0;
+  double *Ld = nullptr, *Lz = nullptr;
+  double *part = nullptr, *rho = nullptr, *fac = nullptr, *norms = nullptr, *rnorm = nullptr;
+  double *ga = nullptr, *gb = nullptr, *y = nullptr, *w = nullptr, *scal = nullptr;
+  GyncPsPart* ps = nullptr;
+  int* flags = nullptr;     // [0] zero flag of the ascent step, [1] NaN flag of dhz, [2] projection passes
+  int ps_grid = 0;
+};
+
+namespace {
+
+void ebmodel_free(gync_ebmodel* m) {
+  if (!m) return;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  if (m->device >= 0) cudaSetDevice(m->device);
+  for (double* p : {m->Ld, m->Lz, m->part, m->rho, m->fac, m->norms, m->rnorm, m->ga, m->gb, m->y, m->w, m->scal})
+    if (p) cudaFree(p);
+  if (m->ps) cudaFree(m->ps);
+  if (m->flags) cudaFree(m->flags);
+  cudaSetDevice(cur);
+  delete m;
+}
+
+int ps_grid_size(int64_t K, int* grid) {
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gync_ascent_step_kernel, GYNC_PS_THREADS, 0));
+  if (per_sm < 1) return fail(GYNC_ERR_CUDA, "ascent kernel does not fit on an SM");
+  *grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)g_num_sms, (K + GYNC_PS_THREADS - 1) / GYNC_PS_THREADS));
+  return GYNC_OK;
+}
+
+int ebmodel_alloc(gync_ebmodel* m) {
+  m->device = g_device;
+  const int64_t K = m->K, M = m->M, Z = m->Z;
+  CK(cudaMalloc((void**)&m->Ld, sizeof(double) * std::max<int64_t>(K * M, 1)));
+  if (Z > 0) CK(cudaMalloc((void**)&m->Lz, sizeof(double) * Z * K));
+  size_t pd = mv_part_doubles(K, std::max<int64_t>(M, 1));
+  if (Z > 0) pd = std::max(pd, mv_part_doubles(Z, K));
+  CK(cudaMalloc((void**)&m->part, sizeof(double) * pd));
+  CK(cudaMalloc((void**)&m->rho, sizeof(double) * std::max<int64_t>(Z, 1)));
+  CK(cudaMalloc((void**)&m->fac, sizeof(double) * std::max<int64_t>(Z, 1)));
+  CK(cudaMalloc((void**)&m->norms, sizeof(double) * std::max<int64_t>(M, 1)));
+  CK(cudaMalloc((void**)&m->rnorm, sizeof(double) * std::max<int64_t>(M, 1)));
+  CK(cudaMalloc((void**)&m->ga, sizeof(double) * K));
+  CK(cudaMalloc((void**)&m->gb, sizeof(double) * K));
+  CK(cudaMalloc((void**)&m->y, sizeof(double) * K));
+  CK(cudaMalloc((void**)&m->w, sizeof(double) * K));
+  CK(cudaMalloc((void**)&m->scal, sizeof(double) * 4));
+  if (int rc = ps_grid_size(K, &m->ps_grid)) return rc;
+  CK(cudaMalloc((void**)&m->ps, sizeof(GyncPsPart) * 2 * m->ps_grid));
+  CK(cudaMalloc((void**)&m->flags, sizeof(int) * 4));
+  CK(cudaMemset(m->flags, 0, sizeof(int) * 4));
+  return GYNC_OK;
+}
+
+// norms = Ld' w, rnorm = 1 ./ norms
+int eb_norms(gync_ebmodel* m, const double* dw, cudaStream_t s) {
+  int np = 0;
+  if (int rc = mv_t_launch(m->Ld, m->K, m->M, dw, m->part, &np, s)) return rc;
+  return mv_finish(m->part, np, m->M, GYNC_EPI_RECIP, m->norms, m->rnorm, nullptr, 0, nullptr, s);
+}
+
+// dlogl(w) = sum(L ./ (L*w), 1) with L = Ld' (regularizers.jl:7-10)  ->  out (K)
+int eb_dlogl(gync_ebmodel* m, const double* dw, double* out, cudaStream_t s) {
+  if (int rc = eb_norms(m, dw, s)) return rc;
+  int np = 0;
+  if (int rc = mv_n_launch(m->Ld, m->K, m->M, m->rnorm, m->part, &np, s)) return rc;
+  return mv_finish(m->part, np, m->K, GYNC_EPI_PLAIN, out, nullptr, nullptr, 0, nullptr, s);
+}
+
+// rho = Lz w (regularizers.jl:36,65)
+int eb_rho(gync_ebmodel* m, const double* dw, cudaStream_t s) {
+  int np = 0;
+  if (int rc = mv_n_launch(m->Lz, m->Z, m->K, dw, m->part, &np, s)) return rc;
+  return mv_finish(m->part, np, m->Z, GYNC_EPI_PLAIN, m->rho, nullptr, nullptr, 0, nullptr, s);
+}
+
+// dhzdiscr / dhzcont (regularizers.jl:59-79, 50-57 + 149-160)  ->  out (K); sets flags[1] on NaN
+int eb_dhz(gync_ebmodel* m, const double* dw, int cont, double* out, cudaStream_t s) {
+  if (int rc = eb_rho(m, dw, s)) return rc;
+  gync_dhz_factors_kernel<<<blocks_for(m->Z, 256), 256, 0, s>>>(dw, m->K, m->zmult, m->rho, m->Z, cont, m->fac);
+  g_launches += 1;
+  int np = 0;
+  if (int rc = mv_t_launch(m->Lz, m->Z, m->K, m->fac, m->part, &np, s)) return rc;
+  return mv_finish(m->part, np, m->K, cont ? GYNC_EPI_DHZ_CONT : GYNC_EPI_DHZ_DISCR, out, nullptr, m->rho, m->zmult,
+                   m->flags + 1, s);
+}
+
+// one projected step on the device weights (in place); ga/gb may be NULL (pure projection)
+int eb_ascent_step(gync_ebmodel* m, double* dw, const double* ga, double ca, const double* gb, double cb, double h,
+                   double relstep, double* d_hist, cudaStream_t s) {
+  CK(cudaMemsetAsync(m->flags, 0, sizeof(int), s));
+  int64_t K = m->K;
+  GyncPsPart* ps = m->ps;
+  int* zf = m->flags;
+  int* npass = m->flags + 2;
+  double* y = m->y;
+  void* args[] = {&dw, &ga, &ca, &gb, &cb, &h, &K, &relstep, &y, &ps, &zf, &d_hist, &npass};
+  CK(cudaLaunchCooperativeKernel((void*)gync_ascent_step_kernel, dim3(m->ps_grid), dim3(GYNC_PS_THREADS), args, 0, s));
+  g_launches += 1;
+  return GYNC_OK;
+}
+
+int eb_check_model(gync_ebmodel* m, const void* w, const char* what) {
+  if (!m || !w) return fail(GYNC_ERR_ARG, std::string(what) + ": NULL argument");
+  if (int rc = ensure_init()) return rc;
+  if (m->device != g_device) return fail(GYNC_ERR_ARG, std::string(what) + ": model lives on another device");
+  return GYNC_OK;
+}
+
+}  // namespace
+
+// emiteration! for more than 64 data columns (em.jl:27-41 as written: norms = L'w, then w[k] <- w[k]/M * (L (1 ./ norms))[k]);
+// the persistent single-pass kernel keeps M/2 accumulators per thread and stops at M = 64.
+extern "C" int gync_em_iterate_generic(double* dw, const double* dL, int64_t K, int M, int niter, double* d_hist, cudaStream_t s) {
+  ABuf part, nr;
+  CK(part.alloc(sizeof(double) * mv_part_doubles(K, M), s));
+  CK(nr.alloc(sizeof(double) * (2 * (size_t)M + (size_t)K), s));
+  double* norms = nr.as<double>();
+  double* rnorm = norms + M;
+  for (int it = 0; it < niter; ++it) {
+    int np = 0;
+    if (int rc = mv_t_launch(dL, K, M, dw, part.as<double>(), &np, s)) return rc;
+    if (int rc = mv_finish(part.as<double>(), np, M, GYNC_EPI_RECIP, norms, rnorm, nullptr, 0, nullptr, s)) return rc;
+    if (int rc = mv_n_launch(dL, K, M, rnorm, part.as<double>(), &np, s)) return rc;
+    if (int rc = mv_finish(part.as<double>(), np, K, GYNC_EPI_EM, dw, nullptr, nullptr, M, nullptr, s)) return rc;
+    if (d_hist) CK(cudaMemcpyAsync(d_hist + (size_t)it * K, dw, sizeof(double) * K, cudaMemcpyDeviceToDevice, s));
+  }
+  return GYNC_OK;
+}
+
+extern "C" {
+
+// ---- likelihoodmat_nanfast ---------------------------------------------------------------------
+int gync_likelihoodmat_dev(const double* dA, int64_t I, int64_t sa_k, int64_t sa_i, const double* dB, int64_t J,
+                           int64_t sb_k, int64_t sb_j, int32_t D, const double* d_sigmas, int32_t renormalize, double* dL,
+                           void* stream) {
+  if (I < 0 || J < 0 || D < 1 || !d_sigmas || (I > 0 && J > 0 && (!dA || !dB || !dL)))
+    return fail(GYNC_ERR_ARG, "gync_likelihoodmat: bad arguments");
+  if (int rc = ensure_init()) return rc;
+  return lmat_launch(dA, I, sa_k, sa_i, dB, J, sb_k, sb_j, D, d_sigmas, renormalize, dL, (cudaStream_t)stream);
+}
+
+int gync_likelihoodmat(const double* xs, int64_t I, const double* ys, int64_t J, int32_t D, const double* sigmas,
+                       int32_t renormalize, double* L) {
+  if (I < 0 || J < 0 || D < 1 || !sigmas || (I > 0 && J > 0 && (!xs || !ys || !L)))
+    return fail(GYNC_ERR_ARG, "gync_likelihoodmat: bad arguments");
+  if (int rc = ensure_init()) return rc;
+  if (I == 0 || J == 0) return GYNC_OK;
+  DBuf dA, dB, dS, dL;
+  CK(dA.alloc(sizeof(double) * D * I));
+  CK(dB.alloc(sizeof(double) * D * J));
+  CK(dS.alloc(sizeof(double) * D));
+  CK(dL.alloc(sizeof(double) * I * J));
+  CK(cudaMemcpyAsync(dA.p, xs, sizeof(double) * D * I, cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemcpyAsync(dB.p, ys, sizeof(double) * D * J, cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemcpyAsync(dS.p, sigmas, sizeof(double) * D, cudaMemcpyHostToDevice, g_stream));
+  if (int rc = lmat_launch(dA.as<double>(), I, 1, D, dB.as<double>(), J, 1, D, D, dS.as<double>(), renormalize,
+                           dL.as<double>(), g_stream)) return rc;
+  CK(cudaMemcpyAsync(L, dL.p, sizeof(double) * I * J, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
+  return GYNC_OK;
+}
+
+// ---- phi(x) = forwardsol(x)[:, measuredinds] on t = 0:30 (eb/gync.jl:11, regularizers.jl:215) ----
+int gync_phi_batch(const double* X, int64_t N, const gync_solver_opts* opts, double* Yphi, int32_t* status) {
+  if (N < 0 || (N > 0 && (!X || !Yphi))) return fail(GYNC_ERR_ARG, "gync_phi_batch: bad arguments");
+  if (int rc = ensure_init()) return rc;
+  if (N == 0) return GYNC_OK;
+  const int nT = 31;
+  double t[31];
+  for (int k = 0; k < nT; ++k) t[k] = (double)k;
+  DBuf dX, dT, dY, dSt, dP;
+  CK(dX.alloc(sizeof(double) * N * GYNC_NX));
+  CK(dT.alloc(sizeof(double) * nT));
+  CK(dY.alloc(sizeof(double) * N * nT * GYNC_NY));
+  CK(dSt.alloc(sizeof(int32_t) * N));
+  CK(dP.alloc(sizeof(double) * N * 124));
+  CK(cudaMemcpyAsync(dX.p, X, sizeof(double) * N * GYNC_NX, cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemcpyAsync(dT.p, t, sizeof(double) * nT, cudaMemcpyHostToDevice, g_stream));
+  if (int rc = prep_solver_kernel(gync_solve_kernel<GYNC_SOLVE_BLOCK>, GyncWorkSm<GYNC_SOLVE_BLOCK>::kSmemBytes, GYNC_SOLVE_BLOCK)) return rc;
+  gync_solve_kernel<GYNC_SOLVE_BLOCK><<<std::min<unsigned>(blocks_for(N, GYNC_SOLVE_BLOCK), g_num_sms), GYNC_SOLVE_BLOCK,
+                                         GyncWorkSm<GYNC_SOLVE_BLOCK>::kSmemBytes, g_stream>>>(
+      dX.as<double>(), nullptr, nullptr, N, dT.as<double>(), nT, to_opts(opts), dY.as<double>(), dSt.as<int32_t>());
+  gync_pick_measured_kernel<<<blocks_for(N * 124, 256), 256, 0, g_stream>>>(dY.as<double>(), N, nT, dP.as<double>());
+  g_launches += 2;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(Yphi, dP.p, sizeof(double) * N * 124, cudaMemcpyDeviceToHost, g_stream));
+  if (status) CK(cudaMemcpyAsync(status, dSt.p, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
+  return GYNC_OK;
+}
+
+// ---- projectsimplex!(y) ------------------------------------------------------------------------
+int gync_projectsimplex(double* yv, int64_t K) {
+  if (K < 1 || !yv) return fail(GYNC_ERR_ARG, "gync_projectsimplex: bad arguments");
+  if (int rc = ensure_init()) return rc;
+  gync_ebmodel tmp;
+  tmp.K = K;
+  tmp.device = g_device;
+  DBuf dw, dy, dps, dfl;
+  if (int rc = ps_grid_size(K, &tmp.ps_grid)) return rc;
+  CK(dw.alloc(sizeof(double) * K));
+  CK(dy.alloc(sizeof(double) * K));
+  CK(dps.alloc(sizeof(GyncPsPart) * 2 * tmp.ps_grid));
+  CK(dfl.alloc(sizeof(int) * 4));
+  tmp.y = dy.as<double>();
+  tmp.ps = dps.as<GyncPsPart>();
+  tmp.flags = dfl.as<int>();
+  CK(cudaMemcpyAsync(dw.p, yv, sizeof(double) * K, cudaMemcpyHostToDevice, g_stream));
+  // relstep = 1: movefromboundary is the identity, the result is the projection itself
+  if (int rc = eb_ascent_step(&tmp, dw.as<double>(), nullptr, 0.0, nullptr, 0.0, 0.0, 1.0, nullptr, g_stream)) return rc;
+  CK(cudaMemcpyAsync(yv, dw.p, sizeof(double) * K, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
+  return GYNC_OK;
+}
+
+// ---- LikelihoodModel ---------------------------------------------------------------------------
+void gync_ebmodel_destroy(gync_ebmodel* m) { ebmodel_free(m); }
+
+int gync_ebmodel_create(const double* ys, int64_t K, const double* datas, int64_t M, const double* zs, int64_t Z,
+                        int32_t D, const double* sig_meas, const double* sig_z, gync_ebmodel** out) {
+  if (K < 1 || M < 0 || Z < 0 || D < 1 || !ys || !sig_meas || !out || (M > 0 && !datas) || (Z > 0 && !zs) || (Z % K) != 0)
+    return fail(GYNC_ERR_ARG, "gync_ebmodel_create: bad arguments (length(zs) must be a multiple of length(ys))");
+  if (int rc = ensure_init()) return rc;
+  gync_ebmodel* m = new gync_ebmodel();
+  m->K = K; m->M = M; m->Z = Z; m->zmult = (int)(Z / K);
+  int rc = ebmodel_alloc(m);
+  DBuf dY, dB, dS;
+  auto up = [&](DBuf& b, const double* h, size_t n) -> int {
+    CK(b.alloc(sizeof(double) * n));
+    CK(cudaMemcpyAsync(b.p, h, sizeof(double) * n, cudaMemcpyHostToDevice, g_stream));
+    return GYNC_OK;
+  };
+  if (!rc) rc = up(dY, ys, (size_t)D * K);
+  if (!rc) rc = up(dS, sig_meas, (size_t)D);
+  if (!rc && M > 0) {
+    rc = up(dB, datas, (size_t)D * M);
+    if (!rc) rc = lmat_launch(dY.as<double>(), K, 1, D, dB.as<double>(), M, 1, D, D, dS.as<double>(), 1, m->Ld, g_stream);
+  }
+  if (!rc && Z > 0) {
+    DBuf dZ, dSz;
+    rc = up(dZ, zs, (size_t)D * Z);
+    if (!rc && sig_z) rc = up(dSz, sig_z, (size_t)D);
+    if (!rc) rc = lmat_launch(dZ.as<double>(), Z, 1, D, dY.as<double>(), K, 1, D, D, sig_z ? dSz.as<double>() : dS.as<double>(),
+                              1, m->Lz, g_stream);
+    if (!rc && cudaStreamSynchronize(g_stream) != cudaSuccess) rc = fail(GYNC_ERR_CUDA, "gync_ebmodel_create: kernel failed");
+  }
+  if (!rc && cudaStreamSynchronize(g_stream) != cudaSuccess) rc = fail(GYNC_ERR_CUDA, "gync_ebmodel_create: kernel failed");
+  if (rc) { ebmodel_free(m); return rc; }
+  *out = m;
+  return GYNC_OK;
+}
+
+int gync_ebmodel_from_matrices(const double* Ld, int64_t K, int64_t M, const double* Lz, int64_t Z, gync_ebmodel** out) {
+  if (K < 1 || M < 0 || Z < 0 || !out || (M > 0 && !Ld) || (Z > 0 && !Lz) || (Z % K) != 0)
+    return fail(GYNC_ERR_ARG, "gync_ebmodel_from_matrices: bad arguments");
+  if (int rc = ensure_init()) return rc;
+  gync_ebmodel* m = new gync_ebmodel();
+  m->K = K; m->M = M; m->Z = Z; m->zmult = (int)(Z / K);
+  int rc = ebmodel_alloc(m);
+  if (!rc && M > 0 && cudaMemcpyAsync(m->Ld, Ld, sizeof(double) * K * M, cudaMemcpyHostToDevice, g_stream) != cudaSuccess) rc = fail(GYNC_ERR_CUDA, "upload Ld");
+  if (!rc && Z > 0 && cudaMemcpyAsync(m->Lz, Lz, sizeof(double) * Z * K, cudaMemcpyHostToDevice, g_stream) != cudaSuccess) rc = fail(GYNC_ERR_CUDA, "upload Lz");
+  if (!rc && cudaStreamSynchronize(g_stream) != cudaSuccess) rc = fail(GYNC_ERR_CUDA, "gync_ebmodel_from_matrices: copy failed");
+  if (rc) { ebmodel_free(m); return rc; }
+  *out = m;
+  return GYNC_OK;
+}
+
+int gync_ebmodel_dims(gync_ebmodel* m, int64_t* K, int64_t* M, int64_t* Z) {
+  if (!m) return fail(GYNC_ERR_ARG, "gync_ebmodel_dims: NULL");
+  if (K) *K = m->K;
+  if (M) *M = m->M;
+  if (Z) *Z = m->Z;
+  return GYNC_OK;
+}
+
+int gync_ebmodel_matrices(gync_ebmodel* m, double* Ld, double* Lz) {
+  if (int rc = eb_check_model(m, m, "gync_ebmodel_matrices")) return rc;
+  if (Ld && m->M > 0) CK(cudaMemcpyAsync(Ld, m->Ld, sizeof(double) * m->K * m->M, cudaMemcpyDeviceToHost, g_stream));
+  if (Lz && m->Z > 0) CK(cudaMemcpyAsync(Lz, m->Lz, sizeof(double) * m->Z * m->K, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
+  return GYNC_OK;
+}
+
+// device pointers of the resident matrices (for callers that keep working on the device: EM, bench)
+int gync_ebmodel_device_ptrs(gync_ebmodel* m, double** dLd, double** dLz) {
+  if (!m) return fail(GYNC_ERR_ARG, "gync_ebmodel_device_ptrs: NULL");
+  if (dLd) *dLd = m->Ld;
+  if (dLz) *dLz = m->Lz;
+  return GYNC_OK;
+}
+
+int gync_ebmodel_logl(gync_ebmodel* m, const double* w, double* out) {
+  if (int rc = eb_check_model(m, w, "gync_ebmodel_logl")) return rc;
+  if (!out || m->M < 1) return fail(GYNC_ERR_ARG, "gync_ebmodel_logl: no data matrix / NULL output");
+  CK(cudaMemcpyAsync(m->w, w, sizeof(double) * m->K, cudaMemcpyHostToDevice, g_stream));
+  if (int rc = eb_norms(m, m->w, g_stream)) return rc;
+  gync_logsum_kernel<<<1, 1024, 0, g_stream>>>(m->norms, m->M, nullptr, 1, 1.0, 1.0, 0, m->scal);
+  g_launches += 1;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, m->scal, sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
+  return GYNC_OK;
+}
+
+int gync_ebmodel_dlogl(gync_ebmodel* m, const double* w, double* d) {
+  if (int rc = eb_check_model(m, w, "gync_ebmodel_dlogl")) return rc;
+  if (!d || m->M < 1) return fail(GYNC_ERR_ARG, "gync_ebmodel_dlogl: no data matrix / NULL output");
+  CK(cudaMemcpyAsync(m->w, w, sizeof(double) * m->K, cudaMemcpyHostToDevice, g_stream));
+  if (int rc = eb_dlogl(m, m->w, m->ga, g_stream)) return rc;
+  CK(cudaMemcpyAsync(d, m->ga, sizeof(double) * m->K, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
+  return GYNC_OK;
+}
+
+// hz(wx, Lzx, wz) (regularizers.jl:30-45); wz == NULL -> repeatweights(w, zs)
+int gync_ebmodel_hz(gync_ebmodel* m, const double* w, const double* wz, double* out) {
+  if (int rc = eb_check_model(m, w, "gync_ebmodel_hz")) return rc;
+  if (!out || m->Z < 1) return fail(GYNC_ERR_ARG, "gync_ebmodel_hz: no z matrix / NULL output");
+  CK(cudaMemcpyAsync(m->w, w, sizeof(double) * m->K, cudaMemcpyHostToDevice, g_stream));
+  if (int rc = eb_rho(m, m->w, g_stream)) return rc;
+  if (wz) {
+    CK(cudaMemcpyAsync(m->fac, wz, sizeof(double) * m->Z, cudaMemcpyHostToDevice, g_stream));
+    gync_logsum_kernel<<<1, 1024, 0, g_stream>>>(m->rho, m->Z, m->fac, m->Z, 1.0, -1.0, 1, m->scal);
+  } else {
+    gync_logsum_kernel<<<1, 1024, 0, g_stream>>>(m->rho, m->Z, m->w, m->K, (double)m->zmult, -1.0, 1, m->scal);
+  }
+  g_launches += 1;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, m->scal, sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
+  return GYNC_OK;
+}
+
+// dhz(w) = DHZCONT ? dhzcont : dhzdiscr (regularizers.jl:47-79); a NaN in the result is an error (:77)
+int gync_ebmodel_dhz(gync_ebmodel* m, const double* w, int32_t cont, double* d) {
+  if (int rc = eb_check_model(m, w, "gync_ebmodel_dhz")) return rc;
+  if (!d || m->Z < 1) return fail(GYNC_ERR_ARG, "gync_ebmodel_dhz: no z matrix / NULL output");
+  CK(cudaMemcpyAsync(m->w, w, sizeof(double) * m->K, cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemsetAsync(m->flags + 1, 0, sizeof(int), g_stream));
+  if (int rc = eb_dhz(m, m->w, cont, m->gb, g_stream)) return rc;
+  int nanflag = 0;
+  CK(cudaMemcpyAsync(d, m->gb, sizeof(double) * m->K, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaMemcpyAsync(&nanflag, m->flags + 1, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
+  if (nanflag) return fail(GYNC_ERR_NUMERIC, "encountered NaN in dhz");
+  return GYNC_OK;
+}
+
+// em(m, w0, niter) (likelihoodmodel.jl:17-20): emiterations on the resident data matrix; w in place, niter steps
+int gync_ebmodel_em(gync_ebmodel* m, double* w, int32_t niter, double* history) {
+  if (int rc = eb_check_model(m, w, "gync_ebmodel_em")) return rc;
+  if (niter < 0 || m->M < 1) return fail(GYNC_ERR_ARG, "gync_ebmodel_em: no data matrix / niter < 0");
+  if (niter == 0) return GYNC_OK;
+  DBuf dH;
+  if (history) CK(dH.alloc(sizeof(double) * m->K * niter));
+  CK(cudaMemcpyAsync(m->w, w, sizeof(double) * m->K, cudaMemcpyHostToDevice, g_stream));
+  if (int rc = gync_em_iterate_dev(m->w, m->Ld, m->K, (int32_t)m->M, niter, history ? dH.as<double>() : nullptr, g_stream)) return rc;
+  CK(cudaMemcpyAsync(w, m->w, sizeof(double) * m->K, cudaMemcpyDeviceToHost, g_stream));
+  if (history) CK(cudaMemcpyAsync(history, dH.p, sizeof(double) * m->K * niter, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
+  return GYNC_OK;
+}
+
+// gradientascent(dmple_obj(m, reg), w0, niter, h) (gradientascent.jl:1-5, likelihoodmodel.jl:33-64), device-resident:
+// nsteps iterations of  w <- movefromboundary(w, projectsimplex(w + h (reg dhz(w) + (1-reg) dlogl(w)))).
+// history (nullable): K x nsteps, column i = weights after step i+1.
+int gync_ebmodel_mple(gync_ebmodel* m, double* w, double reg, double h, int32_t nsteps, int32_t cont, double* history) {
+  if (int rc = eb_check_model(m, w, "gync_ebmodel_mple")) return rc;
+  if (nsteps < 0 || (reg != 0.0 && m->Z < 1) || (reg != 1.0 && m->M < 1))
+    return fail(GYNC_ERR_ARG, "gync_ebmodel_mple: the model lacks the matrix this regularisation weight needs");
+  if (nsteps == 0) return GYNC_OK;
+  cudaStream_t s = g_stream;
+  DBuf dH;
+  if (history) CK(dH.alloc(sizeof(double) * m->K * nsteps));
+  CK(cudaMemcpyAsync(m->w, w, sizeof(double) * m->K, cudaMemcpyHostToDevice, s));
+  CK(cudaMemsetAsync(m->flags + 1, 0, sizeof(int), s));
+  for (int it = 0; it < nsteps; ++it) {
+    const double* ga = nullptr;
+    const double* gb = nullptr;
+    if (reg != 0.0) { if (int rc = eb_dhz(m, m->w, cont, m->ga, s)) return rc; ga = m->ga; }
+    if (reg != 1.0) { if (int rc = eb_dlogl(m, m->w, m->gb, s)) return rc; gb = m->gb; }
+    const double ca = (reg == 1.0) ? 1.0 : reg, cb = (reg == 0.0) ? 1.0 : 1.0 - reg;   // likelihoodmodel.jl:57-63
+    if (int rc = eb_ascent_step(m, m->w, ga, ca, gb, cb, h, 0.5, history ? dH.as<double>() + (size_t)it * m->K : nullptr, s)) return rc;
+  }
+  int nanflag = 0;
+  CK(cudaMemcpyAsync(w, m->w, sizeof(double) * m->K, cudaMemcpyDeviceToHost, s));
+  if (history) CK(cudaMemcpyAsync(history, dH.p, sizeof(double) * m->K * nsteps, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&nanflag, m->flags + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (nanflag) return fail(GYNC_ERR_NUMERIC, "encountered NaN in dhz");
+  return GYNC_OK;
+}
+
+// timing hook for bench.py: `reps` gradient evaluations (dhz + dlogl) on the resident matrices, no host traffic
+int gync_ebmodel_grad_dev(gync_ebmodel* m, const double* dw, int32_t which /*1 dhz, 2 dlogl, 3 both*/, int32_t reps, void* stream) {
+  if (int rc = eb_check_model(m, dw, "gync_ebmodel_grad_dev")) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int r = 0; r < reps; ++r) {
+    if ((which & 1) && m->Z > 0) if (int rc = eb_dhz(m, dw, 0, m->ga, s)) return rc;
+    if ((which & 2) && m->M > 0) if (int rc = eb_dlogl(m, dw, m->gb, s)) return rc;
+  }
+  return GYNC_OK;
+}
+
+}  // extern "C"

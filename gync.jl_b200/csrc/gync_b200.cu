@@ -516,6 +516,7 @@ int gync_forwardsol(const double* X, int64_t N, const double* t, int32_t nT, con
 }
 
 // ------------------------------------------------------------------------------------------ K4
+int gync_em_iterate_generic(double* dw, const double* dL, int64_t K, int M, int niter, double* d_hist, cudaStream_t s);
 
 int gync_em_iterate_dev(double* dw, const double* dL, int64_t K, int32_t M, int32_t niter, double* d_history,
                         void* stream) {
@@ -523,6 +524,7 @@ int gync_em_iterate_dev(double* dw, const double* dL, int64_t K, int32_t M, int3
   if (int rc = ensure_init()) return rc;
   if (K == 0 || niter == 0) return GYNC_OK;
   cudaStream_t s = (cudaStream_t)stream;   // NULL = the legacy default stream, as torch uses
+  if (M > 64) return gync_em_iterate_generic(dw, dL, K, M, niter, d_history, s);
 #define CALL(MH, F) em_persistent_launch<MH, F>(dw, dL, K, M, niter, d_history, s)
   EM_DISPATCH(M, CALL);
 #undef CALL
@@ -601,3 +603,4 @@ int gync_fp64_peak(double* tflops) {
 }  // extern "C"
 
 #include "gync_abi_more.inl"
+#include "gync_abi_eb.inl"

@@ -42,6 +42,10 @@ EXPORTS = [
     "gync_flops_per_step", "gync_em_comm_create", "gync_em_comm_connect", "gync_em_comm_destroy",
     "gync_em_iterate_fused_dev", "gync_em_comm_error", "gync_wc_normalize_dev", "gync_init_multi", "gync_ndev",
     "gync_em_iterate_multi",
+    "gync_likelihoodmat", "gync_likelihoodmat_dev", "gync_phi_batch", "gync_projectsimplex", "gync_ebmodel_create",
+    "gync_ebmodel_from_matrices", "gync_ebmodel_destroy", "gync_ebmodel_dims", "gync_ebmodel_matrices",
+    "gync_ebmodel_device_ptrs", "gync_ebmodel_logl", "gync_ebmodel_dlogl", "gync_ebmodel_hz", "gync_ebmodel_dhz",
+    "gync_ebmodel_em", "gync_ebmodel_mple", "gync_ebmodel_grad_dev",
 ]
 
 _lib = None
@@ -90,6 +94,26 @@ def load():
     lib.gync_em_comm_destroy.restype = None
     lib.gync_em_iterate_fused_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
     lib.gync_em_comm_error.argtypes = [C.c_void_p]
+    lib.gync_likelihoodmat.argtypes = [c_double_p, C.c_int64, c_double_p, C.c_int64, C.c_int32, c_double_p, C.c_int32, c_double_p]
+    lib.gync_likelihoodmat_dev.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
+                                           C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.gync_phi_batch.argtypes = [c_double_p, C.c_int64, C.POINTER(SolverOpts), c_double_p, c_int32_p]
+    lib.gync_projectsimplex.argtypes = [c_double_p, C.c_int64]
+    lib.gync_ebmodel_create.argtypes = [c_double_p, C.c_int64, c_double_p, C.c_int64, c_double_p, C.c_int64, C.c_int32,
+                                        c_double_p, c_double_p, C.POINTER(C.c_void_p)]
+    lib.gync_ebmodel_from_matrices.argtypes = [c_double_p, C.c_int64, C.c_int64, c_double_p, C.c_int64, C.POINTER(C.c_void_p)]
+    lib.gync_ebmodel_destroy.argtypes = [C.c_void_p]
+    lib.gync_ebmodel_destroy.restype = None
+    lib.gync_ebmodel_dims.argtypes = [C.c_void_p, c_int64_p, c_int64_p, c_int64_p]
+    lib.gync_ebmodel_matrices.argtypes = [C.c_void_p, c_double_p, c_double_p]
+    lib.gync_ebmodel_device_ptrs.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    lib.gync_ebmodel_logl.argtypes = [C.c_void_p, c_double_p, c_double_p]
+    lib.gync_ebmodel_dlogl.argtypes = [C.c_void_p, c_double_p, c_double_p]
+    lib.gync_ebmodel_hz.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p]
+    lib.gync_ebmodel_dhz.argtypes = [C.c_void_p, c_double_p, C.c_int32, c_double_p]
+    lib.gync_ebmodel_em.argtypes = [C.c_void_p, c_double_p, C.c_int32, c_double_p]
+    lib.gync_ebmodel_mple.argtypes = [C.c_void_p, c_double_p, C.c_double, C.c_double, C.c_int32, C.c_int32, c_double_p]
+    lib.gync_ebmodel_grad_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
     _lib = lib
     return lib
 

@@ -27,6 +27,7 @@ extern "C" {
 #define GYNC_ERR_ARG    -1
 #define GYNC_ERR_CUDA   -2
 #define GYNC_ERR_NOMEM  -3
+#define GYNC_ERR_NUMERIC -4   /* the reference would have raised (e.g. "encountered NaN in dhz") */
 
 /* per-sample solver status bits */
 #define GYNC_STATUS_OK        0
@@ -145,6 +146,50 @@ int gync_wc_normalize(const double* LL, const double* logprior, const int64_t* c
 /* device-resident form: dLL is normalised in place (LL -> L), so K1 -> K5 -> K4 never leave HBM */
 int gync_wc_normalize_dev(double* dLL_inout, const double* d_logprior, const int64_t* d_counts, int64_t K, int32_t M,
                           double* d_weights, double* d_density, void* stream);
+
+/* ================= empirical-Bayes callers of the likelihood matrix (src/eb) ===================
+ * ---- likelihoodmat_nanfast(xs, ys, d::MatrixNormalCentered; renormalize) — eb/likelihoodmat.jl:34-58
+ *      (with sqeucdist_nan, :61-95).  xs: D x I (column i = vec(xs[i]), NaN = missing), ys: D x J, sigmas: D
+ *      (vec(d.sigmas)).  L: I x J.  The _dev form takes element strides (k, column) so that sample-major device
+ *      arrays need no transpose. */
+int gync_likelihoodmat(const double* xs, int64_t I, const double* ys, int64_t J, int32_t D, const double* sigmas,
+                       int32_t renormalize, double* L);
+int gync_likelihoodmat_dev(const double* dA, int64_t I, int64_t sa_k, int64_t sa_i, const double* dB, int64_t J,
+                           int64_t sb_k, int64_t sb_j, int32_t D, const double* d_sigmas, int32_t renormalize, double* dL,
+                           void* stream);
+/* ---- phi(x) = forwardsol(x)[:, measuredinds] on t = 0:30 — eb/gync.jl:11, eb/regularizers.jl:215.
+ *      X: N x 116 -> Yphi: 124 x N (column n = vec of the 31 x 4 matrix), NaN column on solver failure. */
+int gync_phi_batch(const double* X, int64_t N, const gync_solver_opts* opts, double* Yphi, int32_t* status);
+/* ---- projectsimplex!(y) — eb/projectsimplex.jl:8-46 (in place) */
+int gync_projectsimplex(double* y, int64_t K);
+/* ---- LikelihoodModel — eb/likelihoodmodel.jl:3-14.  Builds and keeps in HBM
+ *        Ld = likelihoodmat(ys, datas, measerr)     K x M   (em: likelihoodmodel.jl:17-20; logl/dlogl use its transpose)
+ *        Lz = likelihoodmat(zs, ys, zsampledistr)   Z x K   (hz/dhz: regularizers.jl:26,60), Z = zmult * K, may be 0
+ *      ys: D x K, datas: D x M, zs: D x Z, sig_*: D (sig_z NULL -> sig_meas, likelihoodmodel.jl:12-14). */
+typedef struct gync_ebmodel gync_ebmodel;
+int  gync_ebmodel_create(const double* ys, int64_t K, const double* datas, int64_t M, const double* zs, int64_t Z,
+                         int32_t D, const double* sig_meas, const double* sig_z, gync_ebmodel** out);
+int  gync_ebmodel_from_matrices(const double* Ld, int64_t K, int64_t M, const double* Lz, int64_t Z, gync_ebmodel** out);
+void gync_ebmodel_destroy(gync_ebmodel* m);
+int  gync_ebmodel_dims(gync_ebmodel* m, int64_t* K, int64_t* M, int64_t* Z);
+int  gync_ebmodel_matrices(gync_ebmodel* m, double* Ld /* K x M or NULL */, double* Lz /* Z x K or NULL */);
+int  gync_ebmodel_device_ptrs(gync_ebmodel* m, double** dLd, double** dLz);
+/* logl(m,w) = sum(log(L*w)), dlogl(m,w) = sum(L./(L*w),1) with L = Ld' — eb/regularizers.jl:3-10 */
+int  gync_ebmodel_logl(gync_ebmodel* m, const double* w, double* out);
+int  gync_ebmodel_dlogl(gync_ebmodel* m, const double* w, double* d /* K */);
+/* hz(wx, Lzx, wz) — regularizers.jl:30-45; wz NULL -> repeatweights(w, zs) (:16-19) */
+int  gync_ebmodel_hz(gync_ebmodel* m, const double* w, const double* wz, double* out);
+/* dhz(m,w): cont == 0 dhzdiscr (:59-79, the reference's DHZCONT = false), else dhzcont (:50-57,149-160).
+ * GYNC_ERR_NUMERIC when the result holds a NaN (:77). */
+int  gync_ebmodel_dhz(gync_ebmodel* m, const double* w, int32_t cont, double* d /* K */);
+/* em(m, w0, niter) — likelihoodmodel.jl:17-20: niter emiteration! steps on Ld, w in place */
+int  gync_ebmodel_em(gync_ebmodel* m, double* w, int32_t niter, double* history);
+/* gradientascent(dmple_obj(m,reg), w0, n, h) — eb/gradientascent.jl:1-25, likelihoodmodel.jl:33-64: nsteps times
+ *   w <- movefromboundary(w, projectsimplex(w + h (reg dhz(w) + (1-reg) dlogl(w)))), all on the device.
+ * history (nullable): K x nsteps, column i = weights after step i+1. */
+int  gync_ebmodel_mple(gync_ebmodel* m, double* w, double reg, double h, int32_t nsteps, int32_t cont, double* history);
+/* `reps` gradient evaluations on device weights, no host traffic (bench hook): which = 1 dhz, 2 dlogl, 3 both */
+int  gync_ebmodel_grad_dev(gync_ebmodel* m, const double* dw, int32_t which, int32_t reps, void* stream);
 
 /* FP64 flops of one RODAS4 step attempt (counted from the generated code; roofline bookkeeping). */
 double gync_flops_per_step(void);
