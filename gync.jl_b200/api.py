@@ -203,8 +203,6 @@ class Config:
             self.inity0 = refy0.copy()
         if self.priorparms is None:
             self.priorparms = priorparms(5 * self.initparms)
-        if self.adapt:
-            raise NotImplementedError("adapt=true (Mamba AMM adaptation) is outside this path's scope (SURVEY §8f-4)")
 
     @property
     def data(self):
@@ -300,6 +298,14 @@ class Variate:
     seed: int
     iteration: int = 0
     naccept: int = 0
+    # AMMTune adaptation state (Mamba): counter, running mean / second moment of the log-space
+    # states, factor of the adapted proposal.  m < 0: adaptation has not started.
+    m: int = -1
+    Mv: np.ndarray = None
+    Mvv: np.ndarray = None
+    SigmaLm: np.ndarray = None
+    beta: float = 0.05          # model.jl:105
+    scale: float = 2.38         # model.jl:106
 
 
 @dataclass
@@ -323,6 +329,17 @@ def new_sampling(c: Config, seed=0) -> Sampling:
     return Sampling(np.empty((0, 116)), c, SamplerVariate(c, seed))
 
 
+def propinit(s: "Sampling"):
+    """sampling.jl:17-20 — covariance of the initial proposal."""
+    return s.variate.SigmaL @ s.variate.SigmaL.T
+
+
+def propadapt(s: "Sampling"):
+    """sampling.jl:26-29 — covariance of the adaptive proposal (zeros before the first full-rank estimate)."""
+    l = np.zeros((116, 116)) if s.variate.SigmaLm is None else s.variate.SigmaLm
+    return l @ l.T
+
+
 def sample_chains(samplings, iters: int):
     """Advance many chains by `iters` Metropolis steps in ONE launch (the batched form of
     sample!, sampling.jl:62-79; replaces the Slurm fan-out of batch.jl:3-22).  Chains may have
@@ -330,7 +347,7 @@ def sample_chains(samplings, iters: int):
     lib = _L.load()
     groups = {}
     for i, s in enumerate(samplings):
-        key = (s.config.thin, s.variate.SigmaL.tobytes(), s.config.rtol, s.config.atol, s.variate.seed,
+        key = (s.config.thin, s.config.adapt, s.variate.SigmaL.tobytes(), s.config.rtol, s.config.atol, s.variate.seed,
                s.variate.iteration, id(s.config.priory0) if s.config.priory0 is not None else 0,
                s.config.priorparms.tobytes())
         groups.setdefault(key, []).append(i)
@@ -355,10 +372,26 @@ def sample_chains(samplings, iters: int):
         pr = c0.prior()
         o = _L.opts(c0.rtol or DEFAULT_RTOL, c0.atol or DEFAULT_ATOL)
         # chain id inside the RNG = position in the group + a per-sampling offset held in the seed
-        _L.check(lib.gync_mcmc_run(_L.dptr(state), _L.dptr(logf), Cn, _L.dptr(chol), float(SL[0, 0]) if diag else 0.0,
-                                   _L.dptr(D), Cn, _L.dptr(sig), pat.ctypes.data_as(_L.c_int32_p), C.byref(pr),
-                                   C.byref(o), iters, thin, v0.seed, v0.iteration, None, None, _L.dptr(out),
-                                   nacc.ctypes.data_as(_L.c_int64_p)))
+        if c0.adapt:                                        # Mamba.sample!(variate, adapt=true) (sampling.jl:72)
+            am = np.array([s.variate.m for s in ss], dtype=np.int64)
+            aMv = np.zeros((Cn, 116))
+            aMvv = np.zeros((Cn, 116, 116))
+            aLm = np.zeros((Cn, 116, 116))
+            for m, s in enumerate(ss):
+                if s.variate.m >= 0:
+                    aMv[m], aMvv[m], aLm[m] = s.variate.Mv, s.variate.Mvv, s.variate.SigmaLm
+            tune = _L.AmmTune(v0.beta, v0.scale, am.ctypes.data_as(_L.c_int64_p), _L.dptr(aMv), _L.dptr(aMvv), _L.dptr(aLm))
+            _L.check(lib.gync_mcmc_run_amm(_L.dptr(state), _L.dptr(logf), Cn, _L.dptr(chol), float(SL[0, 0]) if diag else 0.0,
+                                           _L.dptr(D), Cn, _L.dptr(sig), pat.ctypes.data_as(_L.c_int32_p), C.byref(pr),
+                                           C.byref(o), iters, thin, v0.seed, v0.iteration, None, None, None, _L.dptr(out),
+                                           nacc.ctypes.data_as(_L.c_int64_p), C.byref(tune)))
+            for m, s in enumerate(ss):
+                s.variate.m, s.variate.Mv, s.variate.Mvv, s.variate.SigmaLm = int(am[m]), aMv[m].copy(), aMvv[m].copy(), aLm[m].copy()
+        else:
+            _L.check(lib.gync_mcmc_run(_L.dptr(state), _L.dptr(logf), Cn, _L.dptr(chol), float(SL[0, 0]) if diag else 0.0,
+                                       _L.dptr(D), Cn, _L.dptr(sig), pat.ctypes.data_as(_L.c_int32_p), C.byref(pr),
+                                       C.byref(o), iters, thin, v0.seed, v0.iteration, None, None, _L.dptr(out),
+                                       nacc.ctypes.data_as(_L.c_int64_p)))
         for m, s in enumerate(ss):
             s.samples = np.vstack([s.samples, out[:, :, m]])            # sampling.jl:66-68,74
             s.variate.state = state[m].copy()

@@ -22,10 +22,11 @@ int gync_logprior_batch(const double* X, int64_t N, const gync_prior* prior, dou
   return GYNC_OK;
 }
 
-int gync_mcmc_run(double* state, double* logf, int64_t C, const double* chol, double prop_sd, const double* data,
+static int mcmc_run_impl(double* state, double* logf, int64_t C, const double* chol, double prop_sd, const double* data,
                   int32_t M, const double* sigma_rho, const int32_t* patient_of_chain, const gync_prior* prior,
                   const gync_solver_opts* opts, int64_t iters, int32_t thin, uint64_t seed, uint64_t iter_offset,
-                  const double* inj_z, const double* inj_u, double* samples_out, int64_t* naccept) {
+                  const double* inj_z, const double* inj_u, double* samples_out, int64_t* naccept,
+                  const gync_amm_tune* amm, const double* inj_umix) {
   if (C < 0 || M < 1 || iters < 0 || thin < 1 || !prior || (C > 0 && (!state || !logf || !data || !sigma_rho)))
     return fail(GYNC_ERR_ARG, "gync_mcmc_run: bad arguments");
   if (!chol && !(prop_sd > 0.0)) return fail(GYNC_ERR_ARG, "gync_mcmc_run: need chol or prop_sd > 0");
@@ -39,6 +40,7 @@ int gync_mcmc_run(double* state, double* logf, int64_t C, const double* chol, do
   // speculation depth: fill the solver kernel's sample slots (112 per SM) about twice per round
   int K = (int)std::max<int64_t>(1, std::min<int64_t>(1024, (2 * (int64_t)g_num_sms * GYNC_TM_NSLOT) / C));
   if (const char* v = getenv("GYNC_MCMC_SPEC")) K = std::max(1, std::min(4096, atoi(v)));
+  if (amm) K = std::min(K, 32);     // every speculative slot costs a 116 x 116 factorisation (gync_amm.cuh)
   K = (int)std::min<int64_t>(K, std::max<int64_t>(iters, 1));
   const int64_t N = C * K;
   cudaStream_t s = g_stream;
@@ -82,16 +84,56 @@ int gync_mcmc_run(double* state, double* logf, int64_t C, const double* chol, do
   if (samples_out && n_out > 0) CK(dOut.alloc(sizeof(double) * n_out * GYNC_NX * C));
   gync_prep_patients_kernel<<<blocks_for(M, 64), 64, 0, s>>>(dD.as<double>(), dSig.as<double>(), M, dIsc.as<double>(), dNan.as<int>());
   g_launches += 1;
+  // adaptive proposal: tuning state on the device (chain-major), scratch for the speculative replay
+  DBuf aM, aMv, aMvv, aLm, aVirt, aXold, aIt0, aNacc0, dUm;
+  GyncAmmDev ad;
+  memset(&ad, 0, sizeof(ad));
+  const size_t d1 = GYNC_NX, d2 = (size_t)GYNC_NX * GYNC_NX;
+  if (amm) {
+    if (!amm->m || !amm->Mv || !amm->Mvv || !amm->SigmaLm) return fail(GYNC_ERR_ARG, "gync_mcmc_run_amm: NULL tuning arrays");
+    CK(aM.alloc(sizeof(long long) * C));
+    CK(aMv.alloc(sizeof(double) * C * d1));
+    CK(aMvv.alloc(sizeof(double) * C * d2));
+    CK(aLm.alloc(sizeof(double) * C * d2));
+    CK(aVirt.alloc(sizeof(double) * C * (d1 + d2)));
+    CK(aXold.alloc(sizeof(double) * C * d1));
+    CK(aIt0.alloc(sizeof(long long) * C));
+    CK(aNacc0.alloc(sizeof(long long) * C));
+    CK(cudaMemcpyAsync(aM.p, amm->m, sizeof(long long) * C, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(aMv.p, amm->Mv, sizeof(double) * C * d1, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(aMvv.p, amm->Mvv, sizeof(double) * C * d2, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(aLm.p, amm->SigmaLm, sizeof(double) * C * d2, cudaMemcpyHostToDevice, s));
+    if (inj_umix) {
+      CK(dUm.alloc(sizeof(double) * iters * C));
+      CK(cudaMemcpyAsync(dUm.p, inj_umix, sizeof(double) * iters * C, cudaMemcpyHostToDevice, s));
+    }
+    ad.m = aM.as<long long>(); ad.Mv = aMv.as<double>(); ad.Mvv = aMvv.as<double>(); ad.SigmaLm = aLm.as<double>();
+    ad.beta = amm->beta; ad.scale = amm->scale;
+    CK(cudaFuncSetAttribute(gync_amm_propose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GyncAmmSmem)));
+    CK(cudaFuncSetAttribute(gync_amm_commit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GyncAmmSmem)));
+    gync_amm_init_kernel<<<(unsigned)C, GYNC_AMM_THREADS, 0, s>>>(dS.as<double>(), C, ad);
+    g_launches += 1;
+    CK(cudaGetLastError());
+  }
   const GyncSolverOpts so = to_opts(opts);
   bool need_init = false;
   for (int64_t c = 0; c < C; ++c) need_init |= !(logf[c] == logf[c]);
   // round: propose K slots per chain -> batched likelihoods -> accept scan
   auto round = [&](int mode, int Kr) -> int {
     const int64_t Nr = C * Kr;
-    gync_mcmc_propose_kernel<<<blocks_for(Nr, 128), 128, 0, s>>>(
-        dS.as<double>(), dIt.as<long long>(), C, Kr, iters, mode, chol ? dCh.as<double>() : nullptr, prop_sd,
-        dPr.as<GyncPriorDev>(), seed, iter_offset, inj_z ? dZ.as<double>() : nullptr,
-        patient_of_chain ? dPat.as<int>() : nullptr, dXL.as<double>(), dX.as<double>(), dLpr.as<double>(), dPs.as<int>());
+    const bool adaptive = amm && mode == 0;
+    if (adaptive) {
+      gync_amm_propose_kernel<<<(unsigned)C, GYNC_AMM_THREADS, sizeof(GyncAmmSmem), s>>>(
+          dS.as<double>(), dIt.as<long long>(), dAcc.as<long long>(), C, Kr, iters, chol ? dCh.as<double>() : nullptr, prop_sd,
+          dPr.as<GyncPriorDev>(), seed, iter_offset, inj_z ? dZ.as<double>() : nullptr, inj_umix ? dUm.as<double>() : nullptr,
+          patient_of_chain ? dPat.as<int>() : nullptr, ad, aVirt.as<double>(), aXold.as<double>(), aIt0.as<long long>(),
+          aNacc0.as<long long>(), dXL.as<double>(), dX.as<double>(), dLpr.as<double>(), dPs.as<int>());
+    } else {
+      gync_mcmc_propose_kernel<<<blocks_for(Nr, 128), 128, 0, s>>>(
+          dS.as<double>(), dIt.as<long long>(), C, Kr, iters, mode, chol ? dCh.as<double>() : nullptr, prop_sd,
+          dPr.as<GyncPriorDev>(), seed, iter_offset, inj_z ? dZ.as<double>() : nullptr,
+          patient_of_chain ? dPat.as<int>() : nullptr, dXL.as<double>(), dX.as<double>(), dLpr.as<double>(), dPs.as<int>());
+    }
     g_launches += 1;
     CK(cudaGetLastError());
     if (int rc = launch_loglik(dX.as<double>(), Nr, dD.as<double>(), dIsc.as<double>(), dNan.as<int>(), M, dPs.as<int>(), so,
@@ -103,6 +145,12 @@ int gync_mcmc_run(double* state, double* logf, int64_t C, const double* chol, do
         dLL.as<double>(), seed, iter_offset, inj_u ? dU.as<double>() : nullptr,
         (samples_out && n_out > 0) ? dOut.as<double>() : nullptr, dAcc.as<long long>(), dMin.as<long long>());
     g_launches += 1;
+    if (adaptive) {
+      gync_amm_commit_kernel<<<(unsigned)C, GYNC_AMM_THREADS, sizeof(GyncAmmSmem), s>>>(
+          dS.as<double>(), dIt.as<long long>(), dAcc.as<long long>(), C, ad, aXold.as<double>(), aIt0.as<long long>(),
+          aNacc0.as<long long>());
+      g_launches += 1;
+    }
     CK(cudaGetLastError());
     return GYNC_OK;
   };
@@ -118,8 +166,33 @@ int gync_mcmc_run(double* state, double* logf, int64_t C, const double* chol, do
   if (samples_out && n_out > 0)
     CK(cudaMemcpyAsync(samples_out, dOut.p, sizeof(double) * n_out * GYNC_NX * C, cudaMemcpyDeviceToHost, s));
   if (naccept) CK(cudaMemcpyAsync(naccept, dAcc.p, sizeof(long long) * C, cudaMemcpyDeviceToHost, s));
+  if (amm) {
+    CK(cudaMemcpyAsync(amm->m, aM.p, sizeof(long long) * C, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(amm->Mv, aMv.p, sizeof(double) * C * d1, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(amm->Mvv, aMvv.p, sizeof(double) * C * d2, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(amm->SigmaLm, aLm.p, sizeof(double) * C * d2, cudaMemcpyDeviceToHost, s));
+  }
   CK(cudaStreamSynchronize(s));
   return GYNC_OK;
+}
+
+int gync_mcmc_run(double* state, double* logf, int64_t C, const double* chol, double prop_sd, const double* data,
+                  int32_t M, const double* sigma_rho, const int32_t* patient_of_chain, const gync_prior* prior,
+                  const gync_solver_opts* opts, int64_t iters, int32_t thin, uint64_t seed, uint64_t iter_offset,
+                  const double* inj_z, const double* inj_u, double* samples_out, int64_t* naccept) {
+  return mcmc_run_impl(state, logf, C, chol, prop_sd, data, M, sigma_rho, patient_of_chain, prior, opts, iters, thin, seed,
+                       iter_offset, inj_z, inj_u, samples_out, naccept, nullptr, nullptr);
+}
+
+int gync_mcmc_run_amm(double* state, double* logf, int64_t C, const double* chol, double prop_sd, const double* data,
+                      int32_t M, const double* sigma_rho, const int32_t* patient_of_chain, const gync_prior* prior,
+                      const gync_solver_opts* opts, int64_t iters, int32_t thin, uint64_t seed, uint64_t iter_offset,
+                      const double* inj_z, const double* inj_u, const double* inj_umix, double* samples_out,
+                      int64_t* naccept, const gync_amm_tune* tune) {
+  if (!tune) return fail(GYNC_ERR_ARG, "gync_mcmc_run_amm: NULL tune");
+  if (C > 65535LL * 32768LL) return fail(GYNC_ERR_ARG, "gync_mcmc_run_amm: too many chains");
+  return mcmc_run_impl(state, logf, C, chol, prop_sd, data, M, sigma_rho, patient_of_chain, prior, opts, iters, thin, seed,
+                       iter_offset, inj_z, inj_u, samples_out, naccept, tune, inj_umix);
 }
 
 int gync_wc_normalize_dev(double* dLL_inout, const double* d_logprior, const int64_t* d_counts, int64_t K, int32_t M,

@@ -8,6 +8,7 @@
 #include <vector>
 #include "gync_kernels.cuh"
 #include "gync_mcmc.cuh"
+#include "gync_amm.cuh"
 #include "../../include/gync_b200.h"
 
 extern "C" int gync_init(int device);

@@ -29,6 +29,11 @@ class Prior(C.Structure):
                 ("upper", C.c_double * 82), ("mu_T", C.c_double), ("sd_T", C.c_double)]
 
 
+class AmmTune(C.Structure):
+    _fields_ = [("beta", C.c_double), ("scale", C.c_double), ("m", c_int64_p), ("Mv", c_double_p), ("Mvv", c_double_p),
+                ("SigmaLm", c_double_p)]
+
+
 class GyncError(RuntimeError):
     pass
 
@@ -41,7 +46,7 @@ EXPORTS = [
     "gync_em_norms_dev", "gync_em_step_dev", "gync_launch_count", "gync_wc_normalize", "gync_fp64_peak",
     "gync_flops_per_step", "gync_em_comm_create", "gync_em_comm_connect", "gync_em_comm_destroy",
     "gync_em_iterate_fused_dev", "gync_em_comm_error", "gync_wc_normalize_dev", "gync_init_multi", "gync_ndev",
-    "gync_em_iterate_multi",
+    "gync_em_iterate_multi", "gync_mcmc_run_amm",
     "gync_likelihoodmat", "gync_likelihoodmat_dev", "gync_phi_batch", "gync_projectsimplex", "gync_ebmodel_create",
     "gync_ebmodel_from_matrices", "gync_ebmodel_destroy", "gync_ebmodel_dims", "gync_ebmodel_matrices",
     "gync_ebmodel_device_ptrs", "gync_ebmodel_logl", "gync_ebmodel_dlogl", "gync_ebmodel_hz", "gync_ebmodel_dhz",
@@ -79,6 +84,10 @@ def load():
     lib.gync_mcmc_run.argtypes = [c_double_p, c_double_p, C.c_int64, c_double_p, C.c_double, c_double_p, C.c_int32,
                                   c_double_p, c_int32_p, C.POINTER(Prior), C.POINTER(SolverOpts), C.c_int64,
                                   C.c_int32, C.c_uint64, C.c_uint64, c_double_p, c_double_p, c_double_p, c_int64_p]
+    lib.gync_mcmc_run_amm.argtypes = [c_double_p, c_double_p, C.c_int64, c_double_p, C.c_double, c_double_p, C.c_int32,
+                                      c_double_p, c_int32_p, C.POINTER(Prior), C.POINTER(SolverOpts), C.c_int64,
+                                      C.c_int32, C.c_uint64, C.c_uint64, c_double_p, c_double_p, c_double_p, c_double_p,
+                                      c_int64_p, C.POINTER(AmmTune)]
     lib.gync_em_iterate.argtypes = [c_double_p, c_double_p, C.c_int64, C.c_int32, C.c_int32, c_double_p]
     lib.gync_em_iterate_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     lib.gync_em_norms_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]

@@ -110,6 +110,26 @@ int gync_mcmc_run(double* state, double* logf, int64_t C, const double* chol, do
                   const double* inj_z, const double* inj_u,
                   double* samples_out, int64_t* naccept);
 
+/* ---- the same with Mamba's adaptation switched on (Config.adapt = true; model.jl:104-106, sampling.jl:72) ----------
+ * AMMTune state per chain, in/out so that a Sampling can be continued (sampling.jl:62-68) and propadapt() read
+ * (sampling.jl:26-29).  m[c] < 0 on entry: adaptation starts here (m = 0, Mv = v, Mvv = v v', SigmaLm = 0).
+ * Per iteration: m += 1; x' = x + (m > 2*116 && u_mix >= beta ? SigmaLm : SigmaL) z; accept; p = m/(m+1);
+ * Mv = p Mv + (1-p) v; Mvv = p Mvv + (1-p) v v'; Sigma = scale^2/116/p (Mvv - Mv Mv'); if full rank SigmaLm = chol. */
+typedef struct {
+  double   beta, scale;   /* 0.05, 2.38 (model.jl:105-106) */
+  int64_t* m;             /* C */
+  double*  Mv;            /* 116 x C */
+  double*  Mvv;           /* 116 x 116 x C */
+  double*  SigmaLm;       /* 116 x 116 x C, chain c's lower factor stored ROW-major ([i][j] at i*116 + j) */
+} gync_amm_tune;
+int gync_mcmc_run_amm(double* state, double* logf, int64_t C, const double* chol, double prop_sd,
+                      const double* data, int32_t M, const double* sigma_rho,
+                      const int32_t* patient_of_chain, const gync_prior* prior,
+                      const gync_solver_opts* opts, int64_t iters, int32_t thin,
+                      uint64_t seed, uint64_t iter_offset,
+                      const double* inj_z, const double* inj_u, const double* inj_umix /* iters x C */,
+                      double* samples_out, int64_t* naccept, const gync_amm_tune* tune);
+
 /* ---- emiteration!(w,L) / emiterations — em.jl:27-41, em.jl:5 ----------------------------
  * L: K x M, w: K (updated in place, niter times).  history (nullable): K x niter, column i =
  * weights after iteration i+1. */

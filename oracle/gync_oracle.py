@@ -428,6 +428,52 @@ def metropolis_step(state, cur_logf, chol, z, u, logf):
     return state, cur_logf, False
 
 
+def amm_new_tune(state, SigmaL, beta=0.05, scale=2.38):
+    """AMMTune after setadapt!(v, true) on a fresh variate: m = 0, Mv = v, Mvv = v v'."""
+    v = np.asarray(state, dtype=np.float64)
+    return {"m": 0, "Mv": v.copy(), "Mvv": np.outer(v, v), "SigmaL": np.asarray(SigmaL, dtype=np.float64),
+            "SigmaLm": np.zeros((v.size, v.size)), "beta": beta, "scale": scale}
+
+
+def chol_fullrank(S):
+    """Lower Cholesky factor of S, or None when S is not numerically of full rank — the LAPACK dpstrf stopping rule
+    (pivot <= n eps max(diag)) that `rank(cholfact(S, :U, Val{true})) == n` tests in Mamba, on the unpivoted
+    factorisation (same Sigma = L L'; Mamba uses the pivoted square root P L — same proposal distribution)."""
+    S = np.array(S, dtype=np.float64)
+    n = S.shape[0]
+    tol = n * np.finfo(float).eps * np.max(np.diag(S))
+    L = np.zeros_like(S)
+    for k in range(n):
+        piv = S[k, k] - np.dot(L[k, :k], L[k, :k])
+        if not piv > tol:
+            return None
+        L[k, k] = np.sqrt(piv)
+        L[k + 1:, k] = (S[k + 1:, k] - L[k + 1:, :k] @ L[k, :k]) / L[k, k]
+    return L
+
+
+def amm_step(state, cur_logf, tune, z, u, umix, logf):
+    """One ADAPTIVE Mamba AMM step (Mamba.sample!(v, adapt=true); SURVEY Appendix D — recalled third-party behaviour,
+    parity unpinned; call sites model.jl:104-106, sampling.jl:72).  Mutates `tune`."""
+    d = state.size
+    tune["m"] += 1
+    m = tune["m"]
+    F = tune["SigmaLm"] if (m > 2 * d and umix >= tune["beta"]) else tune["SigmaL"]
+    prop = state + F @ z
+    lp = logf(prop)
+    acc = bool(np.log(u) < lp - cur_logf)
+    if acc:
+        state, cur_logf = prop, lp
+    p = m / (m + 1.0)
+    tune["Mv"] = p * tune["Mv"] + (1 - p) * state
+    tune["Mvv"] = p * tune["Mvv"] + (1 - p) * np.outer(state, state)
+    Sigma = (tune["scale"] ** 2 / d / p) * (tune["Mvv"] - np.outer(tune["Mv"], tune["Mv"]))
+    L = chol_fullrank(Sigma) if m >= d else None
+    if L is not None:
+        tune["SigmaLm"] = L
+    return state, cur_logf, acc
+
+
 # --------------------------------------------------------------- WeightedChain/EM
 def weightedchain_normalize(logprior_k, LL, counts):
     """weightedchain.jl:59-67 — exp-normalise, column-normalise, weights and density."""

@@ -340,6 +340,113 @@ def test_mcmc_step_with_injected_randomness(gpu, gold):
             assert np.allclose(state[cidx], xs, rtol=0, atol=1e-13)
 
 
+def test_amm_adaptive_step_with_injected_randomness(gpu, gold):
+    """Config.adapt = true (Mamba AMM with adaptation): the kernel pair against the oracle's
+    amm_step with the same normals / uniforms / mixture uniforms, started from a tuning state past m > 2d so that
+    adapted proposals, the moment updates and the re-factorisation are all exercised, and from a fresh variate."""
+    import c_oracle as co
+    import gync_oracle as o
+    lib, L = gpu.lib.load(), gpu.lib
+    c = gpu.Config(priory0=gpu.api.GaussianMixture(gold["gmm_means"], gold["gmm_stds"]))
+    Cn, iters = 3, 6
+    rng = np.random.default_rng(18)
+    datas = [gold["data"][:, :, m] for m in range(4)]
+    sd = np.sqrt(np.log(1.01))
+    x0 = np.log(o.init_x())
+
+    def logf(xl, m):
+        x = np.exp(xl)
+        lp = o.logprior(x, gold["gmm_means"], gold["gmm_stds"])
+        if lp == -np.inf:
+            return lp
+        return lp + co.llh_batch(x[None, :], [datas[m]], [0.1], 1, 1e-12, 1e-12)[0, 0] + xl.sum()
+
+    def history_tune(seed, m):
+        """A tuning state as m iterations of a slowly moving chain would leave it."""
+        r = np.random.default_rng(seed)
+        V = x0[None, :] + np.cumsum(r.standard_normal((m + 1, 116)) * 0.004, axis=0)
+        t = o.amm_new_tune(V[0], np.eye(116) * sd)
+        for k in range(1, m + 1):
+            p = k / (k + 1.0)
+            t["Mv"] = p * t["Mv"] + (1 - p) * V[k]
+            t["Mvv"] = p * t["Mvv"] + (1 - p) * np.outer(V[k], V[k])
+        t["m"] = m
+        p = m / (m + 1.0)
+        t["SigmaLm"] = o.chol_fullrank((2.38 ** 2 / 116 / p) * (t["Mvv"] - np.outer(t["Mv"], t["Mv"])))
+        assert t["SigmaLm"] is not None
+        return t
+
+    for fresh in (False, True):
+        z = rng.standard_normal((iters, 116, Cn)) * (1.0 if fresh else 0.3)
+        u = rng.random((iters, Cn))
+        um = rng.random((iters, Cn))
+        u[1] = 1e-300                      # force an accept
+        u[3] = 1.0                         # force a reject
+        um[2] = 0.01                       # below beta: the initial proposal even past 2d
+        tunes = [o.amm_new_tune(x0, np.eye(116) * sd) if fresh else history_tune(100 + k, 300) for k in range(Cn)]
+        am = np.array([-1 if fresh else t["m"] for t in tunes], dtype=np.int64)
+        aMv = np.stack([t["Mv"] for t in tunes])
+        aMvv = np.stack([t["Mvv"] for t in tunes])
+        aLm = np.stack([t["SigmaLm"] for t in tunes])
+        state = L.fcol(np.tile(x0, (Cn, 1)))
+        lf = np.full(Cn, np.nan)
+        out = np.empty((iters, 116, Cn), order="F")
+        nacc = np.zeros(Cn, dtype=np.int64)
+        pr = c.prior()
+        op = L.opts(1e-9, 1e-9)
+        D = np.asfortranarray(gold["data"])
+        sig = np.full(4, 0.1)
+        pat = np.arange(Cn, dtype=np.int32)
+        tune = L.AmmTune(0.05, 2.38, am.ctypes.data_as(L.c_int64_p), L.dptr(aMv), L.dptr(aMvv), L.dptr(aLm))
+        L.check(lib.gync_mcmc_run_amm(L.dptr(state), L.dptr(lf), Cn, None, sd, L.dptr(D), 4, L.dptr(sig),
+                                      pat.ctypes.data_as(L.c_int32_p), C.byref(pr), C.byref(op), iters, 1, 0, 0,
+                                      L.dptr(np.asfortranarray(z)), L.dptr(np.asfortranarray(u)), L.dptr(np.asfortranarray(um)),
+                                      L.dptr(out), nacc.ctypes.data_as(L.c_int64_p), C.byref(tune)))
+        for cidx in range(Cn):
+            xs, t = x0.copy(), tunes[cidx]
+            cur = logf(xs, cidx)
+            acc = 0
+            for it in range(iters):
+                xs, cur, a = o.amm_step(xs, cur, t, z[it, :, cidx], u[it, cidx], um[it, cidx], lambda v: logf(v, cidx))
+                acc += a
+                assert relerr(out[it, :, cidx], np.exp(xs)) < 1e-11, (fresh, cidx, it)
+            assert acc == nacc[cidx] and acc >= 1
+            assert am[cidx] == t["m"]
+            assert np.allclose(aMv[cidx], t["Mv"], rtol=1e-13, atol=0)
+            assert np.allclose(aMvv[cidx], t["Mvv"], rtol=1e-13, atol=0)
+            if not fresh:
+                # the factor amplifies rounding by the conditioning of Sigma; compare the covariance it represents
+                assert np.allclose(aLm[cidx] @ aLm[cidx].T, t["SigmaLm"] @ t["SigmaLm"].T, rtol=1e-7, atol=1e-12)
+                assert np.allclose(aLm[cidx], np.tril(aLm[cidx]))
+            else:
+                assert not aLm[cidx].any()                      # rank-deficient so far: SigmaLm stays zero
+
+
+def test_sample_api_adaptive(gpu):
+    """sample(Config(adapt=true), n): reproducible, resumable, independent of the speculation depth; adaptation
+    kicks in after 2d = 232 iterations (propadapt becomes a full-rank covariance)."""
+    c = gpu.Config(gpu.Lausanne(1), adapt=True)
+    s = gpu.sample(c, 150, seed=5)
+    assert s.samples.shape == (150, 116) and s.variate.m == 150
+    assert np.array_equal(gpu.api.propinit(s), c.propvar)
+    s = gpu.sample_bang(s, 150)
+    assert s.samples.shape == (300, 116) and s.variate.m == 300
+    s2 = gpu.sample(c, 300, seed=5)
+    assert np.array_equal(s.samples, s2.samples)                       # resumable: 150 + 150 == 300
+    os.environ["GYNC_MCMC_SPEC"] = "3"
+    try:
+        s3 = gpu.sample(c, 300, seed=5)
+    finally:
+        del os.environ["GYNC_MCMC_SPEC"]
+    assert np.array_equal(s3.samples, s.samples)                       # speculation is exact under adaptation too
+    P = gpu.api.propadapt(s)
+    nuniq = len(np.unique(s.samples[:, 0]))
+    assert nuniq > 20
+    if nuniq > 140:                                                    # > d distinct states: the estimate has full rank
+        assert np.all(np.linalg.eigvalsh(P) > 0)
+    assert np.allclose(s.variate.Mv, np.log(np.vstack([gpu.api.init(c), s.samples])).mean(0), rtol=1e-10)
+
+
 def test_sample_api_shapes_and_reproducibility(gpu):
     c = gpu.Config(gpu.Lausanne(1), thin=2)
     s = gpu.sample(c, 20, seed=3)

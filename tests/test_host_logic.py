@@ -171,8 +171,10 @@ def test_api_constants_and_config_defaults(built):
     assert np.array_equal(np.isnan(g.Lausanne(1).data), np.isnan(o.lausanne(1)))
     assert (~np.isnan(g.Lausanne(1).data)).sum() == 60
     assert len(api.alldatas()) == 53                                                           # notebook: 53 pass minmeas=20
-    with pytest.raises(NotImplementedError):
-        g.Config(adapt=True)
+    ca = g.Config(adapt=True)                                                                   # notebooks: production runs adapt
+    assert ca.adapt and ca.filename().endswith("atrue.jld")
+    v = api.SamplerVariate(ca)
+    assert v.m == -1 and v.beta == 0.05 and v.scale == 2.38                                     # model.jl:104-106
 
 
 def test_api_collapse_duplicates_matches_oracle(built):

@@ -155,3 +155,36 @@ def test_weightedchain_pieces():
     LL[2, 1] = -np.inf
     lhs, w, d = o.weightedchain_normalize(rng.standard_normal(4), LL, counts)
     assert np.allclose(lhs.sum(0), 1) and lhs[2, 1] == 0 and abs(w.sum() - 1) < 1e-15 and abs(d.sum() - 1) < 1e-15
+
+
+def test_amm_oracle_step_properties():
+    """Adaptive Metropolis restatement: the running moments equal the sample moments of the
+    visited states, the adapted factor reproduces scale^2/d times their covariance, and before m > 2d only the
+    initial proposal is used."""
+    rng = np.random.default_rng(21)
+    d = 6
+    SL = np.eye(d) * 0.3
+    x = rng.standard_normal(d)
+    logf = lambda v: -0.5 * float(v @ v)
+    tune = o.amm_new_tune(x, SL)
+    cur = logf(x)
+    visited = [x.copy()]
+    for it in range(60):
+        z, u, um = rng.standard_normal(d), rng.random(), rng.random()
+        before = x.copy()
+        x, cur, acc = o.amm_step(x, cur, tune, z, u, um, logf)
+        if tune["m"] <= 2 * d:
+            assert (not acc) or np.allclose(x, before + SL @ z)
+        visited.append(x.copy())
+    V = np.array(visited)
+    assert tune["m"] == 60
+    assert np.allclose(tune["Mv"], V.mean(0), rtol=1e-12)
+    assert np.allclose(tune["Mvv"], (V[:, :, None] * V[:, None, :]).mean(0), rtol=1e-12)
+    p = 60 / 61.0
+    Sigma = (2.38 ** 2 / d / p) * np.cov(V.T, bias=True)
+    Lm = tune["SigmaLm"]
+    assert np.allclose(Lm @ Lm.T, Sigma, rtol=1e-9, atol=1e-12) and np.allclose(Lm, np.tril(Lm))
+    assert o.chol_fullrank(np.ones((3, 3))) is None                      # rank 1
+    A = rng.standard_normal((5, 5))
+    S = A @ A.T + np.eye(5)
+    assert np.allclose(o.chol_fullrank(S), np.linalg.cholesky(S), rtol=1e-12)
