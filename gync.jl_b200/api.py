@@ -335,8 +335,8 @@ def propinit(s: "Sampling"):
 
 
 def propadapt(s: "Sampling"):
-    """sampling.jl:26-29 — covariance of the adaptive proposal (zeros before the first full-rank estimate)."""
-    l = np.zeros((116, 116)) if s.variate.SigmaLm is None else s.variate.SigmaLm
+    """sampling.jl:26-29 — covariance of the adaptive proposal (the initial one before the first full-rank estimate)."""
+    l = s.variate.SigmaL if s.variate.SigmaLm is None else s.variate.SigmaLm
     return l @ l.T
 
 
@@ -413,6 +413,62 @@ def sample(obj, n, seed=0):
     if isinstance(obj, WeightedChain):
         return obj.sample(n, seed)
     raise TypeError(type(obj))
+
+
+# ------------------------------------------------------------------------------ checkpoint / resume
+def save(path, s: Sampling):
+    """save(path, s::Sampling) (utils.jl:49).  The reference writes JLD (HDF5) with the Mamba variate as a Julia
+    `Base.serialize` blob (utils.jl:31-44) — neither is readable outside Julia, so the container here is .npz with the
+    same content: samples, the Config fields, and the variate (state, current log-target, proposal factor, RNG position
+    and the AMM tuning state), enough for sample!(load(path), n) to continue the chain bit-identically."""
+    c, v = s.config, s.variate
+    if c.priory0 is None:
+        c.prior()
+    z = {"samples": s.samples, "patient_data": c.patient.data, "patient_id": np.array(str(c.patient.id)),
+         "sigma_rho": c.sigma_rho, "propvar": c.propvar, "adapt": c.adapt, "thin": c.thin, "initparms": c.initparms,
+         "inity0": c.inity0, "priorparms": c.priorparms, "priory0_means": c.priory0.means, "priory0_stds": c.priory0.stds,
+         "rtol": np.nan if c.rtol is None else c.rtol, "atol": np.nan if c.atol is None else c.atol,
+         "v_state": v.state, "v_logf": v.logf, "v_SigmaL": v.SigmaL, "v_seed": v.seed, "v_iteration": v.iteration,
+         "v_naccept": v.naccept, "v_m": v.m, "v_beta": v.beta, "v_scale": v.scale}
+    if v.m >= 0:
+        z.update(v_Mv=v.Mv, v_Mvv=v.Mvv, v_SigmaLm=v.SigmaLm)
+    with open(path, "wb") as f:                      # np.savez would append ".npz" to the reference's ".jld" file names
+        np.savez(f, **z)
+
+
+def load(path) -> Sampling:
+    """load(path) (utils.jl:48)."""
+    z = np.load(path, allow_pickle=False)
+    nz = lambda k: None if np.isnan(z[k]) else float(z[k])
+    c = Config(patient=Patient(z["patient_data"], str(z["patient_id"])), sigma_rho=float(z["sigma_rho"]), propvar=z["propvar"],
+               adapt=bool(z["adapt"]), thin=int(z["thin"]), initparms=z["initparms"], inity0=z["inity0"],
+               priorparms=z["priorparms"], priory0=GaussianMixture(z["priory0_means"], z["priory0_stds"]),
+               rtol=nz("rtol"), atol=nz("atol"))
+    v = Variate(z["v_state"], float(z["v_logf"]), z["v_SigmaL"], int(z["v_seed"]), int(z["v_iteration"]), int(z["v_naccept"]),
+                int(z["v_m"]), beta=float(z["v_beta"]), scale=float(z["v_scale"]))
+    if v.m >= 0:
+        v.Mv, v.Mvv, v.SigmaLm = z["v_Mv"], z["v_Mvv"], z["v_SigmaLm"]
+    return Sampling(z["samples"], c, v)
+
+
+def batch(c: Config, iters, path, overwrite=False, seed=0):
+    """batch(c, iters::Vector{Int}, path) (batch.jl:26-46): sample up to each iteration count in `iters`, saving after
+    each; an existing file is continued unless `overwrite`.  (The Slurm fan-out of batch.jl:3-22 is replaced by
+    sample_chains: many chains in one launch.)"""
+    if not overwrite and os.path.isfile(path):
+        s = load(path)
+        c = s.config
+    else:
+        s = new_sampling(c, seed)
+    thin = c.thin
+    for i in iters:
+        n = s.samples.shape[0] * thin
+        i = i - n
+        if i < thin:
+            continue
+        s = sample_bang(s, i)
+        save(path, s)
+    return s
 
 
 # ------------------------------------------------------------------------------ WeightedChain / EM

@@ -40,7 +40,7 @@ static int mcmc_run_impl(double* state, double* logf, int64_t C, const double* c
   // speculation depth: fill the solver kernel's sample slots (112 per SM) about twice per round
   int K = (int)std::max<int64_t>(1, std::min<int64_t>(1024, (2 * (int64_t)g_num_sms * GYNC_TM_NSLOT) / C));
   if (const char* v = getenv("GYNC_MCMC_SPEC")) K = std::max(1, std::min(4096, atoi(v)));
-  if (amm) K = std::min(K, 32);     // every speculative slot costs a 116 x 116 factorisation (gync_amm.cuh)
+  if (amm && C > 1) K = std::min(K, 32);     // every speculative slot costs a 116 x 116 factorisation (gync_amm.cuh)
   K = (int)std::min<int64_t>(K, std::max<int64_t>(iters, 1));
   const int64_t N = C * K;
   cudaStream_t s = g_stream;
@@ -111,7 +111,7 @@ static int mcmc_run_impl(double* state, double* logf, int64_t C, const double* c
     ad.beta = amm->beta; ad.scale = amm->scale;
     CK(cudaFuncSetAttribute(gync_amm_propose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GyncAmmSmem)));
     CK(cudaFuncSetAttribute(gync_amm_commit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GyncAmmSmem)));
-    gync_amm_init_kernel<<<(unsigned)C, GYNC_AMM_THREADS, 0, s>>>(dS.as<double>(), C, ad);
+    gync_amm_init_kernel<<<(unsigned)C, GYNC_AMM_THREADS, 0, s>>>(dS.as<double>(), C, chol ? dCh.as<double>() : nullptr, prop_sd, ad);
     g_launches += 1;
     CK(cudaGetLastError());
   }
@@ -156,10 +156,18 @@ static int mcmc_run_impl(double* state, double* logf, int64_t C, const double* c
   };
   if (need_init) if (int rc = round(1, 1)) return rc;
   long long min_it = 0;
+  int Kr = K;
+  if (amm && C == 1) Kr = std::min(K, 32);
   while (min_it < iters) {
-    if (int rc = round(0, K)) return rc;
+    const long long before = min_it;
+    if (int rc = round(0, Kr)) return rc;
     CK(cudaMemcpyAsync(&min_it, dMin.p, sizeof(long long), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    if (amm && C == 1) {     // every adaptive slot costs a factorisation: follow the acceptance rate with the depth
+      const long long used = min_it - before;
+      if (used >= Kr) Kr = std::min(K, 2 * Kr);
+      else if (4 * used < Kr) Kr = std::max(8, Kr / 2);
+    }
   }
   CK(cudaMemcpyAsync(state, dS.p, sizeof(double) * C * GYNC_NX, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(logf, dLf.p, sizeof(double) * C, cudaMemcpyDeviceToHost, s));

@@ -5,7 +5,7 @@
 //   x' = x + (m > 2d && u_mix >= beta ? SigmaLm : SigmaL) z          mixture of the adapted and the initial proposal
 //   accept iff u < exp(logf(x') - logf(x))
 //   p = m/(m+1);  Mv = p Mv + (1-p) v;  Mvv = p Mvv + (1-p) v v'      v = the state after the accept/reject
-//   Sigma = (scale^2 / d / p) (Mvv - Mv Mv');  if Sigma factorises (full rank): SigmaLm = its factor
+//   Sigma = (scale^2 / d / p) (Mvv - Mv Mv');  if Sigma factorises (full rank): SigmaLm = its factor (initially SigmaL)
 //
 // Speculation stays exact: under "everything so far was rejected" the tuning state of iteration i+j is determined (j
 // updates with the unchanged state), so one CTA per chain walks the K slots sequentially on a scratch copy of
@@ -23,7 +23,7 @@ struct GyncAmmDev {
   long long* m;        // C
   double* Mv;          // C x 116       (chain-major: one CTA owns one chain)
   double* Mvv;         // C x 116 x 116
-  double* SigmaLm;     // C x 116 x 116 lower factors, row-major [i][j], zero until the first full-rank estimate
+  double* SigmaLm;     // C x 116 x 116 lower factors, row-major [i][j]; SigmaL until the first full-rank estimate
   double beta, scale;
 };
 
@@ -216,17 +216,21 @@ gync_amm_commit_kernel(const double* __restrict__ state, const long long* __rest
   if (tid == 0) amm.m[c] = m;
 }
 
-// setadapt!(v, true) on a fresh variate: m = 0, Mv = v, Mvv = v v', SigmaLm = 0 (chains with m < 0 on entry)
+// setadapt!(v, true) on a fresh variate (chains with m < 0 on entry): m = 0, Mv = v, Mvv = v v', SigmaLm = SigmaL — until
+// the running covariance has full rank the "adapted" component of the mixture is the initial proposal (a zero SigmaLm
+// would propose x' = x, accept it with probability one and freeze the chain, which the reference's production runs
+// with adapt = true contradict).
 __global__ void __launch_bounds__(GYNC_AMM_THREADS)
-gync_amm_init_kernel(const double* __restrict__ state, int64_t C, GyncAmmDev amm) {
+gync_amm_init_kernel(const double* __restrict__ state, int64_t C, const double* __restrict__ chol, double prop_sd, GyncAmmDev amm) {
   const int64_t c = blockIdx.x;
   if (amm.m[c] >= 0) return;
   double* Mv = amm.Mv + (size_t)c * GYNC_NX;
   double* Mvv = amm.Mvv + (size_t)c * GYNC_NX * GYNC_NX;
   double* Lm = amm.SigmaLm + (size_t)c * GYNC_NX * GYNC_NX;
   for (int e = threadIdx.x; e < GYNC_NX * GYNC_NX; e += GYNC_AMM_THREADS) {
-    Mvv[e] = state[c + C * (e / GYNC_NX)] * state[c + C * (e % GYNC_NX)];
-    Lm[e] = 0.0;
+    const int i = e / GYNC_NX, j = e % GYNC_NX;
+    Mvv[e] = state[c + C * i] * state[c + C * j];
+    Lm[e] = chol ? ((j <= i) ? chol[i + GYNC_NX * j] : 0.0) : ((i == j) ? prop_sd : 0.0);
   }
   for (int d = threadIdx.x; d < GYNC_NX; d += GYNC_AMM_THREADS) Mv[d] = state[c + C * d];
   __syncthreads();

@@ -112,7 +112,7 @@ int gync_mcmc_run(double* state, double* logf, int64_t C, const double* chol, do
 
 /* ---- the same with Mamba's adaptation switched on (Config.adapt = true; model.jl:104-106, sampling.jl:72) ----------
  * AMMTune state per chain, in/out so that a Sampling can be continued (sampling.jl:62-68) and propadapt() read
- * (sampling.jl:26-29).  m[c] < 0 on entry: adaptation starts here (m = 0, Mv = v, Mvv = v v', SigmaLm = 0).
+ * (sampling.jl:26-29).  m[c] < 0 on entry: adaptation starts here (m = 0, Mv = v, Mvv = v v', SigmaLm = SigmaL).
  * Per iteration: m += 1; x' = x + (m > 2*116 && u_mix >= beta ? SigmaLm : SigmaL) z; accept; p = m/(m+1);
  * Mv = p Mv + (1-p) v; Mvv = p Mvv + (1-p) v v'; Sigma = scale^2/116/p (Mvv - Mv Mv'); if full rank SigmaLm = chol. */
 typedef struct {

@@ -429,10 +429,11 @@ def metropolis_step(state, cur_logf, chol, z, u, logf):
 
 
 def amm_new_tune(state, SigmaL, beta=0.05, scale=2.38):
-    """AMMTune after setadapt!(v, true) on a fresh variate: m = 0, Mv = v, Mvv = v v'."""
+    """AMMTune after setadapt!(v, true) on a fresh variate: m = 0, Mv = v, Mvv = v v',
+    SigmaLm = SigmaL until the running covariance has full rank (a zero factor would freeze the chain at m > 2d)."""
     v = np.asarray(state, dtype=np.float64)
     return {"m": 0, "Mv": v.copy(), "Mvv": np.outer(v, v), "SigmaL": np.asarray(SigmaL, dtype=np.float64),
-            "SigmaLm": np.zeros((v.size, v.size)), "beta": beta, "scale": scale}
+            "SigmaLm": np.array(SigmaL, dtype=np.float64), "beta": beta, "scale": scale}
 
 
 def chol_fullrank(S):

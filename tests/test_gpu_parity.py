@@ -409,17 +409,18 @@ def test_amm_adaptive_step_with_injected_randomness(gpu, gold):
             for it in range(iters):
                 xs, cur, a = o.amm_step(xs, cur, t, z[it, :, cidx], u[it, cidx], um[it, cidx], lambda v: logf(v, cidx))
                 acc += a
-                assert relerr(out[it, :, cidx], np.exp(xs)) < 1e-11, (fresh, cidx, it)
+                # the re-factorised SigmaLm amplifies rounding by the conditioning of Sigma (two different Cholesky orders)
+                assert relerr(out[it, :, cidx], np.exp(xs)) < 1e-9, (fresh, cidx, it)
             assert acc == nacc[cidx] and acc >= 1
             assert am[cidx] == t["m"]
-            assert np.allclose(aMv[cidx], t["Mv"], rtol=1e-13, atol=0)
-            assert np.allclose(aMvv[cidx], t["Mvv"], rtol=1e-13, atol=0)
+            assert np.allclose(aMv[cidx], t["Mv"], rtol=1e-12, atol=1e-14)        # fma contraction on the device
+            assert np.allclose(aMvv[cidx], t["Mvv"], rtol=1e-12, atol=1e-14)
             if not fresh:
                 # the factor amplifies rounding by the conditioning of Sigma; compare the covariance it represents
                 assert np.allclose(aLm[cidx] @ aLm[cidx].T, t["SigmaLm"] @ t["SigmaLm"].T, rtol=1e-7, atol=1e-12)
                 assert np.allclose(aLm[cidx], np.tril(aLm[cidx]))
             else:
-                assert not aLm[cidx].any()                      # rank-deficient so far: SigmaLm stays zero
+                assert np.array_equal(aLm[cidx], np.eye(116) * sd)   # rank-deficient so far: SigmaLm is still SigmaL
 
 
 def test_sample_api_adaptive(gpu):
@@ -441,10 +442,26 @@ def test_sample_api_adaptive(gpu):
     assert np.array_equal(s3.samples, s.samples)                       # speculation is exact under adaptation too
     P = gpu.api.propadapt(s)
     nuniq = len(np.unique(s.samples[:, 0]))
-    assert nuniq > 20
-    if nuniq > 140:                                                    # > d distinct states: the estimate has full rank
-        assert np.all(np.linalg.eigvalsh(P) > 0)
+    assert nuniq >= 2 and np.all(np.linalg.eigvalsh(P) > 0)
+    if nuniq <= 116:                                                   # fewer than d+1 distinct states: rank-deficient estimate
+        assert np.allclose(P, c.propvar)                               # -> the adapted component is still the initial proposal
     assert np.allclose(s.variate.Mv, np.log(np.vstack([gpu.api.init(c), s.samples])).mean(0), rtol=1e-10)
+
+
+def test_checkpoint_resume(gpu, tmp_path):
+    """save / load / batch (utils.jl:48-49, batch.jl:26-46): a chain continued from its checkpoint equals the
+    uninterrupted one, with and without adaptation."""
+    for adapt in (False, True):
+        c = gpu.Config(gpu.Lausanne(2), thin=2, adapt=adapt)
+        path = str(tmp_path / c.filename())
+        s = gpu.api.batch(c, [10, 30], path, seed=4)
+        assert s.samples.shape == (15, 116) and os.path.isfile(path)
+        s = gpu.api.batch(c, [30, 50], path)                       # continues the file: 20 more iterations
+        assert s.samples.shape == (25, 116)
+        ref = gpu.sample(c, 50, seed=4)
+        assert np.array_equal(s.samples, ref.samples) and s.variate.naccept == ref.variate.naccept
+        l = gpu.api.load(path)
+        assert l.config.adapt == adapt and l.config.patient.id == "l2" and l.variate.m == (50 if adapt else -1)
 
 
 def test_sample_api_shapes_and_reproducibility(gpu):

@@ -219,3 +219,24 @@ def test_bench_reference_arm_contract():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                        capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2"), timeout=60)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_save_load_roundtrip(built, tmp_path):
+    """Checkpoint container (utils.jl:48-49 stand-in): every field of Sampling / Config / variate survives."""
+    import gync_b200 as g
+    c = g.Config(g.Lausanne(3), sigma_rho=0.2, thin=5, adapt=True,
+                 priory0=g.api.GaussianMixture(np.ones((31, 33)), np.ones(33)))
+    s = g.new_sampling(c, seed=9)
+    s.samples = np.arange(232.0).reshape(2, 116)
+    s.variate.logf, s.variate.iteration, s.variate.naccept = -3.5, 10, 4
+    s.variate.m, s.variate.Mv = 10, np.arange(116.0)
+    s.variate.Mvv, s.variate.SigmaLm = np.eye(116) * 2, np.eye(116) * 3
+    path = str(tmp_path / c.filename())
+    g.api.save(path, s)
+    l = g.api.load(path)
+    assert np.array_equal(l.samples, s.samples) and l.config.thin == 5 and l.config.adapt and l.config.sigma_rho == 0.2
+    assert l.config.patient.id == "l3" and np.array_equal(np.isnan(l.config.data), np.isnan(c.data))
+    v, w = l.variate, s.variate
+    assert (v.logf, v.iteration, v.naccept, v.seed, v.m) == (w.logf, w.iteration, w.naccept, w.seed, w.m)
+    assert np.array_equal(v.state, w.state) and np.array_equal(v.SigmaL, w.SigmaL) and np.array_equal(v.SigmaLm, w.SigmaLm)
+    assert l.config.rtol is None and np.array_equal(l.config.priory0.means, np.ones((31, 33)))
