@@ -81,12 +81,13 @@ size_t mv_part_doubles(int64_t R, int64_t C) {
 
 // LikelihoodModel (eb/likelihoodmodel.jl:3-14) with both likelihood matrices resident in HBM:
 //   Ld = likelihoodmat(ys, datas, measerr)      K x M   (its transpose is what logl/dlogl use, regularizers.jl:3,8)
-//   Lz = likelihoodmat(zs, ys, zsampledistr)    Z x K   (hz/dhz, regularizers.jl:26,60)
+//   Lz = likelihoodmat(zs, ys, zsampledistr)    Z x K   (hz/dhz, regularizers.jl:26,60) — held TRANSPOSED (Lzt, K x Z
+//        column-major: every z-row contiguous) so that dhz can run in one pass over HBM (gync_dhz_fused_kernel)
 struct gync_ebmodel {
   int device = -1;
   int64_t K = 0, M = 0, Z = 0;
   int zmult = 0;
-  double *Ld = nullptr, *Lz = nullptr;
+  double *Ld = nullptr, *Lzt = nullptr;
   double *part = nullptr, *rho = nullptr, *fac = nullptr, *norms = nullptr, *rnorm = nullptr;
   double *ga = nullptr, *gb = nullptr, *y = nullptr, *w = nullptr, *scal = nullptr;
   GyncPsPart* ps = nullptr;
@@ -101,7 +102,7 @@ void ebmodel_free(gync_ebmodel* m) {
   int cur = 0;
   cudaGetDevice(&cur);
   if (m->device >= 0) cudaSetDevice(m->device);
-  for (double* p : {m->Ld, m->Lz, m->part, m->rho, m->fac, m->norms, m->rnorm, m->ga, m->gb, m->y, m->w, m->scal})
+  for (double* p : {m->Ld, m->Lzt, m->part, m->rho, m->fac, m->norms, m->rnorm, m->ga, m->gb, m->y, m->w, m->scal})
     if (p) cudaFree(p);
   if (m->ps) cudaFree(m->ps);
   if (m->flags) cudaFree(m->flags);
@@ -121,9 +122,9 @@ int ebmodel_alloc(gync_ebmodel* m) {
   m->device = g_device;
   const int64_t K = m->K, M = m->M, Z = m->Z;
   CK(cudaMalloc((void**)&m->Ld, sizeof(double) * std::max<int64_t>(K * M, 1)));
-  if (Z > 0) CK(cudaMalloc((void**)&m->Lz, sizeof(double) * Z * K));
+  if (Z > 0) CK(cudaMalloc((void**)&m->Lzt, sizeof(double) * Z * K));
   size_t pd = mv_part_doubles(K, std::max<int64_t>(M, 1));
-  if (Z > 0) pd = std::max(pd, mv_part_doubles(Z, K));
+  if (Z > 0) pd = std::max(std::max(pd, mv_part_doubles(K, Z)), (size_t)g_num_sms * (size_t)K);
   CK(cudaMalloc((void**)&m->part, sizeof(double) * pd));
   CK(cudaMalloc((void**)&m->rho, sizeof(double) * std::max<int64_t>(Z, 1)));
   CK(cudaMalloc((void**)&m->fac, sizeof(double) * std::max<int64_t>(Z, 1)));
@@ -156,20 +157,38 @@ int eb_dlogl(gync_ebmodel* m, const double* dw, double* out, cudaStream_t s) {
   return mv_finish(m->part, np, m->K, GYNC_EPI_PLAIN, out, nullptr, nullptr, 0, nullptr, s);
 }
 
-// rho = Lz w (regularizers.jl:36,65)
+// rho = Lz w (regularizers.jl:36,65): column sums of Lzt
 int eb_rho(gync_ebmodel* m, const double* dw, cudaStream_t s) {
   int np = 0;
-  if (int rc = mv_n_launch(m->Lz, m->Z, m->K, dw, m->part, &np, s)) return rc;
+  if (int rc = mv_t_launch(m->Lzt, m->K, m->Z, dw, m->part, &np, s)) return rc;
   return mv_finish(m->part, np, m->Z, GYNC_EPI_PLAIN, m->rho, nullptr, nullptr, 0, nullptr, s);
+}
+
+// one-pass form available?  (even K for 16-byte rows; accumulator + w in shared memory)
+bool eb_dhz_fusable(const gync_ebmodel* m, size_t* smem) {
+  *smem = sizeof(double) * 2 * (size_t)m->K;
+  int max_optin = 0;
+  if (cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, g_device) != cudaSuccess) return false;
+  return (m->K % 2 == 0) && *smem + 2048 <= (size_t)max_optin && !getenv("GYNC_DHZ_TWO_PASS");
 }
 
 // dhzdiscr / dhzcont (regularizers.jl:59-79, 50-57 + 149-160)  ->  out (K); sets flags[1] on NaN
 int eb_dhz(gync_ebmodel* m, const double* dw, int cont, double* out, cudaStream_t s) {
+  size_t smem = 0;
+  if (eb_dhz_fusable(m, &smem)) {
+    const int nb = (int)std::min<int64_t>(g_num_sms, (m->Z + GYNC_DHZ_ROWS - 1) / GYNC_DHZ_ROWS);
+    CK(cudaFuncSetAttribute(gync_dhz_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gync_dhz_fused_kernel<<<nb, GYNC_DHZ_THREADS, smem, s>>>(m->Lzt, m->K, m->Z, dw, m->zmult, cont, m->rho, m->part);
+    g_launches += 1;
+    CK(cudaGetLastError());
+    return mv_finish(m->part, nb, m->K, cont ? GYNC_EPI_DHZ_CONT : GYNC_EPI_DHZ_DISCR, out, nullptr, m->rho, m->zmult,
+                     m->flags + 1, s);
+  }
   if (int rc = eb_rho(m, dw, s)) return rc;
   gync_dhz_factors_kernel<<<blocks_for(m->Z, 256), 256, 0, s>>>(dw, m->K, m->zmult, m->rho, m->Z, cont, m->fac);
   g_launches += 1;
   int np = 0;
-  if (int rc = mv_t_launch(m->Lz, m->Z, m->K, m->fac, m->part, &np, s)) return rc;
+  if (int rc = mv_n_launch(m->Lzt, m->K, m->Z, m->fac, m->part, &np, s)) return rc;
   return mv_finish(m->part, np, m->K, cont ? GYNC_EPI_DHZ_CONT : GYNC_EPI_DHZ_DISCR, out, nullptr, m->rho, m->zmult,
                    m->flags + 1, s);
 }
@@ -330,8 +349,9 @@ int gync_ebmodel_create(const double* ys, int64_t K, const double* datas, int64_
     DBuf dZ, dSz;
     rc = up(dZ, zs, (size_t)D * Z);
     if (!rc && sig_z) rc = up(dSz, sig_z, (size_t)D);
-    if (!rc) rc = lmat_launch(dZ.as<double>(), Z, 1, D, dY.as<double>(), K, 1, D, D, sig_z ? dSz.as<double>() : dS.as<double>(),
-                              1, m->Lz, g_stream);
+    // likelihoodmat(zs, ys)' == likelihoodmat(ys, zs): built directly in the transposed layout
+    if (!rc) rc = lmat_launch(dY.as<double>(), K, 1, D, dZ.as<double>(), Z, 1, D, D, sig_z ? dSz.as<double>() : dS.as<double>(),
+                              1, m->Lzt, g_stream);
     if (!rc && cudaStreamSynchronize(g_stream) != cudaSuccess) rc = fail(GYNC_ERR_CUDA, "gync_ebmodel_create: kernel failed");
   }
   if (!rc && cudaStreamSynchronize(g_stream) != cudaSuccess) rc = fail(GYNC_ERR_CUDA, "gync_ebmodel_create: kernel failed");
@@ -348,7 +368,15 @@ int gync_ebmodel_from_matrices(const double* Ld, int64_t K, int64_t M, const dou
   m->K = K; m->M = M; m->Z = Z; m->zmult = (int)(Z / K);
   int rc = ebmodel_alloc(m);
   if (!rc && M > 0 && cudaMemcpyAsync(m->Ld, Ld, sizeof(double) * K * M, cudaMemcpyHostToDevice, g_stream) != cudaSuccess) rc = fail(GYNC_ERR_CUDA, "upload Ld");
-  if (!rc && Z > 0 && cudaMemcpyAsync(m->Lz, Lz, sizeof(double) * Z * K, cudaMemcpyHostToDevice, g_stream) != cudaSuccess) rc = fail(GYNC_ERR_CUDA, "upload Lz");
+  DBuf tmp;
+  if (!rc && Z > 0) {
+    if (tmp.alloc(sizeof(double) * Z * K) != cudaSuccess ||
+        cudaMemcpyAsync(tmp.p, Lz, sizeof(double) * Z * K, cudaMemcpyHostToDevice, g_stream) != cudaSuccess) rc = fail(GYNC_ERR_CUDA, "upload Lz");
+    else {
+      gync_transpose_kernel<<<dim3(blocks_for(Z, 32), blocks_for(K, 32)), 256, 0, g_stream>>>(tmp.as<double>(), Z, K, m->Lzt);
+      g_launches += 1;
+    }
+  }
   if (!rc && cudaStreamSynchronize(g_stream) != cudaSuccess) rc = fail(GYNC_ERR_CUDA, "gync_ebmodel_from_matrices: copy failed");
   if (rc) { ebmodel_free(m); return rc; }
   *out = m;
@@ -366,16 +394,23 @@ int gync_ebmodel_dims(gync_ebmodel* m, int64_t* K, int64_t* M, int64_t* Z) {
 int gync_ebmodel_matrices(gync_ebmodel* m, double* Ld, double* Lz) {
   if (int rc = eb_check_model(m, m, "gync_ebmodel_matrices")) return rc;
   if (Ld && m->M > 0) CK(cudaMemcpyAsync(Ld, m->Ld, sizeof(double) * m->K * m->M, cudaMemcpyDeviceToHost, g_stream));
-  if (Lz && m->Z > 0) CK(cudaMemcpyAsync(Lz, m->Lz, sizeof(double) * m->Z * m->K, cudaMemcpyDeviceToHost, g_stream));
+  DBuf tmp;
+  if (Lz && m->Z > 0) {
+    CK(tmp.alloc(sizeof(double) * m->Z * m->K));
+    gync_transpose_kernel<<<dim3(blocks_for(m->K, 32), blocks_for(m->Z, 32)), 256, 0, g_stream>>>(m->Lzt, m->K, m->Z, tmp.as<double>());
+    g_launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(Lz, tmp.p, sizeof(double) * m->Z * m->K, cudaMemcpyDeviceToHost, g_stream));
+  }
   CK(cudaStreamSynchronize(g_stream));
   return GYNC_OK;
 }
 
 // device pointers of the resident matrices (for callers that keep working on the device: EM, bench)
-int gync_ebmodel_device_ptrs(gync_ebmodel* m, double** dLd, double** dLz) {
+int gync_ebmodel_device_ptrs(gync_ebmodel* m, double** dLd, double** dLzt) {
   if (!m) return fail(GYNC_ERR_ARG, "gync_ebmodel_device_ptrs: NULL");
   if (dLd) *dLd = m->Ld;
-  if (dLz) *dLz = m->Lz;
+  if (dLzt) *dLzt = m->Lzt;
   return GYNC_OK;
 }
 

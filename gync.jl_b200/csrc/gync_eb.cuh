@@ -411,3 +411,108 @@ __global__ void __launch_bounds__(256) gync_pick_measured_kernel(const double* _
   const int sp = (h == 0) ? 1 : (h == 1) ? 6 : (h == 2) ? 23 : 24;
   out[k + 124 * n] = Y[n + N * ((int64_t)t + (int64_t)nT * sp)];
 }
+
+// ------------------------------------------------------------------------------------------ K7b
+// dhz in ONE pass over HBM.  The two products of dhzdiscr (rho = Lz w, then Lz' (wz ./ rho), regularizers.jl:65-72)
+// cannot be fused entry by entry — a row's factor needs the whole row first — but they can be fused ROW by row when a
+// z-row is contiguous: the matrix is therefore kept as Lzt (K x Z column-major: element (z,k) at k + K z; the
+// likelihood matrix is symmetric in its arguments, so it is simply built with the operands swapped).  A CTA owns a set
+// of z-rows; for four rows at a time it streams them once from HBM for the dot products with w (w staged in shared
+// memory), reduces, forms the four factors and immediately re-reads the same 4 K doubles — now L2 hits — to
+// accumulate f_z Lz[z,:] into its private K-vector in shared memory.  Per-CTA vectors are summed in a fixed order by
+// gync_mv_finish_kernel.  HBM traffic: 8 Z K bytes per gradient instead of 16 Z K.
+// (A software-pipelined variant that overlaps the L2 re-read of group g with the HBM stream of group g+1 measured
+// the same 177-183 us at K = Z = 1e4, so the simpler form is kept.)
+#define GYNC_DHZ_THREADS 512
+#define GYNC_DHZ_ROWS 4
+
+__global__ void __launch_bounds__(GYNC_DHZ_THREADS, 1)
+gync_dhz_fused_kernel(const double* __restrict__ Lzt, int64_t K, int64_t Z, const double* __restrict__ w, int zmult, int cont,
+                      double* __restrict__ rho_out, double* __restrict__ part /* gridDim.x x K */) {
+  extern __shared__ __align__(16) double gync_dhz_sm[];
+  double* acc = gync_dhz_sm;            // K
+  double* ws = gync_dhz_sm + K;         // K
+  __shared__ double red[GYNC_DHZ_ROWS][GYNC_DHZ_THREADS / 32];
+  __shared__ double fz[GYNC_DHZ_ROWS];
+  const int tid = threadIdx.x;
+  for (int64_t k = tid; k < K; k += GYNC_DHZ_THREADS) { acc[k] = 0.0; ws[k] = w[k]; }
+  __syncthreads();
+  const int64_t K2 = K >> 1;            // K is even on this path (16-byte row alignment)
+  const double2* __restrict__ ws2 = reinterpret_cast<const double2*>(ws);
+  double2* acc2 = reinterpret_cast<double2*>(acc);
+  for (int64_t z0 = (int64_t)blockIdx.x * GYNC_DHZ_ROWS; z0 < Z; z0 += (int64_t)gridDim.x * GYNC_DHZ_ROWS) {
+    const double2* __restrict__ row[GYNC_DHZ_ROWS];
+#pragma unroll
+    for (int r = 0; r < GYNC_DHZ_ROWS; ++r)
+      row[r] = reinterpret_cast<const double2*>(Lzt + K * min(z0 + r, Z - 1));     // rows past Z: re-read the last one, unused
+    double dot[GYNC_DHZ_ROWS];
+#pragma unroll
+    for (int r = 0; r < GYNC_DHZ_ROWS; ++r) dot[r] = 0.0;
+    int64_t k = tid;
+    for (; k + GYNC_DHZ_THREADS < K2; k += 2 * GYNC_DHZ_THREADS) {
+      double2 a[GYNC_DHZ_ROWS], b[GYNC_DHZ_ROWS];
+#pragma unroll
+      for (int r = 0; r < GYNC_DHZ_ROWS; ++r) { a[r] = row[r][k]; b[r] = row[r][k + GYNC_DHZ_THREADS]; }
+      const double2 wa = ws2[k], wb = ws2[k + GYNC_DHZ_THREADS];
+#pragma unroll
+      for (int r = 0; r < GYNC_DHZ_ROWS; ++r) {
+        dot[r] = fma(a[r].x, wa.x, dot[r]); dot[r] = fma(a[r].y, wa.y, dot[r]);
+        dot[r] = fma(b[r].x, wb.x, dot[r]); dot[r] = fma(b[r].y, wb.y, dot[r]);
+      }
+    }
+    for (; k < K2; k += GYNC_DHZ_THREADS) {
+      const double2 wa = ws2[k];
+#pragma unroll
+      for (int r = 0; r < GYNC_DHZ_ROWS; ++r) { const double2 a = row[r][k]; dot[r] = fma(a.x, wa.x, dot[r]); dot[r] = fma(a.y, wa.y, dot[r]); }
+    }
+#pragma unroll
+    for (int r = 0; r < GYNC_DHZ_ROWS; ++r) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dot[r] += __shfl_xor_sync(0xffffffffu, dot[r], o);
+      if ((tid & 31) == 0) red[r][tid >> 5] = dot[r];
+    }
+    __syncthreads();
+    if (tid < GYNC_DHZ_ROWS) {
+      double s = 0.0;
+      for (int wp = 0; wp < GYNC_DHZ_THREADS / 32; ++wp) s += red[tid][wp];
+      const int64_t z = z0 + tid;
+      double f = 0.0;
+      if (z < Z) {
+        rho_out[z] = s;
+        const double wz = ws[z % K] / (double)zmult;
+        f = cont ? wz * log(s) / s : wz / s;
+      }
+      fz[tid] = f;
+    }
+    __syncthreads();
+    double f[GYNC_DHZ_ROWS];
+#pragma unroll
+    for (int r = 0; r < GYNC_DHZ_ROWS; ++r) f[r] = fz[r];
+    const int nrow = (int)min((int64_t)GYNC_DHZ_ROWS, Z - z0);
+    for (k = tid; k < K2; k += GYNC_DHZ_THREADS) {
+      double2 a[GYNC_DHZ_ROWS];
+#pragma unroll
+      for (int r = 0; r < GYNC_DHZ_ROWS; ++r) a[r] = row[r][k];
+      double2 c = acc2[k];
+#pragma unroll
+      for (int r = 0; r < GYNC_DHZ_ROWS; ++r)
+        if (r < nrow) { c.x = fma(f[r], a[r].x, c.x); c.y = fma(f[r], a[r].y, c.y); }   // a 0 * Inf of a padding row must not leak in
+      acc2[k] = c;
+    }
+    // red / fz are rewritten only after the next __syncthreads pair; acc entries are private to their thread
+  }
+  __syncthreads();
+  for (int64_t k = tid; k < K; k += GYNC_DHZ_THREADS) part[(int64_t)blockIdx.x * K + k] = acc[k];
+}
+
+// out (C x R column-major) = in' (in: R x C column-major); 32 x 32 tiles through shared memory
+__global__ void __launch_bounds__(256) gync_transpose_kernel(const double* __restrict__ in, int64_t R, int64_t C, double* __restrict__ out) {
+  __shared__ double tile[32][33];
+  const int64_t r0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8)
+    if (r0 + tx < R && c0 + j < C) tile[j][tx] = in[(r0 + tx) + R * (c0 + j)];
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8)
+    if (c0 + tx < C && r0 + j < R) out[(c0 + tx) + C * (r0 + j)] = tile[tx][j];
+}

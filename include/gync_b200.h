@@ -193,7 +193,8 @@ int  gync_ebmodel_from_matrices(const double* Ld, int64_t K, int64_t M, const do
 void gync_ebmodel_destroy(gync_ebmodel* m);
 int  gync_ebmodel_dims(gync_ebmodel* m, int64_t* K, int64_t* M, int64_t* Z);
 int  gync_ebmodel_matrices(gync_ebmodel* m, double* Ld /* K x M or NULL */, double* Lz /* Z x K or NULL */);
-int  gync_ebmodel_device_ptrs(gync_ebmodel* m, double** dLd, double** dLz);
+/* resident matrices: Ld (K x M) and Lzt = Lz' (K x Z column-major: every z-row contiguous) */
+int  gync_ebmodel_device_ptrs(gync_ebmodel* m, double** dLd, double** dLzt);
 /* logl(m,w) = sum(log(L*w)), dlogl(m,w) = sum(L./(L*w),1) with L = Ld' — eb/regularizers.jl:3-10 */
 int  gync_ebmodel_logl(gync_ebmodel* m, const double* w, double* out);
 int  gync_ebmodel_dlogl(gync_ebmodel* m, const double* w, double* d /* K */);

@@ -413,8 +413,11 @@ def test_amm_adaptive_step_with_injected_randomness(gpu, gold):
                 assert relerr(out[it, :, cidx], np.exp(xs)) < 1e-9, (fresh, cidx, it)
             assert acc == nacc[cidx] and acc >= 1
             assert am[cidx] == t["m"]
-            assert np.allclose(aMv[cidx], t["Mv"], rtol=1e-12, atol=1e-14)        # fma contraction on the device
-            assert np.allclose(aMvv[cidx], t["Mvv"], rtol=1e-12, atol=1e-14)
+            # moments inherit the state differences: rounding only (fma contraction) without adapted proposals, the
+            # factor-conditioning bound above with them
+            tolm = dict(rtol=1e-12, atol=1e-13) if fresh else dict(rtol=1e-9, atol=1e-10)
+            assert np.allclose(aMv[cidx], t["Mv"], **tolm)
+            assert np.allclose(aMvv[cidx], t["Mvv"], **tolm)
             if not fresh:
                 # the factor amplifies rounding by the conditioning of Sigma; compare the covariance it represents
                 assert np.allclose(aLm[cidx] @ aLm[cidx].T, t["SigmaLm"] @ t["SigmaLm"].T, rtol=1e-7, atol=1e-12)
@@ -429,7 +432,7 @@ def test_sample_api_adaptive(gpu):
     c = gpu.Config(gpu.Lausanne(1), adapt=True)
     s = gpu.sample(c, 150, seed=5)
     assert s.samples.shape == (150, 116) and s.variate.m == 150
-    assert np.array_equal(gpu.api.propinit(s), c.propvar)
+    assert np.allclose(gpu.api.propinit(s), c.propvar, rtol=1e-14, atol=0)
     s = gpu.sample_bang(s, 150)
     assert s.samples.shape == (300, 116) and s.variate.m == 300
     s2 = gpu.sample(c, 300, seed=5)
