@@ -81,6 +81,20 @@ type B200Variate
   SigmaL::Matrix{Float64}       # chol(propvar).L (model.jl:104)
   seed::UInt64
   iteration::UInt64
+  # AMMTune adaptation state (used when c.adapt; m < 0: adaptation not started)
+  m::Vector{Int64}              # length 1
+  Mv::Vector{Float64}           # 116
+  Mvv::Matrix{Float64}          # 116 x 116 (symmetric)
+  SigmaLm::Matrix{Float64}      # 116 x 116, the library stores the lower factor ROW-major == its transpose column-major
+end
+
+immutable AmmTune               # gync_amm_tune
+  beta::Cdouble
+  scale::Cdouble
+  m::Ptr{Int64}
+  Mv::Ptr{Cdouble}
+  Mvv::Ptr{Cdouble}
+  SigmaLm::Ptr{Cdouble}
 end
 
 function sample!(s::Sampling, iters::Int)
@@ -92,11 +106,21 @@ function sample!(s::Sampling, iters::Int)
   state = reshape(copy(v.state), 1, 116)
   lf    = [v.logf]
   o     = Ref(SolverOpts(1e-8, 1e-10))
+  if c.adapt                                            # Mamba.sample!(variate, adapt=true) (sampling.jl:72, model.jl:104-106)
+    tune = Ref(AmmTune(0.05, 2.38, pointer(v.m), pointer(v.Mv), pointer(v.Mvv), pointer(v.SigmaLm)))
+    check(ccall((:gync_mcmc_run_amm, LIBGYNC), Cint,
+                (Ptr{Cdouble}, Ptr{Cdouble}, Int64, Ptr{Cdouble}, Cdouble, Ptr{Cdouble}, Cint, Ptr{Cdouble}, Ptr{Cint},
+                 Ptr{Cdouble}, Ptr{SolverOpts}, Int64, Cint, UInt64, UInt64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble},
+                 Ptr{Cdouble}, Ptr{Int64}, Ptr{AmmTune}),
+                state, lf, 1, v.SigmaL, 0.0, data(c), 1, [c.sigma_rho], Cint[0], priorvector(c), o,
+                iters, thin, v.seed, v.iteration, C_NULL, C_NULL, C_NULL, out, nacc, tune))
+  else
   check(ccall((:gync_mcmc_run, LIBGYNC), Cint,
               (Ptr{Cdouble}, Ptr{Cdouble}, Int64, Ptr{Cdouble}, Cdouble, Ptr{Cdouble}, Cint, Ptr{Cdouble}, Ptr{Cint},
                Ptr{Cdouble}, Ptr{SolverOpts}, Int64, Cint, UInt64, UInt64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Int64}),
               state, lf, 1, v.SigmaL, 0.0, data(c), 1, [c.sigma_rho], Cint[0], priorvector(c), o,
               iters, thin, v.seed, v.iteration, C_NULL, C_NULL, out, nacc))
+  end
   v.state, v.logf, v.iteration = vec(state), lf[1], v.iteration + iters
   s.samples = vcat(s.samples, out)                      # sampling.jl:66-68,74
   s
@@ -127,4 +151,83 @@ function wcnormalize(LL::Matrix{Float64}, prior::Vector{Float64}, counts::Vector
               (Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Int64}, Int64, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
               LL, prior, counts, K, M, L, w, d))
   L, w, d
+end
+
+# propadapt(s) (sampling.jl:26-29): SigmaLm is held row-major by the library, i.e. transposed in Julia's view
+propadapt(s::Sampling) = (l = s.variate.SigmaLm'; l * l')
+
+# === src/eb: likelihood matrix, LikelihoodModel, regularisers, projected gradient ascent =================
+
+cols(ms) = hcat([vec(m) for m in ms]...)               # likelihoodmat.jl:35: D x n, NaN = missing
+
+# --- likelihoodmat_nanfast(xs, ys, d::MatrixNormalCentered; renormalize) (eb/likelihoodmat.jl:34-58) ---
+function likelihoodmat_nanfast(xs, ys, d::MatrixNormalCentered; renormalize=true)
+  A, B, s = cols(xs), cols(ys), vec(d.sigmas)
+  L = Array(Float64, size(A, 2), size(B, 2))
+  check(ccall((:gync_likelihoodmat, LIBGYNC), Cint,
+              (Ptr{Cdouble}, Int64, Ptr{Cdouble}, Int64, Cint, Ptr{Cdouble}, Cint, Ptr{Cdouble}),
+              A, size(A, 2), B, size(B, 2), length(s), s, renormalize ? 1 : 0, L))
+  L
+end
+
+# --- phi(x) = forwardsol(x)[:, measuredinds] (eb/gync.jl:11): all samples in one launch ---
+function phi(xs::Vector{Vector{Float64}})
+  X  = vcat([x' for x in xs]...)                        # N x 116
+  Y  = Array(Float64, 124, length(xs))
+  st = Array(Cint, length(xs))
+  o  = Ref(SolverOpts(1e-8, 1e-10))
+  check(ccall((:gync_phi_batch, LIBGYNC), Cint, (Ptr{Cdouble}, Int64, Ptr{SolverOpts}, Ptr{Cdouble}, Ptr{Cint}),
+              X, length(xs), o, Y, st))
+  [reshape(Y[:, n], 31, 4) for n in 1:length(xs)]       # NaN matrix on solver failure (gyncycle.jl:18-19)
+end
+
+# --- LikelihoodModel (eb/likelihoodmodel.jl:3-14): one handle per model, both likelihood matrices stay in HBM.
+#     Keep it in a field / WeakKeyDict next to the model and free it with a finalizer.
+function b200model(m::LikelihoodModel)
+  Y, D, Zs = cols(m.ys), cols(m.datas), cols(m.zs)
+  h = Ref{Ptr{Void}}(C_NULL)
+  check(ccall((:gync_ebmodel_create, LIBGYNC), Cint,
+              (Ptr{Cdouble}, Int64, Ptr{Cdouble}, Int64, Ptr{Cdouble}, Int64, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Ptr{Void}}),
+              Y, size(Y, 2), D, size(D, 2), Zs, size(Zs, 2), size(Y, 1), vec(m.measerr.sigmas), vec(m.zsampledistr.sigmas), h))
+  h[]
+end
+b200free(h::Ptr{Void}) = ccall((:gync_ebmodel_destroy, LIBGYNC), Void, (Ptr{Void},), h)
+
+function logl(h::Ptr{Void}, w::Vector{Float64})         # logl(m, w) (regularizers.jl:5, likelihoodmodel.jl:72)
+  r = Cdouble[0]
+  check(ccall((:gync_ebmodel_logl, LIBGYNC), Cint, (Ptr{Void}, Ptr{Cdouble}, Ptr{Cdouble}), h, w, r)); r[1]
+end
+function dlogl(h::Ptr{Void}, w::Vector{Float64})        # regularizers.jl:7-10
+  d = similar(w)
+  check(ccall((:gync_ebmodel_dlogl, LIBGYNC), Cint, (Ptr{Void}, Ptr{Cdouble}, Ptr{Cdouble}), h, w, d)); d
+end
+function hz(h::Ptr{Void}, w::Vector{Float64})           # hz(m, w) (regularizers.jl:24-45); wz = repeatweights(w, zs)
+  r = Cdouble[0]
+  check(ccall((:gync_ebmodel_hz, LIBGYNC), Cint, (Ptr{Void}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}), h, w, C_NULL, r)); r[1]
+end
+function dhz(h::Ptr{Void}, w::Vector{Float64})          # dhzdiscr (regularizers.jl:59-79); errors on NaN like :77
+  d = similar(w)
+  check(ccall((:gync_ebmodel_dhz, LIBGYNC), Cint, (Ptr{Void}, Ptr{Cdouble}, Cint, Ptr{Cdouble}), h, w, DHZCONT ? 1 : 0, d)); d
+end
+
+# em(m, w0, niter) (likelihoodmodel.jl:17-20)
+function em(h::Ptr{Void}, w0::Vector{Float64}, niter::Int)
+  w, H = copy(w0), Array(Float64, length(w0), max(niter - 1, 0))
+  niter > 1 && check(ccall((:gync_ebmodel_em, LIBGYNC), Cint, (Ptr{Void}, Ptr{Cdouble}, Cint, Ptr{Cdouble}), h, w, niter - 1, H))
+  vcat(Vector[w0], [H[:, i] for i in 1:size(H, 2)])
+end
+
+# mple(m, reg, h, niter; autoh, w0) (likelihoodmodel.jl:33-41): the whole gradientascent loop on the device
+function mple(hm::Ptr{Void}, ndata::Int, reg, h, niter; autoh=true, w0=Float64[])
+  autoh && (h = h / ((1 - reg) * (ndata / (1 / 100)) + reg / (1 / 1000)))
+  w, H = copy(w0), Array(Float64, length(w0), max(niter - 1, 0))
+  niter > 1 && check(ccall((:gync_ebmodel_mple, LIBGYNC), Cint,
+                           (Ptr{Void}, Ptr{Cdouble}, Cdouble, Cdouble, Cint, Cint, Ptr{Cdouble}),
+                           hm, w, reg, h, niter - 1, DHZCONT ? 1 : 0, H))
+  vcat(Vector[w0], [H[:, i] for i in 1:size(H, 2)])
+end
+
+# projectsimplex!(y) (projectsimplex.jl:8)
+function projectsimplex!(y::Vector{Float64})
+  check(ccall((:gync_projectsimplex, LIBGYNC), Cint, (Ptr{Cdouble}, Int64), y, length(y))); y
 end
