@@ -65,7 +65,7 @@ int mv_t_launch(const double* A, int64_t R, int64_t C, const double* x, double* 
 
 int mv_finish(const double* part, int nparts, int64_t n, int epi, double* out, double* out2, const double* rho, int zmult,
               int* nan_flag, cudaStream_t s) {
-  gync_mv_finish_kernel<<<blocks_for(n, 256), 256, 0, s>>>(part, nparts, n, epi, out, out2, rho, zmult, nan_flag);
+  gync_mv_finish_kernel<<<blocks_for(n, 256 / GYNC_FIN_SLICES), 256, 0, s>>>(part, nparts, n, epi, out, out2, rho, zmult, nan_flag);
   g_launches += 1;
   CK(cudaGetLastError());
   return GYNC_OK;

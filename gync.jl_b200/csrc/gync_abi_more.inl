@@ -224,6 +224,55 @@ int gync_wc_normalize_dev(double* dLL_inout, const double* d_logprior, const int
   return GYNC_OK;
 }
 
+// Row-sharded normalisation (one process per GPU): three phases, the caller's collectives in between.
+int gync_wc_colstats_dev(const double* dLL, const double* d_logprior, const int64_t* d_counts, int64_t K, int32_t M,
+                         double* d_stats /* M + 2 */, void* stream) {
+  if (K < 0 || M < 1 || !d_stats || (K > 0 && (!dLL || !d_logprior || !d_counts))) return fail(GYNC_ERR_ARG, "gync_wc_colstats: bad arguments");
+  if (int rc = ensure_init()) return rc;
+  gync_wc_colstats_kernel<<<M + 2, GYNC_WC_THREADS, 0, (cudaStream_t)stream>>>(dLL, d_logprior, (const long long*)d_counts, K, M, d_stats);
+  g_launches += 1;
+  CK(cudaGetLastError());
+  return GYNC_OK;
+}
+
+int gync_wc_expsum_dev(double* dLL_inout, int64_t K, int32_t M, const double* d_colmax, double* d_colsum, void* stream) {
+  if (K < 0 || M < 1 || !d_colmax || !d_colsum || (K > 0 && !dLL_inout)) return fail(GYNC_ERR_ARG, "gync_wc_expsum: bad arguments");
+  if (int rc = ensure_init()) return rc;
+  gync_wc_expsum_kernel<<<M, GYNC_WC_THREADS, 0, (cudaStream_t)stream>>>(dLL_inout, K, M, d_colmax, d_colsum);
+  g_launches += 1;
+  CK(cudaGetLastError());
+  return GYNC_OK;
+}
+
+// d_stats: [colsum(M) | lpmax | sumcounts] (global values).  Writes the local weights, the unnormalised local density and
+// its local total (d_total[0]); gync_wc_scale_dev divides by the global total.
+int gync_wc_rows_dev(double* dL_inout, const double* d_logprior, const int64_t* d_counts, int64_t K, int32_t M,
+                     const double* d_stats, double* d_weights, double* d_density, double* d_total, void* stream) {
+  if (K < 0 || M < 1 || !d_stats || !d_total || (K > 0 && (!dL_inout || !d_logprior || !d_counts || !d_weights || !d_density)))
+    return fail(GYNC_ERR_ARG, "gync_wc_rows: bad arguments");
+  if (int rc = ensure_init()) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nb = g_num_sms * 4;
+  double* part = nullptr;
+  CK(cudaMallocAsync((void**)&part, sizeof(double) * nb, s));
+  gync_wc_rowpass_kernel<<<nb, 256, 0, s>>>(dL_inout, d_logprior, (const long long*)d_counts, K, M, d_stats, d_stats + M, d_weights,
+                                            d_density, part);
+  gync_wc_total_kernel<<<1, 32, 0, s>>>(part, nb, d_total);
+  g_launches += 2;
+  CK(cudaGetLastError());
+  CK(cudaFreeAsync(part, s));
+  return GYNC_OK;
+}
+
+int gync_wc_scale_dev(double* d_density, int64_t K, const double* d_total, void* stream) {
+  if (K < 0 || !d_total || (K > 0 && !d_density)) return fail(GYNC_ERR_ARG, "gync_wc_scale: bad arguments");
+  if (int rc = ensure_init()) return rc;
+  gync_wc_scale_kernel<<<g_num_sms * 4, 256, 0, (cudaStream_t)stream>>>(d_density, K, d_total, 1);
+  g_launches += 1;
+  CK(cudaGetLastError());
+  return GYNC_OK;
+}
+
 int gync_wc_normalize(const double* LL, const double* logprior, const int64_t* counts, int64_t K, int32_t M,
                       double* L, double* weights, double* density) {
   if (K < 1 || M < 1 || !LL || !logprior || !counts || !L || !weights || !density)

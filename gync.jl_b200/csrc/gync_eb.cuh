@@ -250,13 +250,22 @@ enum GyncMvEpi {
   GYNC_EPI_DHZ_CONT = 3,  // out = -1 - s                                          (regularizers.jl:149-160)
   GYNC_EPI_EM = 4         // out = out / M * s      (in place on w; em.jl:33-38)
 };
+#define GYNC_FIN_SLICES 4     /* threads per output element: slice s adds partials s, s+4, ..; slices are combined in order */
 __global__ void __launch_bounds__(256)
 gync_mv_finish_kernel(const double* __restrict__ part, int nparts, int64_t n, int epi, double* __restrict__ out,
                       double* __restrict__ out2, const double* __restrict__ rho, int zmult, int* __restrict__ nan_flag) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  __shared__ double sl[GYNC_FIN_SLICES][256 / GYNC_FIN_SLICES];
+  const int col = threadIdx.x % (256 / GYNC_FIN_SLICES), slice = threadIdx.x / (256 / GYNC_FIN_SLICES);
+  const int64_t i = (int64_t)blockIdx.x * (256 / GYNC_FIN_SLICES) + col;
   double s = 0.0;
-  for (int p = 0; p < nparts; ++p) s += part[(int64_t)p * n + i];
+  if (i < n)
+    for (int p = slice; p < nparts; p += GYNC_FIN_SLICES) s += part[(int64_t)p * n + i];
+  sl[slice][col] = s;
+  __syncthreads();
+  if (slice != 0 || i >= n) return;
+  s = sl[0][col];
+#pragma unroll
+  for (int q = 1; q < GYNC_FIN_SLICES; ++q) s += sl[q][col];
   double r = s;
   if (epi == GYNC_EPI_RECIP) {
     out2[i] = 1.0 / s;
@@ -489,14 +498,33 @@ gync_dhz_fused_kernel(const double* __restrict__ Lzt, int64_t K, int64_t Z, cons
 #pragma unroll
     for (int r = 0; r < GYNC_DHZ_ROWS; ++r) f[r] = fz[r];
     const int nrow = (int)min((int64_t)GYNC_DHZ_ROWS, Z - z0);
-    for (k = tid; k < K2; k += GYNC_DHZ_THREADS) {
+#pragma unroll
+    for (int r = 0; r < GYNC_DHZ_ROWS; ++r) if (r >= nrow) f[r] = 0.0;
+    const bool full = (nrow == GYNC_DHZ_ROWS);      // padding rows re-read the last row: 0 * Inf must not leak in
+    k = tid;
+    if (full) {
+      for (; k + GYNC_DHZ_THREADS < K2; k += 2 * GYNC_DHZ_THREADS) {      // two column pairs per trip: 8 L2 loads in flight
+        double2 a[GYNC_DHZ_ROWS], b[GYNC_DHZ_ROWS];
+#pragma unroll
+        for (int r = 0; r < GYNC_DHZ_ROWS; ++r) { a[r] = row[r][k]; b[r] = row[r][k + GYNC_DHZ_THREADS]; }
+        double2 c = acc2[k], d = acc2[k + GYNC_DHZ_THREADS];
+#pragma unroll
+        for (int r = 0; r < GYNC_DHZ_ROWS; ++r) {
+          c.x = fma(f[r], a[r].x, c.x); c.y = fma(f[r], a[r].y, c.y);
+          d.x = fma(f[r], b[r].x, d.x); d.y = fma(f[r], b[r].y, d.y);
+        }
+        acc2[k] = c;
+        acc2[k + GYNC_DHZ_THREADS] = d;
+      }
+    }
+    for (; k < K2; k += GYNC_DHZ_THREADS) {
       double2 a[GYNC_DHZ_ROWS];
 #pragma unroll
       for (int r = 0; r < GYNC_DHZ_ROWS; ++r) a[r] = row[r][k];
       double2 c = acc2[k];
 #pragma unroll
       for (int r = 0; r < GYNC_DHZ_ROWS; ++r)
-        if (r < nrow) { c.x = fma(f[r], a[r].x, c.x); c.y = fma(f[r], a[r].y, c.y); }   // a 0 * Inf of a padding row must not leak in
+        if (r < nrow) { c.x = fma(f[r], a[r].x, c.x); c.y = fma(f[r], a[r].y, c.y); }
       acc2[k] = c;
     }
     // red / fz are rewritten only after the next __syncthreads pair; acc entries are private to their thread

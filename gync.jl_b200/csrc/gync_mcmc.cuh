@@ -264,3 +264,50 @@ gync_wc_scale_kernel(double* __restrict__ density, int64_t K, const double* __re
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < K; k += (int64_t)gridDim.x * blockDim.x)
     density[k] /= tot;
 }
+
+// ---- K5 row-sharded: the same normalisation with the collectives between the phases left to the
+// caller: colstats -> allreduce(max) of [colmax(M), lpmax] and allreduce(sum) of sumcounts -> expsum -> allreduce(sum)
+// of colsum(M) -> rowpass (above) -> total -> allreduce(sum) of the density total -> scale.
+// blocks 0..M-1: column maxima; block M: max of logprior; block M+1: sum of counts.  out: M + 2 doubles.
+__global__ void __launch_bounds__(GYNC_WC_THREADS)
+gync_wc_colstats_kernel(const double* __restrict__ LL, const double* __restrict__ logprior, const long long* __restrict__ counts,
+                        int64_t K, int M, double* __restrict__ out) {
+  __shared__ double s[32];
+  const int b = blockIdx.x;
+  double v = (b <= M) ? -INFINITY : 0.0;
+  if (b < M) {
+    const double* col = LL + (size_t)b * K;
+    for (int64_t k = threadIdx.x; k < K; k += blockDim.x) v = fmax(v, col[k]);
+  } else if (b == M) {
+    for (int64_t k = threadIdx.x; k < K; k += blockDim.x) v = fmax(v, logprior[k]);
+  } else {
+    for (int64_t k = threadIdx.x; k < K; k += blockDim.x) v += (double)counts[k];
+  }
+  v = wc_block_reduce(v, b <= M, s);
+  if (threadIdx.x == 0) out[b] = v;
+}
+
+// L = exp(LL - colmax[m]) in place, colsum[m] = sum over the local rows
+__global__ void __launch_bounds__(GYNC_WC_THREADS)
+gync_wc_expsum_kernel(double* __restrict__ LL, int64_t K, int M, const double* __restrict__ colmax, double* __restrict__ colsum) {
+  __shared__ double s[32];
+  const int b = blockIdx.x;
+  double* col = LL + (size_t)b * K;
+  const double mx = colmax[b];
+  double sm = 0.0;
+  for (int64_t k = threadIdx.x; k < K; k += blockDim.x) {
+    const double e = exp(col[k] - mx);
+    col[k] = e;
+    sm += e;
+  }
+  sm = wc_block_reduce(sm, false, s);
+  if (threadIdx.x == 0) colsum[b] = sm;
+}
+
+__global__ void __launch_bounds__(256) gync_wc_total_kernel(const double* __restrict__ dens_partial, int nb, double* __restrict__ total) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double t = 0.0;
+    for (int b = 0; b < nb; ++b) t += dens_partial[b];
+    total[0] = t;
+  }
+}

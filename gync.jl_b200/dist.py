@@ -33,6 +33,73 @@ def em_iterate_sharded(niter, norms_fn, step_fn, allreduce):
     return norms
 
 
+def wc_normalize_sharded(colstats_fn, expsum_fn, rows_fn, scale_fn, allreduce_max, allreduce_sum):
+    """WeightedChain normalisation (weightedchain.jl:59-67) on row shards.  The local phases are callables:
+      colstats_fn() -> stats (M+2): column maxima of LL, max log-prior, count total (local)
+      expsum_fn(stats) -> colsum (M): L = exp(LL - colmax) in place, local column sums
+      rows_fn(stats)  -> total (1):  stats = [colsum | lpmax | sumcounts]; local weights, unnormalised density, its total
+      scale_fn(total):               density /= total
+    Collectives: one max (M+1 values), two sums (1 and M values), one sum (1 value) — each once."""
+    stats = colstats_fn()
+    M = stats.shape[0] - 2
+    allreduce_max(stats[:M + 1])
+    allreduce_sum(stats[M + 1:])
+    colsum = expsum_fn(stats)
+    allreduce_sum(colsum)
+    stats[:M] = colsum
+    total = rows_fn(stats)
+    allreduce_sum(total)
+    scale_fn(total)
+    return stats
+
+
+class DeviceWC:
+    """Row shard of (LL, logprior, counts) on this rank's GPU for wc_normalize_sharded; kernels through the C ABI."""
+
+    def __init__(self, LL_local_colmajor, logprior_local, counts_local):
+        import torch
+        from . import lib as _L
+        self.torch, self._L, self.lib = torch, _L, _L.load()
+        self.LL, self.lp, self.cn = LL_local_colmajor, logprior_local, counts_local    # (M, K_local) row-major == K_local x M col-major
+        self.M, self.K = self.LL.shape
+        dev = self.LL.device
+        self.stats = torch.empty(self.M + 2, dtype=torch.float64, device=dev)
+        self.colsum = torch.empty(self.M, dtype=torch.float64, device=dev)
+        self.total = torch.empty(1, dtype=torch.float64, device=dev)
+        self.weights = torch.empty(self.K, dtype=torch.float64, device=dev)
+        self.density = torch.empty(self.K, dtype=torch.float64, device=dev)
+
+    def _s(self):
+        return self.torch.cuda.current_stream().cuda_stream
+
+    def colstats(self):
+        self._L.check(self.lib.gync_wc_colstats_dev(self.LL.data_ptr(), self.lp.data_ptr(), self.cn.data_ptr(), self.K, self.M,
+                                                    self.stats.data_ptr(), self._s()))
+        return self.stats
+
+    def expsum(self, stats):
+        self._L.check(self.lib.gync_wc_expsum_dev(self.LL.data_ptr(), self.K, self.M, stats.data_ptr(), self.colsum.data_ptr(), self._s()))
+        return self.colsum
+
+    def rows(self, stats):
+        self._L.check(self.lib.gync_wc_rows_dev(self.LL.data_ptr(), self.lp.data_ptr(), self.cn.data_ptr(), self.K, self.M,
+                                                stats.data_ptr(), self.weights.data_ptr(), self.density.data_ptr(),
+                                                self.total.data_ptr(), self._s()))
+        return self.total
+
+    def scale(self, total):
+        self._L.check(self.lib.gync_wc_scale_dev(self.density.data_ptr(), self.K, total.data_ptr(), self._s()))
+
+    def normalize(self, allreduce_max=None, allreduce_sum=None):
+        """LL -> L in place; returns (weights, density) of the local rows."""
+        if allreduce_max is None:
+            import torch.distributed as dist
+            allreduce_max = lambda x: dist.all_reduce(x, op=dist.ReduceOp.MAX)
+            allreduce_sum = lambda x: dist.all_reduce(x)
+        wc_normalize_sharded(self.colstats, self.expsum, self.rows, self.scale, allreduce_max, allreduce_sum)
+        return self.weights, self.density
+
+
 class DeviceEM:
     """Row shard of (w, L) resident on this rank's GPU; kernels through the C ABI (device pointers)."""
 

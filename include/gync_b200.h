@@ -212,6 +212,17 @@ int  gync_ebmodel_mple(gync_ebmodel* m, double* w, double reg, double h, int32_t
 /* `reps` gradient evaluations on device weights, no host traffic (bench hook): which = 1 dhz, 2 dlogl, 3 both */
 int  gync_ebmodel_grad_dev(gync_ebmodel* m, const double* dw, int32_t which, int32_t reps, void* stream);
 
+/* Row-sharded form (one process per GPU): each rank holds K_local rows; the caller's collectives sit
+ * between the phases:  colstats -> allreduce(max) of d_stats[0..M] (column maxima, max log-prior) and allreduce(sum) of
+ * d_stats[M+1] (count total) -> expsum(d_colmax = d_stats) -> allreduce(sum) of the M column sums -> rows (d_stats =
+ * [colsum(M) | lpmax | sumcounts]) -> allreduce(sum) of d_total -> scale. */
+int gync_wc_colstats_dev(const double* dLL, const double* d_logprior, const int64_t* d_counts, int64_t K, int32_t M,
+                         double* d_stats /* M + 2 */, void* stream);
+int gync_wc_expsum_dev(double* dLL_inout, int64_t K, int32_t M, const double* d_colmax, double* d_colsum, void* stream);
+int gync_wc_rows_dev(double* dL_inout, const double* d_logprior, const int64_t* d_counts, int64_t K, int32_t M,
+                     const double* d_stats, double* d_weights, double* d_density, double* d_total, void* stream);
+int gync_wc_scale_dev(double* d_density, int64_t K, const double* d_total, void* stream);
+
 /* FP64 flops of one RODAS4 step attempt (counted from the generated code; roofline bookkeeping). */
 double gync_flops_per_step(void);
 /* FP64 FMA peak microbenchmark (TFLOP/s) used as the solver's roofline denominator. */

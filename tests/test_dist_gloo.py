@@ -57,3 +57,54 @@ def test_sharded_em_gloo_world2(tmp_path):
                        capture_output=True, text=True, env=env, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("ok") == 2
+
+
+WORKER_WC = r'''
+import os, sys
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "oracle"))
+from gync_b200.dist import shard_bounds, wc_normalize_sharded
+import gync_oracle as o
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+rng = np.random.default_rng(12)
+K, M = 501, 5
+LL = -50.0 * rng.random((K, M)); lp = -3.0 * rng.random(K); cn = rng.integers(1, 9, K)
+lo, hi = shard_bounds(K, world, rank)
+Ll, lpl, cnl = LL[lo:hi].copy(), lp[lo:hi], cn[lo:hi]
+w = np.empty(hi - lo); d = np.empty(hi - lo)
+def colstats():
+    return torch.from_numpy(np.concatenate([Ll.max(0), [lpl.max()], [float(cnl.sum())]]))
+def expsum(st):
+    Ll[:] = np.exp(Ll - st.numpy()[None, :M])
+    return torch.from_numpy(Ll.sum(0))
+def rows(st):
+    s = st.numpy()
+    Ll[:] = Ll / s[None, :M]
+    d[:] = Ll.mean(1) * np.exp(lpl - s[M]); w[:] = cnl / s[M + 1]
+    return torch.tensor([d.sum()])
+def scale(t):
+    d[:] = d / t.item()
+ncoll = [0]
+def amax(x): ncoll[0] += 1; dist.all_reduce(x, op=dist.ReduceOp.MAX)
+def asum(x): ncoll[0] += 1; dist.all_reduce(x)
+wc_normalize_sharded(colstats, expsum, rows, scale, amax, asum)
+assert ncoll[0] == 4
+Lr, wr, dr = o.weightedchain_normalize(lp, LL, cn)
+assert np.allclose(Ll, Lr[lo:hi], rtol=1e-13) and np.allclose(w, wr[lo:hi], rtol=1e-13) and np.allclose(d, dr[lo:hi], rtol=1e-12)
+print("rank", rank, "ok")
+dist.destroy_process_group()
+'''
+
+
+def test_sharded_wc_normalize_gloo_world2(tmp_path):
+    """SURVEY §8e row K5: row-sharded WeightedChain normalisation — allreduce(max), allreduce(sum) — equals the unsharded oracle."""
+    script = tmp_path / "worker_wc.py"
+    script.write_text(WORKER_WC.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29563", str(script)],
+                       capture_output=True, text=True, env=env, timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ok") == 2

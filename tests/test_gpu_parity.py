@@ -508,3 +508,49 @@ def test_wc_normalize_vs_oracle(gpu):
         nz = l0 > 0
         assert np.array_equal(Lm == 0, l0 == 0) and relerr(Lm[nz], l0[nz]) < 1e-12
         assert relerr(w, w0) < 1e-14 and relerr(d, d0) < 1e-12
+
+
+def test_wc_normalize_sharded_kernels(gpu):
+    """SURVEY §8e row K5 on one GPU: two row shards driven through dist.wc_normalize_sharded with the collectives
+    emulated by combining the shards' buffers; equals the unsharded oracle."""
+    import torch
+    import gync_oracle as o
+    from gync_b200.dist import DeviceWC
+    rng = np.random.default_rng(19)
+    K, M = 20011, 40
+    LL = -rng.random((K, M)) * 600
+    LL[rng.integers(K), rng.integers(M)] = -np.inf
+    lp = -rng.random(K) * 50
+    counts = rng.integers(1, 9, K).astype(np.int64)
+    dev = torch.device("cuda", 0)
+    cut = 7003
+    shards = []
+    for lo, hi in ((0, cut), (cut, K)):
+        shards.append(DeviceWC(torch.from_numpy(np.ascontiguousarray(LL[lo:hi].T)).to(dev),
+                               torch.from_numpy(lp[lo:hi].copy()).to(dev), torch.from_numpy(counts[lo:hi].copy()).to(dev)))
+    # lock-step emulation of the four collectives
+    st = [s.colstats() for s in shards]
+    torch.cuda.synchronize()
+    g = torch.maximum(st[0][:M + 1], st[1][:M + 1])
+    tot = st[0][M + 1:] + st[1][M + 1:]
+    for x in st:
+        x[:M + 1] = g
+        x[M + 1:] = tot
+    cs = [s.expsum(x) for s, x in zip(shards, st)]
+    torch.cuda.synchronize()
+    gs = cs[0] + cs[1]
+    for x in st:
+        x[:M] = gs
+    tt = [s.rows(x) for s, x in zip(shards, st)]
+    torch.cuda.synchronize()
+    gt = tt[0] + tt[1]
+    for s in shards:
+        s.scale(gt)
+    torch.cuda.synchronize()
+    l0, w0, d0 = o.weightedchain_normalize(lp, LL, counts)
+    Lg = np.vstack([s.LL.cpu().numpy().T for s in shards])
+    wg = np.concatenate([s.weights.cpu().numpy() for s in shards])
+    dg = np.concatenate([s.density.cpu().numpy() for s in shards])
+    nz = l0 > 0
+    assert np.array_equal(Lg == 0, l0 == 0) and relerr(Lg[nz], l0[nz]) < 1e-12
+    assert relerr(wg, w0) < 1e-14 and relerr(dg, d0) < 1e-12
