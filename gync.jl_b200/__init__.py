@@ -4,6 +4,7 @@ Host-side mirror of the reference's Julia API for this path (api.py) over the C-
 (csrc/, include/gync_b200.h).  Import as `gync_b200` (the directory name is not a Python identifier).
 """
 from . import lib  # noqa: F401
+from . import eb  # noqa: F401
 from .api import *  # noqa: F401,F403
 from .api import (DEFAULT_ATOL, DEFAULT_RTOL, Config, Lausanne, Patient, Pfizer, Sampling, WeightedChain,  # noqa: F401
                   emiteration, emiteration_bang, emiterations, forwardsol, gync, llh, loglik_matrix, logprior,
