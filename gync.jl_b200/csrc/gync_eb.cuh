@@ -33,37 +33,56 @@ struct GyncLmSmem {
   double red[2][GYNC_LM_THREADS / 32];
 };
 
-// element (k, col) of a matrix given by two strides; NaN-split and scaled while staging
-__device__ __forceinline__ void gync_lm_stage(const double* __restrict__ X, int64_t n, int64_t s_k, int64_t s_c, int64_t c0,
-                                              int k0, int D, const double* __restrict__ sigmas, double (*v)[GYNC_LM_TP],
-                                              double (*m)[GYNC_LM_TP], int& any_missing) {
-  const int tid = threadIdx.x;
-  // thread -> (k, col): the faster index follows the smaller stride so that the loads coalesce
-  for (int e = tid; e < GYNC_LM_KC * GYNC_LM_T; e += GYNC_LM_THREADS) {
+// Staging of one k-chunk of a tile in two halves so that the global loads of chunk c+1 are in flight while chunk c is
+// being multiplied: fetch (global -> registers, raw values, NaN kept) and put (registers -> shared memory: scaled by
+// 1/sigma_k, NaN -> value 0 / mask 0).  Element e of the tile maps to (k, col) with the faster index along the smaller
+// stride so that the loads coalesce; both halves use the same mapping.
+#define GYNC_LM_EPT (GYNC_LM_KC * GYNC_LM_T / GYNC_LM_THREADS)      /* 8 elements per thread and tile */
+#define GYNC_LM_MAXD 512                                             /* 1/sigma table in shared memory */
+
+__device__ __forceinline__ void gync_lm_map(int e, bool kfast, int& kk, int& cc) {
+  if (kfast) { kk = e % GYNC_LM_KC; cc = e / GYNC_LM_KC; }
+  else       { cc = e % GYNC_LM_T;  kk = e / GYNC_LM_T; }
+}
+
+__device__ __forceinline__ void gync_lm_fetch(const double* __restrict__ X, int64_t n, int64_t s_k, int64_t s_c, int64_t c0,
+                                              int k0, int D, double (&r)[GYNC_LM_EPT]) {
+#pragma unroll
+  for (int q = 0; q < GYNC_LM_EPT; ++q) {
     int kk, cc;
-    if (s_k == 1) { kk = e % GYNC_LM_KC; cc = e / GYNC_LM_KC; }
-    else          { cc = e % GYNC_LM_T;  kk = e / GYNC_LM_T; }
+    gync_lm_map(threadIdx.x + q * GYNC_LM_THREADS, s_k == 1, kk, cc);
     const int k = k0 + kk;
     const int64_t col = c0 + cc;
-    double val = 0.0, msk = 0.0;
-    if (k < D && col < n) {
-      const double x = X[k * s_k + col * s_c];
-      if (x == x) { val = x / sigmas[k]; msk = 1.0; }     // likelihoodmat.jl:35-36
-      else any_missing = 1;
-    }
-    // padding (rows past D, columns past n) is staged as observed zeros: it must not force the slow path
-    v[kk][cc] = val;
-    m[kk][cc] = (k < D && col < n) ? msk : 1.0;
+    r[q] = (k < D && col < n) ? __ldg(X + k * s_k + col * s_c) : 0.0;      // padding: observed zeros (never force the slow path)
   }
 }
 
-__global__ void __launch_bounds__(GYNC_LM_THREADS)
+__device__ __forceinline__ void gync_lm_put(const double (&r)[GYNC_LM_EPT], bool kfast, int k0, int D, const double* isig,
+                                            const double* __restrict__ sigmas, double (*v)[GYNC_LM_TP], double (*m)[GYNC_LM_TP],
+                                            int& any_missing) {
+#pragma unroll
+  for (int q = 0; q < GYNC_LM_EPT; ++q) {
+    int kk, cc;
+    gync_lm_map(threadIdx.x + q * GYNC_LM_THREADS, kfast, kk, cc);
+    const int k = min(k0 + kk, D - 1);
+    const double x = r[q];
+    const bool obs = (x == x);
+    if (!obs) any_missing = 1;
+    // likelihoodmat.jl:35-36 divides by sigma; the table holds 1/sigma (one rounding apart); D > table: divide
+    const double sc = (D <= GYNC_LM_MAXD) ? x * isig[k] : x / sigmas[k];
+    v[kk][cc] = obs ? sc : 0.0;
+    m[kk][cc] = obs ? 1.0 : 0.0;
+  }
+}
+
+__global__ void __launch_bounds__(GYNC_LM_THREADS, 2)
 gync_lmat_kernel(const double* __restrict__ A, int64_t I, int64_t sa_k, int64_t sa_i,
                  const double* __restrict__ B, int64_t J, int64_t sb_k, int64_t sb_j, int D,
                  const double* __restrict__ sigmas, int renormalize, double* __restrict__ L,
                  double* __restrict__ blk_min, double* __restrict__ blk_max) {
   extern __shared__ __align__(16) unsigned char gync_lm_raw[];
   GyncLmSmem& sm = *reinterpret_cast<GyncLmSmem*>(gync_lm_raw);
+  __shared__ double isig[GYNC_LM_MAXD];
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const int64_t i0 = (int64_t)blockIdx.x * GYNC_LM_T, j0 = (int64_t)blockIdx.y * GYNC_LM_T;
@@ -73,20 +92,29 @@ gync_lmat_kernel(const double* __restrict__ A, int64_t I, int64_t sa_k, int64_t 
 #pragma unroll
     for (int v = 0; v < 4; ++v) { sq[u][v] = 0.0; g[u][v] = 0.0; }
   double gfast = 0.0;
+  if (D <= GYNC_LM_MAXD)
+    for (int k = tid; k < D; k += GYNC_LM_THREADS) isig[k] = 1.0 / sigmas[k];
+  double ra[GYNC_LM_EPT], rb[GYNC_LM_EPT];
+  gync_lm_fetch(A, I, sa_k, sa_i, i0, 0, D, ra);
+  gync_lm_fetch(B, J, sb_k, sb_j, j0, 0, D, rb);
+  __syncthreads();
 
   for (int k0 = 0; k0 < D; k0 += GYNC_LM_KC) {
     int miss = 0;
-    gync_lm_stage(A, I, sa_k, sa_i, i0, k0, D, sigmas, sm.a, sm.am, miss);
-    gync_lm_stage(B, J, sb_k, sb_j, j0, k0, D, sigmas, sm.b, sm.bm, miss);
+    gync_lm_put(ra, sa_k == 1, k0, D, isig, sigmas, sm.a, sm.am, miss);
+    gync_lm_put(rb, sb_k == 1, k0, D, isig, sigmas, sm.b, sm.bm, miss);
     if (tid < GYNC_LM_KC) sm.c[tid] = (k0 + tid < D) ? log(sigmas[k0 + tid]) + 1.8378770664093453 : 0.0;
     const int slow = __syncthreads_or(miss);
+    if (k0 + GYNC_LM_KC < D) {                     // next chunk's loads fly while this one is multiplied
+      gync_lm_fetch(A, I, sa_k, sa_i, i0, k0 + GYNC_LM_KC, D, ra);
+      gync_lm_fetch(B, J, sb_k, sb_j, j0, k0 + GYNC_LM_KC, D, rb);
+    }
     const int kn = min(GYNC_LM_KC, D - k0);
     if (!slow) {
       for (int kk = 0; kk < kn; ++kk) {
         double a[4], b[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) { a[u] = sm.a[kk][tx + 16 * u]; b[u] = sm.b[kk][ty + 16 * u]; }
-        const double c = sm.c[kk];
 #pragma unroll
         for (int u = 0; u < 4; ++u)
 #pragma unroll
@@ -94,7 +122,7 @@ gync_lmat_kernel(const double* __restrict__ A, int64_t I, int64_t sa_k, int64_t 
             const double d = a[u] - b[v];
             sq[u][v] = fma(d, d, sq[u][v]);
           }
-        gfast += c;                      // every pair of the tile observes entry k: one scalar instead of 16 adds
+        gfast += sm.c[kk];               // every pair of the tile observes entry k: one scalar instead of 16 adds
       }
     } else {
       for (int kk = 0; kk < kn; ++kk) {
