@@ -5,8 +5,16 @@
 
 namespace {
 
+void lmat_finish(double* dL, int64_t n, const double* d_scal, cudaStream_t s) {
+  const unsigned nb = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)g_num_sms * 16);
+  gync_lmat_exp_kernel<<<nb, 256, 0, s>>>(dL, n, d_scal);
+  g_launches += 1;
+}
+
+// d_scal_out != NULL: stop after the (min sq, max g) reduction — the matrix then holds the logs of the unnormalised
+// entries and the caller finishes it with lmat_finish once the scalars are global (row-sharded builds).
 int lmat_launch(const double* dA, int64_t I, int64_t sa_k, int64_t sa_i, const double* dB, int64_t J, int64_t sb_k,
-                int64_t sb_j, int D, const double* d_sig, int renorm, double* dL, cudaStream_t s) {
+                int64_t sb_j, int D, const double* d_sig, int renorm, double* dL, cudaStream_t s, double* d_scal_out = nullptr) {
   if (I == 0 || J == 0) return GYNC_OK;
   const int64_t gx = (I + GYNC_LM_T - 1) / GYNC_LM_T, gy = (J + GYNC_LM_T - 1) / GYNC_LM_T;
   if (gy > 65535) return fail(GYNC_ERR_ARG, "likelihoodmat: more than 4.19 M columns");
@@ -21,11 +29,9 @@ int lmat_launch(const double* dA, int64_t I, int64_t sa_k, int64_t sa_i, const d
       dA, I, sa_k, sa_i, dB, J, sb_k, sb_j, D, d_sig, renorm, dL, bmin, bmax);
   g_launches += 1;
   if (renorm) {
-    gync_lmat_minmax_kernel<<<1, 1024, 0, s>>>(bmin, bmax, nblk, scal);
-    const int64_t n = I * J;
-    const unsigned nb = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)g_num_sms * 16);
-    gync_lmat_exp_kernel<<<nb, 256, 0, s>>>(dL, n, scal);
-    g_launches += 2;
+    gync_lmat_minmax_kernel<<<1, 1024, 0, s>>>(bmin, bmax, nblk, d_scal_out ? d_scal_out : scal);
+    g_launches += 1;
+    if (!d_scal_out) lmat_finish(dL, I * J, scal, s);
   }
   CK(cudaGetLastError());
   return GYNC_OK;
@@ -64,8 +70,10 @@ int mv_t_launch(const double* A, int64_t R, int64_t C, const double* x, double* 
 }
 
 int mv_finish(const double* part, int nparts, int64_t n, int epi, double* out, double* out2, const double* rho, int zmult,
-              int* nan_flag, cudaStream_t s) {
-  gync_mv_finish_kernel<<<blocks_for(n, 256 / GYNC_FIN_SLICES), 256, 0, s>>>(part, nparts, n, epi, out, out2, rho, zmult, nan_flag);
+              int* nan_flag, cudaStream_t s, int64_t z_off = 0, int64_t z_len = -1) {
+  if (z_len < 0) z_len = n * (int64_t)std::max(zmult, 1);
+  gync_mv_finish_kernel<<<blocks_for(n, 256 / GYNC_FIN_SLICES), 256, 0, s>>>(part, nparts, n, epi, out, out2, rho, zmult, nan_flag,
+                                                                              z_off, z_len);
   g_launches += 1;
   CK(cudaGetLastError());
   return GYNC_OK;
@@ -85,7 +93,8 @@ size_t mv_part_doubles(int64_t R, int64_t C) {
 //        column-major: every z-row contiguous) so that dhz can run in one pass over HBM (gync_dhz_fused_kernel)
 struct gync_ebmodel {
   int device = -1;
-  int64_t K = 0, M = 0, Z = 0;
+  int64_t K = 0, M = 0, Z = 0;     // Z: rows of the z-matrix held HERE
+  int64_t z_off = 0;               // z-sharded model: this device holds rows [z_off, z_off + Z) of Z_total = zmult K
   int zmult = 0;
   double *Ld = nullptr, *Lzt = nullptr;
   double *part = nullptr, *rho = nullptr, *fac = nullptr, *norms = nullptr, *rnorm = nullptr;
@@ -178,19 +187,19 @@ int eb_dhz(gync_ebmodel* m, const double* dw, int cont, double* out, cudaStream_
   if (eb_dhz_fusable(m, &smem)) {
     const int nb = (int)std::min<int64_t>(g_num_sms, (m->Z + GYNC_DHZ_ROWS - 1) / GYNC_DHZ_ROWS);
     CK(cudaFuncSetAttribute(gync_dhz_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gync_dhz_fused_kernel<<<nb, GYNC_DHZ_THREADS, smem, s>>>(m->Lzt, m->K, m->Z, dw, m->zmult, cont, m->rho, m->part);
+    gync_dhz_fused_kernel<<<nb, GYNC_DHZ_THREADS, smem, s>>>(m->Lzt, m->K, m->Z, m->z_off, dw, m->zmult, cont, m->rho, m->part);
     g_launches += 1;
     CK(cudaGetLastError());
     return mv_finish(m->part, nb, m->K, cont ? GYNC_EPI_DHZ_CONT : GYNC_EPI_DHZ_DISCR, out, nullptr, m->rho, m->zmult,
-                     m->flags + 1, s);
+                     m->flags + 1, s, m->z_off, m->Z);
   }
   if (int rc = eb_rho(m, dw, s)) return rc;
-  gync_dhz_factors_kernel<<<blocks_for(m->Z, 256), 256, 0, s>>>(dw, m->K, m->zmult, m->rho, m->Z, cont, m->fac);
+  gync_dhz_factors_kernel<<<blocks_for(m->Z, 256), 256, 0, s>>>(dw, m->K, m->zmult, m->rho, m->Z, m->z_off, cont, m->fac);
   g_launches += 1;
   int np = 0;
   if (int rc = mv_n_launch(m->Lzt, m->K, m->Z, m->fac, m->part, &np, s)) return rc;
   return mv_finish(m->part, np, m->K, cont ? GYNC_EPI_DHZ_CONT : GYNC_EPI_DHZ_DISCR, out, nullptr, m->rho, m->zmult,
-                   m->flags + 1, s);
+                   m->flags + 1, s, m->z_off, m->Z);
 }
 
 // one projected step on the device weights (in place); ga/gb may be NULL (pure projection)
@@ -325,13 +334,15 @@ int gync_projectsimplex(double* yv, int64_t K) {
 // ---- LikelihoodModel ---------------------------------------------------------------------------
 void gync_ebmodel_destroy(gync_ebmodel* m) { ebmodel_free(m); }
 
-int gync_ebmodel_create(const double* ys, int64_t K, const double* datas, int64_t M, const double* zs, int64_t Z,
-                        int32_t D, const double* sig_meas, const double* sig_z, gync_ebmodel** out) {
-  if (K < 1 || M < 0 || Z < 0 || D < 1 || !ys || !sig_meas || !out || (M > 0 && !datas) || (Z > 0 && !zs) || (Z % K) != 0)
+static int ebmodel_create_impl(const double* ys, int64_t K, const double* datas, int64_t M, const double* zs, int64_t Z,
+                               int64_t z_off, int64_t Z_total, int32_t D, const double* sig_meas, const double* sig_z,
+                               double* scal_out, gync_ebmodel** out) {
+  if (K < 1 || M < 0 || Z < 0 || D < 1 || !ys || !sig_meas || !out || (M > 0 && !datas) || (Z > 0 && !zs) || (Z_total % K) != 0 ||
+      z_off < 0 || z_off + Z > Z_total)
     return fail(GYNC_ERR_ARG, "gync_ebmodel_create: bad arguments (length(zs) must be a multiple of length(ys))");
   if (int rc = ensure_init()) return rc;
   gync_ebmodel* m = new gync_ebmodel();
-  m->K = K; m->M = M; m->Z = Z; m->zmult = (int)(Z / K);
+  m->K = K; m->M = M; m->Z = Z; m->z_off = z_off; m->zmult = (int)(Z_total / K);
   int rc = ebmodel_alloc(m);
   DBuf dY, dB, dS;
   auto up = [&](DBuf& b, const double* h, size_t n) -> int {
@@ -351,12 +362,38 @@ int gync_ebmodel_create(const double* ys, int64_t K, const double* datas, int64_
     if (!rc && sig_z) rc = up(dSz, sig_z, (size_t)D);
     // likelihoodmat(zs, ys)' == likelihoodmat(ys, zs): built directly in the transposed layout
     if (!rc) rc = lmat_launch(dY.as<double>(), K, 1, D, dZ.as<double>(), Z, 1, D, D, sig_z ? dSz.as<double>() : dS.as<double>(),
-                              1, m->Lzt, g_stream);
+                              1, m->Lzt, g_stream, scal_out ? m->scal + 2 : nullptr);
+    if (!rc && scal_out && cudaMemcpyAsync(scal_out, m->scal + 2, 2 * sizeof(double), cudaMemcpyDeviceToHost, g_stream) != cudaSuccess)
+      rc = fail(GYNC_ERR_CUDA, "gync_ebmodel_create: copy of the renormalisation scalars failed");
     if (!rc && cudaStreamSynchronize(g_stream) != cudaSuccess) rc = fail(GYNC_ERR_CUDA, "gync_ebmodel_create: kernel failed");
   }
   if (!rc && cudaStreamSynchronize(g_stream) != cudaSuccess) rc = fail(GYNC_ERR_CUDA, "gync_ebmodel_create: kernel failed");
   if (rc) { ebmodel_free(m); return rc; }
   *out = m;
+  return GYNC_OK;
+}
+
+int gync_ebmodel_create(const double* ys, int64_t K, const double* datas, int64_t M, const double* zs, int64_t Z,
+                        int32_t D, const double* sig_meas, const double* sig_z, gync_ebmodel** out) {
+  return ebmodel_create_impl(ys, K, datas, M, zs, Z, 0, Z, D, sig_meas, sig_z, nullptr, out);
+}
+
+// z-sharded LikelihoodModel (one process per GPU): this device holds rows [z_off, z_off + Z_local) of the z-matrix, the
+// (small) data matrix is replicated.  The renormalisation of likelihoodmat.jl:53-54 is global, so the build stops after the
+// local (min sq, max g) — scal_out — and gync_ebmodel_zshard_finish takes the values combined over ranks (min, max).
+int gync_ebmodel_create_zshard(const double* ys, int64_t K, const double* datas, int64_t M, const double* zs_local,
+                               int64_t Z_local, int64_t z_off, int64_t Z_total, int32_t D, const double* sig_meas,
+                               const double* sig_z, double* scal_out /* 2 */, gync_ebmodel** out) {
+  if (!scal_out || Z_local < 1) return fail(GYNC_ERR_ARG, "gync_ebmodel_create_zshard: bad arguments");
+  return ebmodel_create_impl(ys, K, datas, M, zs_local, Z_local, z_off, Z_total, D, sig_meas, sig_z, scal_out, out);
+}
+
+int gync_ebmodel_zshard_finish(gync_ebmodel* m, const double* scal /* 2: global min sq, global max g */) {
+  if (int rc = eb_check_model(m, scal, "gync_ebmodel_zshard_finish")) return rc;
+  CK(cudaMemcpyAsync(m->scal + 2, scal, 2 * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+  lmat_finish(m->Lzt, m->Z * m->K, m->scal + 2, g_stream);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(g_stream));
   return GYNC_OK;
 }
 
@@ -419,7 +456,7 @@ int gync_ebmodel_logl(gync_ebmodel* m, const double* w, double* out) {
   if (!out || m->M < 1) return fail(GYNC_ERR_ARG, "gync_ebmodel_logl: no data matrix / NULL output");
   CK(cudaMemcpyAsync(m->w, w, sizeof(double) * m->K, cudaMemcpyHostToDevice, g_stream));
   if (int rc = eb_norms(m, m->w, g_stream)) return rc;
-  gync_logsum_kernel<<<1, 1024, 0, g_stream>>>(m->norms, m->M, nullptr, 1, 1.0, 1.0, 0, m->scal);
+  gync_logsum_kernel<<<1, 1024, 0, g_stream>>>(m->norms, m->M, nullptr, 1, 0, 1.0, 1.0, 0, m->scal);
   g_launches += 1;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, m->scal, sizeof(double), cudaMemcpyDeviceToHost, g_stream));
@@ -445,9 +482,9 @@ int gync_ebmodel_hz(gync_ebmodel* m, const double* w, const double* wz, double* 
   if (int rc = eb_rho(m, m->w, g_stream)) return rc;
   if (wz) {
     CK(cudaMemcpyAsync(m->fac, wz, sizeof(double) * m->Z, cudaMemcpyHostToDevice, g_stream));
-    gync_logsum_kernel<<<1, 1024, 0, g_stream>>>(m->rho, m->Z, m->fac, m->Z, 1.0, -1.0, 1, m->scal);
+    gync_logsum_kernel<<<1, 1024, 0, g_stream>>>(m->rho, m->Z, m->fac, m->Z, 0, 1.0, -1.0, 1, m->scal);
   } else {
-    gync_logsum_kernel<<<1, 1024, 0, g_stream>>>(m->rho, m->Z, m->w, m->K, (double)m->zmult, -1.0, 1, m->scal);
+    gync_logsum_kernel<<<1, 1024, 0, g_stream>>>(m->rho, m->Z, m->w, m->K, m->z_off, (double)m->zmult, -1.0, 1, m->scal);
   }
   g_launches += 1;
   CK(cudaGetLastError());
@@ -516,15 +553,47 @@ int gync_ebmodel_mple(gync_ebmodel* m, double* w, double reg, double h, int32_t 
   return GYNC_OK;
 }
 
-// timing hook for bench.py: `reps` gradient evaluations (dhz + dlogl) on the resident matrices, no host traffic
-int gync_ebmodel_grad_dev(gync_ebmodel* m, const double* dw, int32_t which /*1 dhz, 2 dlogl, 3 both*/, int32_t reps, void* stream) {
-  if (int rc = eb_check_model(m, dw, "gync_ebmodel_grad_dev")) return rc;
+// ---- device-level entry points (device pointers, caller's stream, no synchronisation): what a host that keeps the
+// weights on the GPU calls — bench.py, and the z-sharded loop of dist.ShardedEB where the results of dhz / hz are PARTIAL
+// sums over this device's z-rows, to be allreduce(sum)-ed by the caller.
+int gync_ebmodel_dhz_dev(gync_ebmodel* m, const double* dw, int32_t cont, double* d_out, void* stream) {
+  if (int rc = eb_check_model(m, dw, "gync_ebmodel_dhz_dev")) return rc;
+  if (!d_out || m->Z < 1) return fail(GYNC_ERR_ARG, "gync_ebmodel_dhz_dev: no z matrix / NULL output");
+  return eb_dhz(m, dw, cont, d_out, (cudaStream_t)stream);
+}
+
+int gync_ebmodel_dlogl_dev(gync_ebmodel* m, const double* dw, double* d_out, void* stream) {
+  if (int rc = eb_check_model(m, dw, "gync_ebmodel_dlogl_dev")) return rc;
+  if (!d_out || m->M < 1) return fail(GYNC_ERR_ARG, "gync_ebmodel_dlogl_dev: no data matrix / NULL output");
+  return eb_dlogl(m, dw, d_out, (cudaStream_t)stream);
+}
+
+int gync_ebmodel_hz_dev(gync_ebmodel* m, const double* dw, double* d_out /* 1 */, void* stream) {
+  if (int rc = eb_check_model(m, dw, "gync_ebmodel_hz_dev")) return rc;
+  if (!d_out || m->Z < 1) return fail(GYNC_ERR_ARG, "gync_ebmodel_hz_dev: no z matrix / NULL output");
   cudaStream_t s = (cudaStream_t)stream;
-  for (int r = 0; r < reps; ++r) {
-    if ((which & 1) && m->Z > 0) if (int rc = eb_dhz(m, dw, 0, m->ga, s)) return rc;
-    if ((which & 2) && m->M > 0) if (int rc = eb_dlogl(m, dw, m->gb, s)) return rc;
-  }
+  if (int rc = eb_rho(m, dw, s)) return rc;
+  gync_logsum_kernel<<<1, 1024, 0, s>>>(m->rho, m->Z, dw, m->K, m->z_off, (double)m->zmult, -1.0, 1, d_out);
+  g_launches += 1;
+  CK(cudaGetLastError());
   return GYNC_OK;
+}
+
+// one step  w <- movefromboundary(w, projectsimplex(w + h (ca ga + cb gb)))  on device vectors (gb / ga may be NULL)
+int gync_ebmodel_ascent_dev(gync_ebmodel* m, double* dw, const double* d_ga, double ca, const double* d_gb, double cb, double h,
+                            void* stream) {
+  if (int rc = eb_check_model(m, dw, "gync_ebmodel_ascent_dev")) return rc;
+  return eb_ascent_step(m, dw, d_ga, ca, d_gb, cb, h, 0.5, nullptr, (cudaStream_t)stream);
+}
+
+// 1 if a NaN appeared in a dhz evaluation since the last call (regularizers.jl:77); synchronises the stream
+int gync_ebmodel_nan_flag(gync_ebmodel* m, void* stream) {
+  if (!m) return -1;
+  int f = 0;
+  if (cudaMemcpyAsync(&f, m->flags + 1, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream) != cudaSuccess) return -2;
+  if (cudaMemsetAsync(m->flags + 1, 0, sizeof(int), (cudaStream_t)stream) != cudaSuccess) return -2;
+  if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) return -2;
+  return f;
 }
 
 }  // extern "C"

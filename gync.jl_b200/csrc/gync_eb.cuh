@@ -276,14 +276,15 @@ gync_gemv_t_kernel(const double* __restrict__ A, int64_t R, int64_t C, int64_t l
 enum GyncMvEpi {
   GYNC_EPI_PLAIN = 0,     // out = s
   GYNC_EPI_RECIP = 1,     // out = s, out2 = 1/s                                 (norms and 1/norms: dlogl, EM)
-  GYNC_EPI_DHZ_DISCR = 2, // out = -s - (1/zmult) sum_m log(rho[i + n m])          (regularizers.jl:70-75)
+  GYNC_EPI_DHZ_DISCR = 2, // out = -s - (1/zmult) sum_m log(rho[i + n m])          (regularizers.jl:70-75; local z only)
   GYNC_EPI_DHZ_CONT = 3,  // out = -1 - s                                          (regularizers.jl:149-160)
   GYNC_EPI_EM = 4         // out = out / M * s      (in place on w; em.jl:33-38)
 };
 #define GYNC_FIN_SLICES 4     /* threads per output element: slice s adds partials s, s+4, ..; slices are combined in order */
 __global__ void __launch_bounds__(256)
 gync_mv_finish_kernel(const double* __restrict__ part, int nparts, int64_t n, int epi, double* __restrict__ out,
-                      double* __restrict__ out2, const double* __restrict__ rho, int zmult, int* __restrict__ nan_flag) {
+                      double* __restrict__ out2, const double* __restrict__ rho, int zmult, int* __restrict__ nan_flag,
+                      int64_t z_off, int64_t z_len /* rho holds rows [z_off, z_off + z_len) of the z samples (a shard) */) {
   __shared__ double sl[GYNC_FIN_SLICES][256 / GYNC_FIN_SLICES];
   const int col = threadIdx.x % (256 / GYNC_FIN_SLICES), slice = threadIdx.x / (256 / GYNC_FIN_SLICES);
   const int64_t i = (int64_t)blockIdx.x * (256 / GYNC_FIN_SLICES) + col;
@@ -301,10 +302,13 @@ gync_mv_finish_kernel(const double* __restrict__ part, int nparts, int64_t n, in
     out2[i] = 1.0 / s;
   } else if (epi == GYNC_EPI_DHZ_DISCR) {
     r = -s;
-    for (int m = 0; m < zmult; ++m) r -= log(rho[i + n * m]) / (double)zmult;
+    for (int m = 0; m < zmult; ++m) {
+      const int64_t zl = i + n * m - z_off;
+      if (zl >= 0 && zl < z_len) r -= log(rho[zl]) / (double)zmult;
+    }
     if (r != r && nan_flag) atomicOr(nan_flag, 1);          // regularizers.jl:77
   } else if (epi == GYNC_EPI_DHZ_CONT) {
-    r = -1.0 - s;
+    r = ((z_off == 0) ? -1.0 : 0.0) - s;                    // the constant belongs to one shard only
     if (r != r && nan_flag) atomicOr(nan_flag, 1);
   } else if (epi == GYNC_EPI_EM) {
     r = out[i] / (double)zmult * s;                         // zmult carries M here
@@ -316,10 +320,10 @@ gync_mv_finish_kernel(const double* __restrict__ part, int nparts, int64_t n, in
 // with wz = repeatweights(w, zs) = repmat(w, zmult) / zmult   (regularizers.jl:16-19)
 __global__ void __launch_bounds__(256)
 gync_dhz_factors_kernel(const double* __restrict__ w, int64_t K, int zmult, const double* __restrict__ rho, int64_t Z,
-                        int cont, double* __restrict__ f) {
+                        int64_t z_off, int cont, double* __restrict__ f) {
   const int64_t z = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (z >= Z) return;
-  const double wz = w[z % K] / (double)zmult;
+  const double wz = w[(z + z_off) % K] / (double)zmult;
   const double r = rho[z];
   f[z] = cont ? wz * log(r) / r : wz / r;
 }
@@ -327,14 +331,14 @@ gync_dhz_factors_kernel(const double* __restrict__ w, int64_t K, int zmult, cons
 // out[0] = scale * sum_i log(v[i]) * wt_i     wt_i = wt ? wt[i % wmod] / wdiv : 1;  entries with v == 0 skipped when
 // skipzero (hz, regularizers.jl:40-43); logl (regularizers.jl:5) is the unweighted form.  One CTA, fixed order.
 __global__ void __launch_bounds__(1024)
-gync_logsum_kernel(const double* __restrict__ v, int64_t n, const double* __restrict__ wt, int64_t wmod, double wdiv,
-                   double scale, int skipzero, double* __restrict__ out) {
+gync_logsum_kernel(const double* __restrict__ v, int64_t n, const double* __restrict__ wt, int64_t wmod, int64_t ioff,
+                   double wdiv, double scale, int skipzero, double* __restrict__ out) {
   __shared__ double red[32];
   double acc = 0.0;
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
     const double r = v[i];
     if (skipzero && r == 0.0) continue;
-    acc += wt ? log(r) * (wt[i % wmod] / wdiv) : log(r);
+    acc += wt ? log(r) * (wt[(i + ioff) % wmod] / wdiv) : log(r);
   }
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -466,8 +470,8 @@ __global__ void __launch_bounds__(256) gync_pick_measured_kernel(const double* _
 #define GYNC_DHZ_ROWS 4
 
 __global__ void __launch_bounds__(GYNC_DHZ_THREADS, 1)
-gync_dhz_fused_kernel(const double* __restrict__ Lzt, int64_t K, int64_t Z, const double* __restrict__ w, int zmult, int cont,
-                      double* __restrict__ rho_out, double* __restrict__ part /* gridDim.x x K */) {
+gync_dhz_fused_kernel(const double* __restrict__ Lzt, int64_t K, int64_t Z, int64_t z_off, const double* __restrict__ w, int zmult,
+                      int cont, double* __restrict__ rho_out, double* __restrict__ part /* gridDim.x x K */) {
   extern __shared__ __align__(16) double gync_dhz_sm[];
   double* acc = gync_dhz_sm;            // K
   double* ws = gync_dhz_sm + K;         // K
@@ -518,7 +522,7 @@ gync_dhz_fused_kernel(const double* __restrict__ Lzt, int64_t K, int64_t Z, cons
       double f = 0.0;
       if (z < Z) {
         rho_out[z] = s;
-        const double wz = ws[z % K] / (double)zmult;
+        const double wz = ws[(z + z_off) % K] / (double)zmult;
         f = cont ? wz * log(s) / s : wz / s;
       }
       fz[tid] = f;

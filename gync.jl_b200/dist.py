@@ -1,6 +1,6 @@
 """Multi-GPU host logic: one process per GPU (torchrun), `torch.distributed` for the plumbing.
 
-What shards:
+What shards (plus the z-matrix of the §8f-3 regulariser):
   * likelihood batches / Metropolis chains — contiguous blocks of samples per rank, NO collective;
   * the EM update — rows of L and w are sharded, L never moves; the only exchange is ONE
     allreduce(sum) of the M per-patient denominators sum_k L[k,m] w[k] per iteration.
@@ -51,6 +51,100 @@ def wc_normalize_sharded(colstats_fn, expsum_fn, rows_fn, scale_fn, allreduce_ma
     allreduce_sum(total)
     scale_fn(total)
     return stats
+
+
+def mple_sharded(niter, reg, dhz_partial_fn, dlogl_fn, step_fn, allreduce_sum):
+    """Projected gradient ascent on reg*hz + (1-reg)*logl (likelihoodmodel.jl:33-64, gradientascent.jl:1-5) with the z-matrix
+    of hz row-sharded over the ranks (it is the memory hog: Z x K doubles) and everything else replicated:
+      dhz_partial_fn() -> this rank's partial dhz (K), summed over ranks by ONE allreduce per iteration;
+      dlogl_fn() -> dlogl (K, replicated: the K x M data matrix is small);  step_fn(ga, gb): the projected step, identical
+      on every rank because its inputs are.  The weights live inside the callables (device-resident)."""
+    for _ in range(niter):
+        ga = gb = None
+        if reg != 0:
+            ga = dhz_partial_fn()
+            allreduce_sum(ga)
+        if reg != 1:
+            gb = dlogl_fn()
+        step_fn(ga, gb)
+
+
+class ShardedEB:
+    """LikelihoodModel with the z-matrix row-sharded over the ranks (one process per GPU); kernels through the C ABI.
+    ys: D x K (all samples, replicated), datas: D x M, zs_local: this rank's columns [z_off, z_off + Z_local) of the D x Z_total
+    z samples.  `allreduce_min/max/sum` default to torch.distributed."""
+
+    def __init__(self, ys, datas, zs_local, z_off, Z_total, sig_meas, sig_z=None, device=None,
+                 allreduce_min=None, allreduce_max=None, allreduce_sum=None):
+        import numpy as np
+        import torch
+        from . import lib as _L
+        self.torch, self._L, self.lib, self.np = torch, _L, _L.load(), np
+        if allreduce_sum is None:
+            import torch.distributed as dist
+            allreduce_min = lambda x: dist.all_reduce(x, op=dist.ReduceOp.MIN)
+            allreduce_max = lambda x: dist.all_reduce(x, op=dist.ReduceOp.MAX)
+            allreduce_sum = lambda x: dist.all_reduce(x)
+        self.allreduce_sum = allreduce_sum
+        ys, datas, zs_local = _L.fcol(ys), _L.fcol(datas), _L.fcol(zs_local)
+        self.K, self.M = ys.shape[1], datas.shape[1]
+        sm = np.ascontiguousarray(sig_meas, dtype=np.float64)
+        sz = None if sig_z is None else np.ascontiguousarray(sig_z, dtype=np.float64)
+        scal = np.empty(2)
+        self.h = C.c_void_p()
+        _L.check(self.lib.gync_ebmodel_create_zshard(_L.dptr(ys), self.K, _L.dptr(datas), self.M, _L.dptr(zs_local), zs_local.shape[1],
+                                                     int(z_off), int(Z_total), ys.shape[0], _L.dptr(sm), _L.dptr(sz), _L.dptr(scal),
+                                                     C.byref(self.h)))
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        t = torch.from_numpy(scal).to(dev)
+        allreduce_min(t[0:1])                        # global min of the squared distances (likelihoodmat.jl:53)
+        allreduce_max(t[1:2])                        # global max of the normalisation (likelihoodmat.jl:54)
+        scal = np.ascontiguousarray(t.cpu().numpy())
+        _L.check(self.lib.gync_ebmodel_zshard_finish(self.h, _L.dptr(scal)))
+        self.w = torch.full((self.K,), 1.0 / self.K, dtype=torch.float64, device=dev)
+        self.ga, self.gb = torch.empty_like(self.w), torch.empty_like(self.w)
+        self.hzv = torch.empty(1, dtype=torch.float64, device=dev)
+
+    def _s(self):
+        return self.torch.cuda.current_stream().cuda_stream
+
+    def dhz_partial(self, cont=False):
+        self._L.check(self.lib.gync_ebmodel_dhz_dev(self.h, self.w.data_ptr(), 1 if cont else 0, self.ga.data_ptr(), self._s()))
+        return self.ga
+
+    def dhz(self, cont=False):
+        g = self.dhz_partial(cont)
+        self.allreduce_sum(g)
+        return g
+
+    def dlogl(self):
+        self._L.check(self.lib.gync_ebmodel_dlogl_dev(self.h, self.w.data_ptr(), self.gb.data_ptr(), self._s()))
+        return self.gb
+
+    def hz(self):
+        self._L.check(self.lib.gync_ebmodel_hz_dev(self.h, self.w.data_ptr(), self.hzv.data_ptr(), self._s()))
+        self.allreduce_sum(self.hzv)
+        return float(self.hzv.item())
+
+    def mple(self, reg, h, nsteps, ndata=None, autoh=True):
+        """nsteps projected steps on the resident weights (likelihoodmodel.jl:33-41); raises on NaN in dhz (:77)."""
+        if autoh:
+            h = h / ((1 - reg) * ((self.M if ndata is None else ndata) / (1 / 100)) + reg / (1 / 1000))
+        ca, cb = (1.0 if reg == 1 else reg), (1.0 if reg == 0 else 1.0 - reg)
+
+        def step(ga, gb):
+            self._L.check(self.lib.gync_ebmodel_ascent_dev(self.h, self.w.data_ptr(), None if ga is None else ga.data_ptr(), ca,
+                                                           None if gb is None else gb.data_ptr(), cb, float(h), self._s()))
+        mple_sharded(nsteps, reg, self.dhz_partial, self.dlogl, step, self.allreduce_sum)
+        if self.lib.gync_ebmodel_nan_flag(self.h, self._s()) == 1:
+            raise FloatingPointError("encountered NaN in dhz")
+        return self.w
+
+    def close(self):
+        if self.h:
+            self.torch.cuda.synchronize()
+            self.lib.gync_ebmodel_destroy(self.h)
+            self.h = None
 
 
 class DeviceWC:

@@ -51,7 +51,8 @@ EXPORTS = [
     "gync_likelihoodmat", "gync_likelihoodmat_dev", "gync_phi_batch", "gync_projectsimplex", "gync_ebmodel_create",
     "gync_ebmodel_from_matrices", "gync_ebmodel_destroy", "gync_ebmodel_dims", "gync_ebmodel_matrices",
     "gync_ebmodel_device_ptrs", "gync_ebmodel_logl", "gync_ebmodel_dlogl", "gync_ebmodel_hz", "gync_ebmodel_dhz",
-    "gync_ebmodel_em", "gync_ebmodel_mple", "gync_ebmodel_grad_dev",
+    "gync_ebmodel_em", "gync_ebmodel_mple", "gync_ebmodel_dhz_dev", "gync_ebmodel_dlogl_dev", "gync_ebmodel_hz_dev",
+    "gync_ebmodel_ascent_dev", "gync_ebmodel_nan_flag", "gync_ebmodel_create_zshard", "gync_ebmodel_zshard_finish",
 ]
 
 _lib = None
@@ -128,7 +129,15 @@ def load():
     lib.gync_ebmodel_dhz.argtypes = [C.c_void_p, c_double_p, C.c_int32, c_double_p]
     lib.gync_ebmodel_em.argtypes = [C.c_void_p, c_double_p, C.c_int32, c_double_p]
     lib.gync_ebmodel_mple.argtypes = [C.c_void_p, c_double_p, C.c_double, C.c_double, C.c_int32, C.c_int32, c_double_p]
-    lib.gync_ebmodel_grad_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    lib.gync_ebmodel_dhz_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.gync_ebmodel_dlogl_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.gync_ebmodel_hz_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.gync_ebmodel_ascent_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_double, C.c_double,
+                                            C.c_void_p]
+    lib.gync_ebmodel_nan_flag.argtypes = [C.c_void_p, C.c_void_p]
+    lib.gync_ebmodel_create_zshard.argtypes = [c_double_p, C.c_int64, c_double_p, C.c_int64, c_double_p, C.c_int64, C.c_int64,
+                                               C.c_int64, C.c_int32, c_double_p, c_double_p, c_double_p, C.POINTER(C.c_void_p)]
+    lib.gync_ebmodel_zshard_finish.argtypes = [C.c_void_p, c_double_p]
     _lib = lib
     return lib
 

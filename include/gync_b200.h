@@ -209,8 +209,22 @@ int  gync_ebmodel_em(gync_ebmodel* m, double* w, int32_t niter, double* history)
  *   w <- movefromboundary(w, projectsimplex(w + h (reg dhz(w) + (1-reg) dlogl(w)))), all on the device.
  * history (nullable): K x nsteps, column i = weights after step i+1. */
 int  gync_ebmodel_mple(gync_ebmodel* m, double* w, double reg, double h, int32_t nsteps, int32_t cont, double* history);
-/* `reps` gradient evaluations on device weights, no host traffic (bench hook): which = 1 dhz, 2 dlogl, 3 both */
-int  gync_ebmodel_grad_dev(gync_ebmodel* m, const double* dw, int32_t which, int32_t reps, void* stream);
+/* Device-level forms (device pointers, caller's stream, no synchronisation).  On a z-sharded model the results of
+ * dhz_dev / hz_dev are PARTIAL sums over this device's z-rows: allreduce(sum) them over the ranks. */
+int  gync_ebmodel_dhz_dev(gync_ebmodel* m, const double* dw, int32_t cont, double* d_out /* K */, void* stream);
+int  gync_ebmodel_dlogl_dev(gync_ebmodel* m, const double* dw, double* d_out /* K */, void* stream);
+int  gync_ebmodel_hz_dev(gync_ebmodel* m, const double* dw, double* d_out /* 1 */, void* stream);
+/* one step w <- movefromboundary(w, projectsimplex(w + h (ca ga + cb gb))) — gradientascent.jl:3,19-25 */
+int  gync_ebmodel_ascent_dev(gync_ebmodel* m, double* dw, const double* d_ga, double ca, const double* d_gb, double cb,
+                             double h, void* stream);
+int  gync_ebmodel_nan_flag(gync_ebmodel* m, void* stream);   /* 1 if a dhz held a NaN since the last call (regularizers.jl:77) */
+/* z-sharded LikelihoodModel (one process per GPU): this device holds rows [z_off, z_off + Z_local) of the Z_total x K
+ * z-matrix, the K x M data matrix is replicated.  The renormalisation (likelihoodmat.jl:53-54) is global: create returns
+ * the local (min sq, max g) in scal_out; combine them over the ranks (min, max) and call finish. */
+int  gync_ebmodel_create_zshard(const double* ys, int64_t K, const double* datas, int64_t M, const double* zs_local,
+                                int64_t Z_local, int64_t z_off, int64_t Z_total, int32_t D, const double* sig_meas,
+                                const double* sig_z, double* scal_out /* 2 */, gync_ebmodel** out);
+int  gync_ebmodel_zshard_finish(gync_ebmodel* m, const double* scal /* 2 */);
 
 /* Row-sharded form (one process per GPU): each rank holds K_local rows; the caller's collectives sit
  * between the phases:  colstats -> allreduce(max) of d_stats[0..M] (column maxima, max log-prior) and allreduce(sum) of

@@ -108,3 +108,59 @@ def test_sharded_wc_normalize_gloo_world2(tmp_path):
                        capture_output=True, text=True, env=env, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("ok") == 2
+
+
+WORKER_EB = r'''
+import os, sys
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "oracle"))
+from gync_b200.dist import shard_bounds, mple_sharded
+import eb_oracle as eo
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+rng = np.random.default_rng(13)
+K, M, zm, n = 60, 5, 2, 8
+Ld = rng.random((K, M)) + 0.05
+Lz = rng.random((K * zm, K)) + 0.05
+lo, hi = shard_bounds(K * zm, world, rank)
+Lzl = Lz[lo:hi]
+w = np.full(K, 1.0 / K)
+reg = 0.5
+h = eo.mple_stepsize(1.0, reg, M)
+ncoll = [0]
+def dhz_partial():
+    rho = Lzl @ w                                        # local rows only
+    wz = np.tile(w, zm)[lo:hi] / zm
+    d = -(Lzl.T @ (wz / rho))
+    for z in range(lo, hi):                              # the log term of the rows held here
+        d[z % K] -= np.log(rho[z - lo]) / zm
+    return torch.from_numpy(d)
+def dlogl():
+    return torch.from_numpy(eo.dlogl(w, Ld.T))
+def step(ga, gb):
+    g = reg * ga.numpy() + (1 - reg) * gb.numpy()
+    w[:] = eo.movefromboundary(w, eo.projectsimplex(w + h * g))
+def asum(x):
+    ncoll[0] += 1
+    dist.all_reduce(x)
+mple_sharded(n - 1, reg, dhz_partial, dlogl, step, asum)
+assert ncoll[0] == n - 1                                  # ONE collective per iteration
+ref = eo.gradientascent(eo.dmple_obj(Ld.T, Lz, reg), np.full(K, 1.0 / K), n, h)[-1]
+assert np.max(np.abs(w - ref)) < 1e-14, np.max(np.abs(w - ref))
+print("rank", rank, "ok")
+dist.destroy_process_group()
+'''
+
+
+def test_sharded_mple_gloo_world2(tmp_path):
+    """z-sharded projected gradient ascent (dist.mple_sharded): one allreduce(sum) of the K partial gradients per iteration
+    reproduces the unsharded oracle iterates."""
+    script = tmp_path / "worker_eb.py"
+    script.write_text(WORKER_EB.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29565", str(script)],
+                       capture_output=True, text=True, env=env, timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ok") == 2

@@ -192,3 +192,79 @@ def test_gyncmodel_pipeline(gpu):
     ref = eo.gradientascent(eo.dmple_obj(Ld.T, Lz, 0.5), w, 5, eo.mple_stepsize(1.0, 0.5, len(datas)))
     assert max(np.max(np.abs(a - b)) for a, b in zip(ws, ref)) < 1e-13
     m.close()
+
+
+def test_zsharded_model_two_shards_one_gpu(gpu):
+    """dist.ShardedEB on one GPU: the z-matrix split into two row shards (the collectives emulated by combining the two
+    shards' buffers) reproduces the unsharded model and the oracle: global renormalisation, hz, dhz, mple iterates."""
+    import torch
+    import eb_oracle as eo
+    from gync_b200 import eb
+    rng = np.random.default_rng(17)
+    K, M, zm = 150, 9, 2
+    base = np.array([40.0, 5.0, 150.0, 6.0])
+    ys = [base * (1 + 0.03 * rng.standard_normal((31, 4))) for _ in range(K)]
+    datas = patient_like(rng, M, 0.4)
+    datas = [0.05 * d + 0.95 * base for d in datas]
+    err = eb.MatrixNormalCentered(SIG * 0.3)
+    zs = [y + err.rand(rng) for _ in range(zm) for y in ys]
+    full = eb.LikelihoodModel(ys, ys, zs, datas, err)
+    Ld, Lz = full.matrices()
+    assert relerr(Lz, eo.likelihoodmat_nanfast(zs, ys, err.sigmas)) < 1e-9
+    Y, Dm, Zs = eb._cols(ys), eb._cols(datas), eb._cols(zs)
+    sig = np.ascontiguousarray(err.sigmas.ravel(order="F"))
+    cut = 130
+    # two "ranks" on one GPU through the C ABI; the collectives are emulated by combining the shards' buffers
+    lib, L_ = gpu.lib.load(), gpu.lib
+    import ctypes as C
+    hs, scals = [], []
+    for lo, hi in ((0, cut), (cut, K * zm)):
+        h = C.c_void_p()
+        sc = np.empty(2)
+        L_.check(lib.gync_ebmodel_create_zshard(L_.dptr(Y), K, L_.dptr(Dm), M, L_.dptr(np.asfortranarray(Zs[:, lo:hi])), hi - lo, lo, K * zm,
+                                                124, L_.dptr(sig), None, L_.dptr(sc), C.byref(h)))
+        hs.append(h)
+        scals.append(sc)
+    g = np.array([min(scals[0][0], scals[1][0]), max(scals[0][1], scals[1][1])])
+    for h in hs:
+        L_.check(lib.gync_ebmodel_zshard_finish(h, L_.dptr(g)))
+    dev = torch.device("cuda", 0)
+    st = torch.cuda.current_stream().cuda_stream
+    w = rng.random(K)
+    w /= w.sum()
+    dw = torch.from_numpy(w).to(dev)
+    parts = [torch.empty(K, dtype=torch.float64, device=dev) for _ in hs]
+    hzp = [torch.empty(1, dtype=torch.float64, device=dev) for _ in hs]
+    for h, pt, hp in zip(hs, parts, hzp):
+        L_.check(lib.gync_ebmodel_dhz_dev(h, dw.data_ptr(), 0, pt.data_ptr(), st))
+        L_.check(lib.gync_ebmodel_hz_dev(h, dw.data_ptr(), hp.data_ptr(), st))
+    torch.cuda.synchronize()
+    d = (parts[0] + parts[1]).cpu().numpy()
+    assert relerr(d, eb.dhz(full, w)) < 1e-12 and relerr(d, eo.dhzdiscr(w, Lz)) < 1e-11
+    hzs = float((hzp[0] + hzp[1]).item())
+    assert abs(hzs - eb.hz(full, w)) < 1e-12 * abs(hzs)
+    # cont form: the constant -1 is added by one shard only
+    for h, pt in zip(hs, parts):
+        L_.check(lib.gync_ebmodel_dhz_dev(h, dw.data_ptr(), 1, pt.data_ptr(), st))
+    torch.cuda.synchronize()
+    assert relerr((parts[0] + parts[1]).cpu().numpy(), eb.dhz(full, w, cont=True)) < 1e-12
+    # device-resident ascent loop with the partial gradients summed each iteration == unsharded mple
+    reg, n = 0.5, 6
+    hstep = eo.mple_stepsize(1.0, reg, M)
+    ws = [torch.full((K,), 1.0 / K, dtype=torch.float64, device=dev) for _ in hs]
+    gb = torch.empty(K, dtype=torch.float64, device=dev)
+    for _ in range(n - 1):
+        for h, wv, pt in zip(hs, ws, parts):
+            L_.check(lib.gync_ebmodel_dhz_dev(h, wv.data_ptr(), 0, pt.data_ptr(), st))
+        tot = parts[0] + parts[1]
+        for h, wv in zip(hs, ws):
+            L_.check(lib.gync_ebmodel_dlogl_dev(h, wv.data_ptr(), gb.data_ptr(), st))
+            L_.check(lib.gync_ebmodel_ascent_dev(h, wv.data_ptr(), tot.data_ptr(), reg, gb.data_ptr(), 1 - reg, hstep, st))
+    torch.cuda.synchronize()
+    ref = eb.mple(full, reg, 1.0, n)[-1]
+    assert torch.equal(ws[0], ws[1])                                   # replicated step: identical on every rank
+    assert np.max(np.abs(ws[0].cpu().numpy() - ref)) < 1e-14
+    assert lib.gync_ebmodel_nan_flag(hs[0], st) == 0
+    for h in hs:
+        lib.gync_ebmodel_destroy(h)
+    full.close()

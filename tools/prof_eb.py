@@ -26,9 +26,20 @@ h = C.c_void_p()
 L.check(lib.gync_ebmodel_from_matrices(L.dptr(np.asfortranarray(Ld.cpu().numpy().T)), K, M,
                                        L.dptr(np.asfortranarray(Lz.cpu().numpy().T)), K, C.byref(h)))
 w = torch.full((K,), 1.0 / K, dtype=torch.float64, device=dev)
-L.check(lib.gync_ebmodel_grad_dev(h, w.data_ptr(), 3, 3, st))          # one-pass dhz + dlogl
+ga, gb = torch.empty_like(w), torch.empty_like(w)
+
+
+def grads(which, reps):
+    for _ in range(reps):
+        if which & 1:
+            L.check(lib.gync_ebmodel_dhz_dev(h, w.data_ptr(), 0, ga.data_ptr(), st))
+        if which & 2:
+            L.check(lib.gync_ebmodel_dlogl_dev(h, w.data_ptr(), gb.data_ptr(), st))
+
+
+grads(3, 3)          # one-pass dhz + dlogl
 os.environ["GYNC_DHZ_TWO_PASS"] = "1"
-L.check(lib.gync_ebmodel_grad_dev(h, w.data_ptr(), 1, 2, st))          # two-pass dhz
+grads(1, 2)          # two-pass dhz
 del os.environ["GYNC_DHZ_TWO_PASS"]
 torch.cuda.synchronize()
 wh = np.full(K, 1.0 / K)
