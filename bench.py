@@ -442,7 +442,7 @@ def flops_per_step(lib):
     if f is not None:
         f.restype = C.c_double
         return float(f())
-    return 7746.0
+    return 7422.0
 
 
 def em_leg(lib, L, torch, dist, dev, stream, world, rank, barrier, max_over_ranks, niter=100):

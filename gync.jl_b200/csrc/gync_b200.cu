@@ -279,15 +279,15 @@ const char* gync_last_error(void) { return g_err.c_str(); }
 
 int64_t gync_launch_count(void) { return g_launches.load(); }
 
-// FP64 flops of one RODAS4 step attempt: generated-code counts (add+mul; a reciprocal = seed + 4 DFMA = 8,
+// FP64 flops of one RODAS4 step attempt: generated-code counts (add+mul; a reciprocal = seed + 3 DFMA = 6,
 // the real power = exp+log ~ 60) + the hand-written stage algebra of gync_rodas4_step
-// (33 x [2+2+4+5+6+7+8+9+1+11+1] for the stage combinations + 33 x 15 for the error norm).
+// (33 x [2+2+4+5+6+7+8+9+1+11+1] for the stage combinations + 33 x 13 for the error norm).
 double gync_flops_per_step(void) {
-  const double rcp = 8.0, pw = 60.0;
+  const double rcp = 6.0, pw = 60.0;
   const double rhs = GYNC_OPS_RHS_FLOP + rcp * GYNC_OPS_RHS_RCP + pw * GYNC_OPS_RHS_POW;
   const double rhsw = GYNC_OPS_RHSW_FLOP + rcp * GYNC_OPS_RHSW_RCP + pw * GYNC_OPS_RHSW_POW;
   const double lu = GYNC_OPS_LU_FLOP + rcp * GYNC_OPS_LU_RCP;
-  const double stage = 33.0 * (2 + 2 + 4 + 5 + 6 + 7 + 8 + 9 + 1 + 11 + 1) + 33.0 * 15.0;
+  const double stage = 33.0 * (2 + 2 + 4 + 5 + 6 + 7 + 8 + 9 + 1 + 11 + 1) + 33.0 * 13.0;
   return rhsw + 5.0 * rhs + lu + 6.0 * GYNC_OPS_SOLVE_FLOP + stage;
 }
 
