@@ -221,10 +221,13 @@ __device__ __forceinline__ void gync_tm_st1(uint32_t ta, double v) {
 __device__ __forceinline__ void gync_tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // store a 33-vector to TMEM columns [col, col+66)
+// One x2 store per double: a double already sits in an aligned register pair, so nothing has to be marshalled.
+// (x16 stores need 16 consecutive registers; the allocator keeps the vectors elsewhere and ptxas emitted 16 moves in
+// front of every x16 store — 640 IMAD.MOV per RODAS step, seen in the ncu source page.  Removing them changed the
+// time by +0.5 %: the kernel is bound by dependency latency, not by issue slots.)
 __device__ __forceinline__ void gync_tm_store_vec(uint32_t ta, const double* v) {
 #pragma unroll
-  for (int c = 0; c < 4; ++c) gync_tm_st8(ta + 16 * c, v + 8 * c);
-  gync_tm_st1(ta + 64, v[32]);
+  for (int i = 0; i < GYNC_NY; ++i) gync_tm_st1(ta + 2 * i, v[i]);
   gync_tm_wait_st();
 }
 
@@ -234,7 +237,8 @@ __device__ __forceinline__ void gync_tail_store8(GyncSmViewT<NSLOT>& A, const in
                                                  const double v2, const double v3, const double v4, const double v5,
                                                  const double v6, const double v7) {
   const double v[8] = {v0, v1, v2, v3, v4, v5, v6, v7};
-  gync_tm_st8(A.tm + GYNC_TM_COL_TAIL + 16 * c, v);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) gync_tm_st1(A.tm + GYNC_TM_COL_TAIL + 16 * c + 2 * i, v[i]);
   gync_tm_wait_st();     // chunks are emitted in the order their values become available, not by index
 }
 template <int NSLOT>
