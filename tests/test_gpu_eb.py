@@ -268,3 +268,75 @@ def test_zsharded_model_two_shards_one_gpu(gpu):
     for h in hs:
         lib.gync_ebmodel_destroy(h)
     full.close()
+
+
+def test_eb_full_size_properties(gpu):
+    """BASELINE-size runs checked through size-independent properties (no oracle can run at these sizes in seconds):
+    likelihood matrix 1e5 x 40 — permutation equivariance (bit-exact), argument symmetry, range; regulariser on a
+    1e4 x 1e4 z-matrix — the checksums  sum_k w_k dlogl_k = M  and  sum_k w_k dhz_k = hz(w) - 1  (from
+    regularizers.jl:7-10, 30-45, 59-79), one-pass == two-pass dhz; projection at K = 1e6 — idempotent, on the simplex."""
+    import os
+    import torch
+    from gync_b200 import eb, lib as L_
+    lib = L_.load()
+    dev = torch.device("cuda", 0)
+    st = torch.cuda.current_stream().cuda_stream
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(5)
+    I, J, D = 100_000, 40, 124
+    sig = torch.tensor(SIG.ravel(order="F"), device=dev)
+    A = torch.randn(D, I, dtype=torch.float64, device=dev, generator=gen) * 0.3          # sample-major (stride_k = I)
+    B = torch.randn(J, D, dtype=torch.float64, device=dev, generator=gen) * 0.3          # column-major D x J
+    B[torch.rand(J, D, device=dev, generator=gen) < 0.4] = float("nan")
+    Lm = torch.empty(J, I, dtype=torch.float64, device=dev)
+    L_.check(lib.gync_likelihoodmat_dev(A.data_ptr(), I, I, 1, B.data_ptr(), J, 1, D, D, sig.data_ptr(), 1, Lm.data_ptr(), st))
+    assert torch.isfinite(Lm).all() and Lm.min() >= 0
+    perm = torch.randperm(I, device=dev, generator=gen)
+    Ap = A[:, perm].contiguous()
+    Lp = torch.empty_like(Lm)
+    L_.check(lib.gync_likelihoodmat_dev(Ap.data_ptr(), I, I, 1, B.data_ptr(), J, 1, D, D, sig.data_ptr(), 1, Lp.data_ptr(), st))
+    assert torch.equal(Lp, Lm[:, perm])                                   # rows follow their samples bit-exactly
+    Lt = torch.empty(I, J, dtype=torch.float64, device=dev)               # J x I column-major: arguments swapped
+    L_.check(lib.gync_likelihoodmat_dev(B.data_ptr(), J, 1, D, A.data_ptr(), I, I, 1, D, sig.data_ptr(), 1, Lt.data_ptr(), st))
+    torch.cuda.synchronize()
+    assert float(((Lt.T - Lm).abs() / Lm.clamp_min(1e-300)).max()) < 1e-12
+    del A, Ap, Lm, Lp, Lt
+    # regulariser at K = Z = 1e4, M = 40 (both matrices built on the device)
+    K, M = 10_000, 40
+    rng = np.random.default_rng(23)
+    Y = np.asfortranarray(rng.standard_normal((D, K)) * 0.3)
+    Z = np.asfortranarray(Y + rng.standard_normal((D, K)) * 0.1)
+    Dm = np.asfortranarray(rng.standard_normal((D, M)) * 0.3)
+    Dm[rng.random((D, M)) < 0.4] = np.nan
+    sg = np.ascontiguousarray(SIG.ravel(order="F"))
+    import ctypes as C
+    h = C.c_void_p()
+    L_.check(lib.gync_ebmodel_create(L_.dptr(Y), K, L_.dptr(Dm), M, L_.dptr(Z), K, D, L_.dptr(sg), None, C.byref(h)))
+    w = rng.random(K)
+    w /= w.sum()
+    d = np.empty(K)
+    L_.check(lib.gync_ebmodel_dlogl(h, L_.dptr(w), L_.dptr(d)))
+    assert abs(np.dot(w, d) - M) < 1e-10 * M
+    hz = C.c_double()
+    L_.check(lib.gync_ebmodel_hz(h, L_.dptr(w), None, C.byref(hz)))
+    g1 = np.empty(K)
+    L_.check(lib.gync_ebmodel_dhz(h, L_.dptr(w), 0, L_.dptr(g1)))
+    assert abs(np.dot(w, g1) - (hz.value - 1.0)) < 1e-10 * max(1.0, abs(hz.value))
+    os.environ["GYNC_DHZ_TWO_PASS"] = "1"
+    try:
+        g2 = np.empty(K)
+        L_.check(lib.gync_ebmodel_dhz(h, L_.dptr(w), 0, L_.dptr(g2)))
+    finally:
+        del os.environ["GYNC_DHZ_TWO_PASS"]
+    assert relerr(g1, g2) < 1e-12                                          # one HBM pass == the reference's two matvecs
+    ws = w.copy()
+    L_.check(lib.gync_ebmodel_mple(h, L_.dptr(ws), 0.5, 1e-7, 5, 0, None))
+    assert abs(ws.sum() - 1) < 1e-12 and ws.min() >= 0
+    lib.gync_ebmodel_destroy(h)
+    # projection at K = 1e6
+    y = rng.standard_normal(1_000_000) * 1e-5 + 1e-6
+    p = eb.projectsimplex(y)
+    assert abs(p.sum() - 1) < 1e-11 and p.min() >= 0
+    assert np.max(np.abs(eb.projectsimplex(p) - p)) < 1e-16
+    t = (y - p)[p > 0]
+    assert np.ptp(t) < 1e-15                                               # p = max(y - t, 0) with ONE threshold
