@@ -280,7 +280,7 @@ def main():
     # ---- §8f rows 2-3: alternative likelihood-matrix builder + regulariser gradients (device-resident)
     ebr = None
     if world == 1 and not args.no_eb:
-        ebr = eb_leg(lib, L, torch, dev, stream)
+        ebr = eb_leg(lib, L, torch, dev, stream, cpu=not args.no_cpu)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -343,7 +343,7 @@ def cfg3_leg(lib, L, torch, dev, stream, dX, Xh, op, M=40, niter=100):
             "note": "one forward solve per sample serves all 40 patients (the reference re-solves per patient)"}
 
 
-def eb_leg(lib, L, torch, dev, stream, K=10_000, M=40, D=124):
+def eb_leg(lib, L, torch, dev, stream, K=10_000, M=40, D=124, cpu=False):
     """likelihoodmat_nanfast (eb/likelihoodmat.jl:34) at the cfg-3 shape (1e5 x 40, 124 = 31 days x 4 hormones) and as the
     K x K z-matrix of hz (regularizers.jl:26); then the regulariser gradients on the resident matrices:
     dhzdiscr = two HBM passes over the Z x K matrix (800 MB at K = 1e4), dlogl on K x M, and one projected ascent step."""
@@ -432,6 +432,30 @@ def eb_leg(lib, L, torch, dev, stream, K=10_000, M=40, D=124):
     out["mple_20_steps_host_call_ms"] = (time.perf_counter() - t0) * 1e3
     out["mple_sum_w"] = float(wh.sum())
     lib.gync_ebmodel_destroy(h)
+    if cpu:
+        # the reference's own formulation on the host cores (numpy/BLAS port, oracle/eb_oracle.py) on a bounded sample
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import eb_oracle as eo
+        Kc = 3000
+        rng = np.random.default_rng(3)
+        Yc = [rng.standard_normal((31, 4)) * 0.3 for _ in range(Kc)]
+        Zc = [y + rng.standard_normal((31, 4)) * 0.1 for y in Yc]
+        sg = np.tile(np.array([12.0, 1.0, 40.0, 1.5]), (31, 1))
+        A_ = np.stack([(y / sg).ravel(order="F") for y in Yc], axis=1)
+        B_ = np.stack([(z / sg).ravel(order="F") for z in Zc], axis=1)
+        t0 = time.perf_counter()
+        Lc = np.exp(-0.5 * eo.sqeucdist_nan(B_, A_))           # likelihoodmat.jl:61-95 + :57 (normalisation loop left out)
+        t_l = time.perf_counter() - t0
+        wc = np.full(Kc, 1.0 / Kc)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            rho = Lc @ wc
+            dd = -(Lc.T @ (wc / rho)) - np.log(rho)              # regularizers.jl:65-75 with zmult = 1
+        t_d = (time.perf_counter() - t0) / 3
+        out["cpu_port"] = {"K": Kc, "cores": os.cpu_count(), "kind": "port",
+                           "likelihoodmat_pairs_per_s": Kc * Kc / t_l, "dhzdiscr_GBps_two_reads": 2 * 8 * Kc * Kc / t_d / 1e9,
+                           "sample": f"{Kc} x {Kc} z-matrix (numpy/BLAS restatement of sqeucdist_nan + exp, and of the two matvecs of "
+                                     "dhzdiscr), all host threads"}
     return out
 
 

@@ -217,6 +217,13 @@ int eb_ascent_step(gync_ebmodel* m, double* dw, const double* ga, double ca, con
   return GYNC_OK;
 }
 
+// host-level hz / dhz / mple return complete results: on a z-sharded model they would silently be partial sums
+int eb_check_unsharded(const gync_ebmodel* m, const char* what) {
+  if (m->Z != (int64_t)m->zmult * m->K)
+    return fail(GYNC_ERR_ARG, std::string(what) + ": z-sharded model — use the *_dev entry points and allreduce the partial results");
+  return GYNC_OK;
+}
+
 int eb_check_model(gync_ebmodel* m, const void* w, const char* what) {
   if (!m || !w) return fail(GYNC_ERR_ARG, std::string(what) + ": NULL argument");
   if (int rc = ensure_init()) return rc;
@@ -478,6 +485,7 @@ int gync_ebmodel_dlogl(gync_ebmodel* m, const double* w, double* d) {
 int gync_ebmodel_hz(gync_ebmodel* m, const double* w, const double* wz, double* out) {
   if (int rc = eb_check_model(m, w, "gync_ebmodel_hz")) return rc;
   if (!out || m->Z < 1) return fail(GYNC_ERR_ARG, "gync_ebmodel_hz: no z matrix / NULL output");
+  if (int rc = eb_check_unsharded(m, "gync_ebmodel_hz")) return rc;
   CK(cudaMemcpyAsync(m->w, w, sizeof(double) * m->K, cudaMemcpyHostToDevice, g_stream));
   if (int rc = eb_rho(m, m->w, g_stream)) return rc;
   if (wz) {
@@ -497,6 +505,7 @@ int gync_ebmodel_hz(gync_ebmodel* m, const double* w, const double* wz, double* 
 int gync_ebmodel_dhz(gync_ebmodel* m, const double* w, int32_t cont, double* d) {
   if (int rc = eb_check_model(m, w, "gync_ebmodel_dhz")) return rc;
   if (!d || m->Z < 1) return fail(GYNC_ERR_ARG, "gync_ebmodel_dhz: no z matrix / NULL output");
+  if (int rc = eb_check_unsharded(m, "gync_ebmodel_dhz")) return rc;
   CK(cudaMemcpyAsync(m->w, w, sizeof(double) * m->K, cudaMemcpyHostToDevice, g_stream));
   CK(cudaMemsetAsync(m->flags + 1, 0, sizeof(int), g_stream));
   if (int rc = eb_dhz(m, m->w, cont, m->gb, g_stream)) return rc;
@@ -530,6 +539,7 @@ int gync_ebmodel_mple(gync_ebmodel* m, double* w, double reg, double h, int32_t 
   if (int rc = eb_check_model(m, w, "gync_ebmodel_mple")) return rc;
   if (nsteps < 0 || (reg != 0.0 && m->Z < 1) || (reg != 1.0 && m->M < 1))
     return fail(GYNC_ERR_ARG, "gync_ebmodel_mple: the model lacks the matrix this regularisation weight needs");
+  if (reg != 0.0) if (int rc = eb_check_unsharded(m, "gync_ebmodel_mple")) return rc;
   if (nsteps == 0) return GYNC_OK;
   cudaStream_t s = g_stream;
   DBuf dH;
