@@ -301,12 +301,10 @@ int gync_phi_batch(const double* X, int64_t N, const gync_solver_opts* opts, dou
   CK(dP.alloc(sizeof(double) * N * 124));
   CK(cudaMemcpyAsync(dX.p, X, sizeof(double) * N * GYNC_NX, cudaMemcpyHostToDevice, g_stream));
   CK(cudaMemcpyAsync(dT.p, t, sizeof(double) * nT, cudaMemcpyHostToDevice, g_stream));
-  if (int rc = prep_solver_kernel(gync_solve_kernel<GYNC_SOLVE_BLOCK>, GyncWorkSm<GYNC_SOLVE_BLOCK>::kSmemBytes, GYNC_SOLVE_BLOCK)) return rc;
-  gync_solve_kernel<GYNC_SOLVE_BLOCK><<<std::min<unsigned>(blocks_for(N, GYNC_SOLVE_BLOCK), g_num_sms), GYNC_SOLVE_BLOCK,
-                                         GyncWorkSm<GYNC_SOLVE_BLOCK>::kSmemBytes, g_stream>>>(
-      dX.as<double>(), nullptr, nullptr, N, dT.as<double>(), nT, to_opts(opts), dY.as<double>(), dSt.as<int32_t>());
+  if (int rc = launch_solve_grid(dX.as<double>(), nullptr, nullptr, N, dT.as<double>(), nT, to_opts(opts), dY.as<double>(),
+                                 dSt.as<int32_t>(), g_stream)) return rc;
   gync_pick_measured_kernel<<<blocks_for(N * 124, 256), 256, 0, g_stream>>>(dY.as<double>(), N, nT, dP.as<double>());
-  g_launches += 2;
+  g_launches += 1;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(Yphi, dP.p, sizeof(double) * N * 124, cudaMemcpyDeviceToHost, g_stream));
   if (status) CK(cudaMemcpyAsync(status, dSt.p, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, g_stream));

@@ -121,6 +121,29 @@ int launch_loglik(const double* dX, int64_t N, const double* d_data, const doubl
 }
 }  // namespace
 
+namespace {
+// gync / forwardsol on a shared time grid: the tensor-memory kernel (persistent lanes, 128 samples per SM); the older
+// shared-memory kernel (64 per SM, static assignment) is kept behind GYNC_SOLVE_SM for A/B runs.
+int launch_solve_grid(const double* dX, const double* dY0, const double* dP, int64_t N, const double* d_t, int nT,
+                      const GyncSolverOpts& so, double* dY, int32_t* d_status, cudaStream_t s) {
+  if (getenv("GYNC_SOLVE_SM")) {
+    if (int rc = prep_solver_kernel(gync_solve_kernel<GYNC_SOLVE_BLOCK>, GyncWorkSm<GYNC_SOLVE_BLOCK>::kSmemBytes, GYNC_SOLVE_BLOCK)) return rc;
+    gync_solve_kernel<GYNC_SOLVE_BLOCK><<<std::min<unsigned>(blocks_for(N, GYNC_SOLVE_BLOCK), g_num_sms), GYNC_SOLVE_BLOCK,
+                                           GyncWorkSm<GYNC_SOLVE_BLOCK>::kSmemBytes, s>>>(dX, dY0, dP, N, d_t, nT, so, dY, d_status);
+  } else {
+    ABuf cnt;
+    CK(cnt.alloc(sizeof(unsigned long long), s));
+    CK(cudaMemsetAsync(cnt.p, 0, sizeof(unsigned long long), s));
+    if (int rc = prep_solver_kernel(gync_solve_tm_kernel, GyncWorkTm::kSmemBytes, 128)) return rc;
+    const int nb = (int)std::min<int64_t>((N + GYNC_TM_NSLOT - 1) / GYNC_TM_NSLOT, (int64_t)g_num_sms);
+    gync_solve_tm_kernel<<<nb, 128, GyncWorkTm::kSmemBytes, s>>>(dX, dY0, dP, N, d_t, nT, so, dY, d_status, cnt.as<unsigned long long>());
+  }
+  g_launches += 1;
+  CK(cudaGetLastError());
+  return GYNC_OK;
+}
+}  // namespace
+
 // EM launch helpers (templates: outside extern "C")
 namespace {
 
@@ -492,13 +515,8 @@ static int solve_common(const double* X, const double* Y0, const double* P, int6
   CK(dY.alloc(sizeof(double) * N * nT * GYNC_NY));
   CK(dSt.alloc(sizeof(int32_t) * N));
   CK(cudaMemcpyAsync(dT.p, t, sizeof(double) * nT, cudaMemcpyHostToDevice, g_stream));
-  if (int rc = prep_solver_kernel(gync_solve_kernel<GYNC_SOLVE_BLOCK>, GyncWorkSm<GYNC_SOLVE_BLOCK>::kSmemBytes, GYNC_SOLVE_BLOCK)) return rc;
-  gync_solve_kernel<GYNC_SOLVE_BLOCK><<<std::min<unsigned>(blocks_for(N, GYNC_SOLVE_BLOCK), g_num_sms), GYNC_SOLVE_BLOCK,
-                                         GyncWorkSm<GYNC_SOLVE_BLOCK>::kSmemBytes, g_stream>>>(
-      X ? dX.as<double>() : nullptr, dY0.as<double>(), dP.as<double>(), N, dT.as<double>(), nT, to_opts(opts),
-      dY.as<double>(), dSt.as<int32_t>());
-  g_launches += 1;
-  CK(cudaGetLastError());
+  if (int rc = launch_solve_grid(X ? dX.as<double>() : nullptr, dY0.as<double>(), dP.as<double>(), N, dT.as<double>(), nT, to_opts(opts),
+                                 dY.as<double>(), dSt.as<int32_t>(), g_stream)) return rc;
   CK(cudaMemcpyAsync(Y, dY.p, sizeof(double) * N * nT * GYNC_NY, cudaMemcpyDeviceToHost, g_stream));
   if (status) CK(cudaMemcpyAsync(status, dSt.p, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, g_stream));
   CK(cudaStreamSynchronize(g_stream));

@@ -550,6 +550,122 @@ gync_solve_kernel(const double* __restrict__ X, const double* __restrict__ Y0, c
   }
 }
 
+// gync(y0,p,t) / forwardsol(x,t) in the tensor-memory layout of K1 (128 samples per SM, persistent lanes): the same step
+// function, a per-lane cursor into the shared sorted time grid instead of the merged measurement sequences.  Row 0 of
+// the output is y0 at t[0]; repeated grid times are served from the same state (CVODE's behaviour for a repeated tout).
+__global__ void __launch_bounds__(128, 1)
+gync_solve_tm_kernel(const double* __restrict__ X, const double* __restrict__ Y0, const double* __restrict__ P,
+                     int64_t N, const double* __restrict__ tgrid, int nT, GyncSolverOpts o,
+                     double* __restrict__ Y, int* __restrict__ status, unsigned long long* __restrict__ counter) {
+  extern __shared__ double gync_sm[];
+  __shared__ uint32_t s_tmem;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;"
+                 :: "r"((uint32_t)__cvta_generic_to_shared(&s_tmem)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = s_tmem;
+  GyncWorkTm W;
+  const int slot = warp * 32 + lane;
+  W.q.p = gync_sm + slot;
+  W.A.p = gync_sm + (size_t)GYNC_NQ * GYNC_TM_NSLOT + slot;
+  W.tm = tmem_base + ((uint32_t)(warp * 32) << 16);
+  W.A.tm = W.tm;
+#pragma unroll
+  for (int i = 0; i < GYNC_NY; ++i) { W.y[i] = 1.0; W.yn[i] = 1.0; W.e[i] = 0.0; }
+  bool active = false, done = false;
+  int64_t n = 0;
+  double t = 0.0, tn = 0.0;
+  int kidx = 0, budget = 0, st = GYNC_ST_OK;
+  GyncCtrl c;
+  gync_ctrl_init(c, 1e-3);
+  GyncGridSink sink = {Y, N, nT};
+  for (;;) {
+    if (!active && !done) {
+      n = (int64_t)atomicAdd(counter, 1ull);
+      if (n >= N) {
+        done = true;
+      } else {
+        if (X) {
+          double T;
+          gync_load_sample(W, [&](int k) { return __ldg(X + n + N * k); }, c_refallparms, c_sampledinds, &T);
+        } else {
+          double p[GYNC_NP];
+#pragma unroll
+          for (int k = 0; k < GYNC_NP; ++k) p[k] = __ldg(P + n + N * k);
+          gync_pack_params(p, W.q);
+#pragma unroll
+          for (int i = 0; i < GYNC_NY; ++i) W.y[i] = __ldg(Y0 + n + N * i);
+        }
+        sink.Y = Y + n;
+        kidx = 0;
+        budget = o.max_steps;
+        t = tgrid[0];
+        tn = t;
+        st = (gync_all_finite(W.y, GYNC_NY) && gync_all_finite(W.q, GYNC_NQ) && t == t) ? GYNC_ST_OK : GYNC_ST_NONFINITE;
+        gync_ctrl_init(c, (st == GYNC_ST_OK) ? ((o.h0 > 0.0) ? o.h0 : gync_initial_step(W, o.rtol, o.atol)) : 1.0);
+        active = true;
+        if (st == GYNC_ST_OK) {
+          while (kidx < nT && (tn = tgrid[kidx]) <= t) { sink(kidx, W.y); ++kidx; }
+          if (kidx < nT && !(tn == tn)) st = GYNC_ST_NONFINITE;
+        }
+      }
+    }
+    __syncwarp();
+    if (__all_sync(0xffffffffu, done)) break;
+    // ---- one step attempt, executed by ALL lanes of the warp (TMEM ops are warp-collective)
+    const bool stepping = active && st == GYNC_ST_OK && kidx < nT && tn > t;
+    double h = c.h;
+    if (o.hmax > 0.0) h = fmin(h, o.hmax);
+    const double rem = tn - t;
+    const bool last = stepping && (h * 1.0001 >= rem);
+    if (last) h = rem;
+    if (!stepping || !(h > 0.0)) h = 1.0;                  // idle lanes: any finite positive step
+    const double hprop = c.h;
+    const double err = gync_rodas4_step_tm(W, h, o.rtol, o.atol);
+    __syncwarp();
+    if (stepping) {
+      if (budget-- <= 0) {
+        st = GYNC_ST_MAXSTEPS;
+      } else if (!(h > 1e-14 * fmax(1.0, fabs(t)))) {
+        st = GYNC_ST_HMIN;
+      } else {
+        const bool fin = gync_all_finite(W.yn, GYNC_NY);
+        if (gync_ctrl_update(c, h, err, fin)) {
+          t = last ? tn : t + h;
+#pragma unroll
+          for (int i = 0; i < GYNC_NY; ++i) W.y[i] = W.yn[i];
+          if (last && h < hprop) c.h = fmax(c.h, hprop);
+        }
+      }
+    }
+    if (active) {
+      bool finished = (st != GYNC_ST_OK);
+      if (!finished && t >= tn) {
+        while (kidx < nT && (tn = tgrid[kidx]) <= t) { sink(kidx, W.y); ++kidx; }
+        if (kidx < nT && !(tn == tn)) { st = GYNC_ST_NONFINITE; finished = true; }
+      }
+      if (kidx >= nT) finished = true;
+      if (finished) {
+        if (st != GYNC_ST_OK)
+          for (int64_t k = 0; k < (int64_t)nT * GYNC_NY; ++k) Y[n + N * k] = NAN;   // gyncycle.jl:18-19
+        if (status) status[n] = st;
+        active = false;
+#pragma unroll
+        for (int i = 0; i < GYNC_NY; ++i) if (!(W.y[i] * 0.0 == 0.0)) W.y[i] = 1.0;
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem_base) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // K4: EM / self-consistency iteration  w_k <- w_k/M * sum_m L_km / (L'w)_m   (em.jl:27-41)
 //
