@@ -9,6 +9,7 @@
 #include "gync_kernels.cuh"
 #include "gync_mcmc.cuh"
 #include "gync_amm.cuh"
+#include "gync_sched.cuh"
 #include "../../include/gync_b200.h"
 
 extern "C" int gync_init(int device);
@@ -101,7 +102,52 @@ int prep_solver_kernel(K kern, size_t smem, int block) {
 extern "C" int gync_init(int device);
 
 namespace {
-// One launch of the solver kernel: persistent lanes, one CTA (4 warps x 28 samples, state in shared
+// Longest-first ordering of the sample queue, learned from the step counts of earlier batches (gync_sched.cuh).
+struct SchedState {
+  GyncSchedModel* mdl = nullptr;
+  double *G = nullptr, *b = nullptr, *Phi = nullptr, *target = nullptr, *pred = nullptr;
+  int *order = nullptr, *hist = nullptr, *steps = nullptr;
+  unsigned long long* minmax = nullptr;
+  int64_t cap = 0;
+  bool fitted = false;
+  int device = -1;
+  void release() {
+    if (device >= 0) {
+      int cur = 0;
+      cudaGetDevice(&cur);
+      cudaSetDevice(device);
+      for (void* p : {(void*)mdl, (void*)G, (void*)b, (void*)Phi, (void*)target, (void*)pred, (void*)order, (void*)hist, (void*)steps, (void*)minmax})
+        if (p) cudaFree(p);
+      cudaSetDevice(cur);
+    }
+    *this = SchedState();
+  }
+  int ensure(int64_t N, int dev) {
+    if (device == dev && cap >= N) return GYNC_OK;
+    const bool keep = (device == dev) && fitted;
+    GyncSchedModel* old = keep ? mdl : nullptr;
+    if (keep) mdl = nullptr;                      // survive the reallocation below
+    const bool was_fitted = keep;
+    release();
+    device = dev;
+    cap = N + N / 4;
+    if (old) mdl = old; else { CK(cudaMalloc((void**)&mdl, sizeof(GyncSchedModel))); CK(cudaMemset(mdl, 0, sizeof(GyncSchedModel))); }
+    fitted = was_fitted;
+    CK(cudaMalloc((void**)&G, sizeof(double) * GYNC_SCHED_NF * GYNC_SCHED_NF));
+    CK(cudaMalloc((void**)&b, sizeof(double) * GYNC_SCHED_NF));
+    CK(cudaMalloc((void**)&Phi, sizeof(double) * GYNC_SCHED_MAXS * GYNC_SCHED_NF));
+    CK(cudaMalloc((void**)&target, sizeof(double) * GYNC_SCHED_MAXS));
+    CK(cudaMalloc((void**)&pred, sizeof(double) * cap));
+    CK(cudaMalloc((void**)&order, sizeof(int) * cap));
+    CK(cudaMalloc((void**)&steps, sizeof(int) * 2 * cap));
+    CK(cudaMalloc((void**)&hist, sizeof(int) * GYNC_SCHED_NB));
+    CK(cudaMalloc((void**)&minmax, sizeof(unsigned long long) * 2));
+    return GYNC_OK;
+  }
+};
+SchedState g_sched[8];
+
+// One launch of the solver kernel: persistent lanes, one CTA (4 warps x 32 samples, state in shared
 // + tensor memory) per SM.  `pat` (nullable) gives every sample its own patient -> LL is N x 1.
 int launch_loglik(const double* dX, int64_t N, const double* d_data, const double* iscale, const int* allnan, int M,
                   const int* pat, const GyncSolverOpts& so, double* dLL, double* dYmeas, int32_t* d_status,
@@ -113,9 +159,42 @@ int launch_loglik(const double* dX, int64_t N, const double* d_data, const doubl
   if (int rc = prep_solver_kernel(gync_loglik_tm_kernel, GyncWorkTm::kSmemBytes, 128)) return rc;
   const int64_t want = (N + GYNC_TM_NSLOT - 1) / GYNC_TM_NSLOT;
   const int nb = (int)std::min<int64_t>(want, (int64_t)g_num_sms);
+  // scheduling pays once there is more than one solve per lane; below that every lane starts at once anyway
+  const bool sched = !getenv("GYNC_NO_SCHED") && 4 * N >= 5 * (int64_t)g_num_sms * GYNC_TM_NSLOT && N < (1LL << 31);
+  int* order = nullptr;
+  int32_t* steps = d_nsteps;
+  SchedState* st = nullptr;
+  if (sched) {
+    int slot = 0;
+    for (size_t i = 0; i < g_devs.size(); ++i) if (g_devs[i].device == g_device) slot = (int)i;
+    st = &g_sched[slot];
+    if (int rc = st->ensure(N, g_device)) return rc;
+    if (!steps) steps = st->steps;
+    if (st->fitted) {
+      CK(cudaMemsetAsync(st->minmax, 0xFF, sizeof(unsigned long long), s));
+      CK(cudaMemsetAsync(st->minmax + 1, 0, sizeof(unsigned long long), s));
+      CK(cudaMemsetAsync(st->hist, 0, sizeof(int) * GYNC_SCHED_NB, s));
+      gync_sched_predict_kernel<<<blocks_for(N, 256), 256, 0, s>>>(dX, N, st->mdl, st->pred, st->minmax);
+      gync_sched_hist_kernel<<<blocks_for(N, 256), 256, 0, s>>>(st->pred, N, st->minmax, st->hist);
+      gync_sched_scan_kernel<<<1, GYNC_SCHED_NB, 0, s>>>(st->hist);
+      gync_sched_scatter_kernel<<<blocks_for(N, 256), 256, 0, s>>>(st->pred, N, st->minmax, st->hist, st->order);
+      g_launches += 4;
+      order = st->order;
+    }
+  }
   gync_loglik_tm_kernel<<<nb, 128, GyncWorkTm::kSmemBytes, s>>>(dX, N, d_data, iscale, allnan, M, pat, so, dLL, dYmeas,
-                                                                d_status, d_nsteps, counter);
+                                                                d_status, steps, counter, order);
   g_launches += 1;
+  if (sched) {                                   // refit the cost model on this batch's step counts
+    const int S = (int)std::min<int64_t>(N, GYNC_SCHED_MAXS);
+    const size_t fit_smem = sizeof(double) * (GYNC_SCHED_NF * (GYNC_SCHED_NF + 1) + GYNC_SCHED_NF);
+    CK(cudaFuncSetAttribute(gync_sched_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fit_smem));
+    gync_sched_features_kernel<<<S, 128, 0, s>>>(dX, N, S, N / S, steps, st->Phi, st->target, st->mdl);
+    gync_sched_normal_kernel<<<GYNC_SCHED_NF, 128, 0, s>>>(st->Phi, st->target, S, st->G, st->b);
+    gync_sched_fit_kernel<<<1, 128, fit_smem, s>>>(st->G, st->b, st->mdl);
+    g_launches += 3;
+    st->fitted = true;
+  }
   CK(cudaGetLastError());
   return GYNC_OK;
 }
@@ -370,6 +449,7 @@ int gync_init(int device) {
 
 void gync_shutdown(void) {
   for (EmLaunchState& st : g_em_local) st.release();
+  for (SchedState& st : g_sched) st.release();
   if (g_em_scratch.partials) {
     if (g_em_scratch.device >= 0) cudaSetDevice(g_em_scratch.device);
     cudaFree(g_em_scratch.partials);

@@ -327,7 +327,8 @@ gync_loglik_tm_kernel(const double* __restrict__ X, int64_t N, const double* __r
                       const double* __restrict__ iscale, const int* __restrict__ allnan, int M,
                       const int* __restrict__ pat /* nullable: patient of each sample -> LL is N x 1 */,
                       GyncSolverOpts o, double* __restrict__ LL, double* __restrict__ Ymeas,
-                      int* __restrict__ status, int* __restrict__ nsteps, unsigned long long* __restrict__ counter) {
+                      int* __restrict__ status, int* __restrict__ nsteps, unsigned long long* __restrict__ counter,
+                      const int* __restrict__ order /* nullable: queue position -> sample (gync_sched.cuh) */) {
   extern __shared__ double gync_sm[];
   __shared__ uint32_t s_tmem;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -371,6 +372,7 @@ gync_loglik_tm_kernel(const double* __restrict__ X, int64_t N, const double* __r
       if (n >= N) {
         done = true;
       } else {
+        if (order) n = order[n];
         gync_load_sample(W, [&](int k) { return __ldg(X + n + N * k); }, c_refallparms, c_sampledinds, &T);
         mlo = pat ? pat[n] : 0;
         mcnt = pat ? 1 : M;

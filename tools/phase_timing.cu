@@ -17,7 +17,7 @@ int main() {
   gync_prep_patients_kernel<<<1, 64>>>(D, S, 1, isc, an);
   GyncSolverOpts o = {1e-6, 1e-6, 0, 0, 100000};
   cudaFuncSetAttribute(gync_loglik_tm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GyncWorkTm::kSmemBytes);
-  gync_loglik_tm_kernel<<<148, 128, GyncWorkTm::kSmemBytes>>>(X, N, D, isc, an, 1, nullptr, o, LL, nullptr, nullptr, nullptr, cnt);
+  gync_loglik_tm_kernel<<<148, 128, GyncWorkTm::kSmemBytes>>>(X, N, D, isc, an, 1, nullptr, o, LL, nullptr, nullptr, nullptr, cnt, nullptr);
   cudaError_t e = cudaDeviceSynchronize(); printf("%s LL0=%f\n", cudaGetErrorString(e), LL[0]);
   long long h[8]; cudaMemcpyFromSymbol(h, gync_phase_clk, sizeof(h));
   const char* nm[] = {"rhs_w", "lu", "lusolve x6", "stage combos (TMEM) x5", "rhs x5", "e += v (TMEM) x5", "norm", "outside step"};
