@@ -220,7 +220,6 @@ def main():
     barrier()
     launches = int(lib.gync_launch_count() - l0)
     ms_dev = max_over_ranks(sum(a.elapsed_time(b) for a, b in evs) / args.steps)
-    clk = clocks.stop() if rank == 0 else None
     value = world * N_SAMPLES / (ms_dev * 1e-3)
 
     # ---- roofline of the dominant kernel (the solver): counted work / kernel time vs measured FP64 peak
@@ -255,17 +254,25 @@ def main():
     assert Xnp.flags.f_contiguous
     step_e2e()
     barrier()
+    n_e2e = max(args.steps, 5)
     t0 = time.perf_counter()
     e2e_steps = []
-    for _ in range(args.steps):
+    for _ in range(n_e2e):
         t1 = time.perf_counter()
         step_e2e()
         e2e_steps.append((time.perf_counter() - t1) * 1e3)
     barrier()
-    ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+    ms_e2e_mean = max_over_ranks((time.perf_counter() - t0) * 1e3 / n_e2e)
+    # The shared hosts of this pool stall a process for 100-700 ms now and then (seen with and without this library: the
+    # kernel's event time stays within 1 % while the wall time of an occasional step doubles), so the end-to-end figure
+    # is the MEDIAN step; the mean and every step are reported beside it.
+    ms_e2e = max_over_ranks(float(np.median(e2e_steps)))
+    clk = clocks.stop() if rank == 0 else None          # sampled over BOTH timed regions (device-resident and end-to-end)
     e2e = {"value": world * N_SAMPLES / (ms_e2e * 1e-3), "unit": UNIT,
            "h2d_bytes_per_step": int(N_SAMPLES * 116 * 8 + 124 * 8 + 8), "d2h_bytes_per_step": int(N_SAMPLES * 12),
-           "ms_per_step": ms_e2e, "ms_each_step_rank0": e2e_steps, "llh_checksum": float(np.nansum(LLh[np.isfinite(LLh)]))}
+           "ms_per_step": ms_e2e, "steps": n_e2e, "statistic": "median step (max over ranks)", "ms_per_step_mean": ms_e2e_mean,
+           "value_from_mean": world * N_SAMPLES / (ms_e2e_mean * 1e-3), "ms_each_step_rank0": e2e_steps,
+           "llh_checksum": float(np.nansum(LLh[np.isfinite(LLh)]))}
 
     # ---- cfg 3 pipeline (device-resident): 1e5 x 40 likelihood matrix -> WeightedChain normalisation -> 100 EM steps
     cfg3 = None

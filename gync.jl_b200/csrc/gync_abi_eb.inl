@@ -281,7 +281,7 @@ int gync_likelihoodmat(const double* xs, int64_t I, const double* ys, int64_t J,
   if (int rc = lmat_launch(dA.as<double>(), I, 1, D, dB.as<double>(), J, 1, D, D, dS.as<double>(), renormalize,
                            dL.as<double>(), g_stream)) return rc;
   CK(cudaMemcpyAsync(L, dL.p, sizeof(double) * I * J, cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaStreamSynchronize(g_stream));
+  CK(wait_stream(g_stream));
   return GYNC_OK;
 }
 
@@ -308,7 +308,7 @@ int gync_phi_batch(const double* X, int64_t N, const gync_solver_opts* opts, dou
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(Yphi, dP.p, sizeof(double) * N * 124, cudaMemcpyDeviceToHost, g_stream));
   if (status) CK(cudaMemcpyAsync(status, dSt.p, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaStreamSynchronize(g_stream));
+  CK(wait_stream(g_stream));
   return GYNC_OK;
 }
 
@@ -332,7 +332,7 @@ int gync_projectsimplex(double* yv, int64_t K) {
   // relstep = 1: movefromboundary is the identity, the result is the projection itself
   if (int rc = eb_ascent_step(&tmp, dw.as<double>(), nullptr, 0.0, nullptr, 0.0, 0.0, 1.0, nullptr, g_stream)) return rc;
   CK(cudaMemcpyAsync(yv, dw.p, sizeof(double) * K, cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaStreamSynchronize(g_stream));
+  CK(wait_stream(g_stream));
   return GYNC_OK;
 }
 
@@ -398,7 +398,7 @@ int gync_ebmodel_zshard_finish(gync_ebmodel* m, const double* scal /* 2: global 
   CK(cudaMemcpyAsync(m->scal + 2, scal, 2 * sizeof(double), cudaMemcpyHostToDevice, g_stream));
   lmat_finish(m->Lzt, m->Z * m->K, m->scal + 2, g_stream);
   CK(cudaGetLastError());
-  CK(cudaStreamSynchronize(g_stream));
+  CK(wait_stream(g_stream));
   return GYNC_OK;
 }
 
@@ -444,7 +444,7 @@ int gync_ebmodel_matrices(gync_ebmodel* m, double* Ld, double* Lz) {
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(Lz, tmp.p, sizeof(double) * m->Z * m->K, cudaMemcpyDeviceToHost, g_stream));
   }
-  CK(cudaStreamSynchronize(g_stream));
+  CK(wait_stream(g_stream));
   return GYNC_OK;
 }
 
@@ -465,7 +465,7 @@ int gync_ebmodel_logl(gync_ebmodel* m, const double* w, double* out) {
   g_launches += 1;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, m->scal, sizeof(double), cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaStreamSynchronize(g_stream));
+  CK(wait_stream(g_stream));
   return GYNC_OK;
 }
 
@@ -475,7 +475,7 @@ int gync_ebmodel_dlogl(gync_ebmodel* m, const double* w, double* d) {
   CK(cudaMemcpyAsync(m->w, w, sizeof(double) * m->K, cudaMemcpyHostToDevice, g_stream));
   if (int rc = eb_dlogl(m, m->w, m->ga, g_stream)) return rc;
   CK(cudaMemcpyAsync(d, m->ga, sizeof(double) * m->K, cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaStreamSynchronize(g_stream));
+  CK(wait_stream(g_stream));
   return GYNC_OK;
 }
 
@@ -495,7 +495,7 @@ int gync_ebmodel_hz(gync_ebmodel* m, const double* w, const double* wz, double* 
   g_launches += 1;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, m->scal, sizeof(double), cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaStreamSynchronize(g_stream));
+  CK(wait_stream(g_stream));
   return GYNC_OK;
 }
 
@@ -510,7 +510,7 @@ int gync_ebmodel_dhz(gync_ebmodel* m, const double* w, int32_t cont, double* d) 
   int nanflag = 0;
   CK(cudaMemcpyAsync(d, m->gb, sizeof(double) * m->K, cudaMemcpyDeviceToHost, g_stream));
   CK(cudaMemcpyAsync(&nanflag, m->flags + 1, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaStreamSynchronize(g_stream));
+  CK(wait_stream(g_stream));
   if (nanflag) return fail(GYNC_ERR_NUMERIC, "encountered NaN in dhz");
   return GYNC_OK;
 }
@@ -526,7 +526,7 @@ int gync_ebmodel_em(gync_ebmodel* m, double* w, int32_t niter, double* history) 
   if (int rc = gync_em_iterate_dev(m->w, m->Ld, m->K, (int32_t)m->M, niter, history ? dH.as<double>() : nullptr, g_stream)) return rc;
   CK(cudaMemcpyAsync(w, m->w, sizeof(double) * m->K, cudaMemcpyDeviceToHost, g_stream));
   if (history) CK(cudaMemcpyAsync(history, dH.p, sizeof(double) * m->K * niter, cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaStreamSynchronize(g_stream));
+  CK(wait_stream(g_stream));
   return GYNC_OK;
 }
 
@@ -556,7 +556,7 @@ int gync_ebmodel_mple(gync_ebmodel* m, double* w, double reg, double h, int32_t 
   CK(cudaMemcpyAsync(w, m->w, sizeof(double) * m->K, cudaMemcpyDeviceToHost, s));
   if (history) CK(cudaMemcpyAsync(history, dH.p, sizeof(double) * m->K * nsteps, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(&nanflag, m->flags + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
+  CK(wait_stream(s));
   if (nanflag) return fail(GYNC_ERR_NUMERIC, "encountered NaN in dhz");
   return GYNC_OK;
 }

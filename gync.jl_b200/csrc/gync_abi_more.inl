@@ -18,7 +18,7 @@ int gync_logprior_batch(const double* X, int64_t N, const gync_prior* prior, dou
   g_launches += 1;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(LP, dL.p, sizeof(double) * N, cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaStreamSynchronize(g_stream));
+  CK(wait_stream(g_stream));
   return GYNC_OK;
 }
 
@@ -162,7 +162,7 @@ static int mcmc_run_impl(double* state, double* logf, int64_t C, const double* c
     const long long before = min_it;
     if (int rc = round(0, Kr)) return rc;
     CK(cudaMemcpyAsync(&min_it, dMin.p, sizeof(long long), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    CK(wait_stream(s));
     if (amm && C == 1) {     // every adaptive slot costs a factorisation: follow the acceptance rate with the depth
       const long long used = min_it - before;
       if (used >= Kr) Kr = std::min(K, 2 * Kr);
@@ -180,7 +180,7 @@ static int mcmc_run_impl(double* state, double* logf, int64_t C, const double* c
     CK(cudaMemcpyAsync(amm->Mvv, aMvv.p, sizeof(double) * C * d2, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(amm->SigmaLm, aLm.p, sizeof(double) * C * d2, cudaMemcpyDeviceToHost, s));
   }
-  CK(cudaStreamSynchronize(s));
+  CK(wait_stream(s));
   return GYNC_OK;
 }
 
@@ -292,7 +292,7 @@ int gync_wc_normalize(const double* LL, const double* logprior, const int64_t* c
   CK(cudaMemcpyAsync(L, dLL.p, sizeof(double) * K * M, cudaMemcpyDeviceToHost, g_stream));
   CK(cudaMemcpyAsync(weights, dW.p, sizeof(double) * K, cudaMemcpyDeviceToHost, g_stream));
   CK(cudaMemcpyAsync(density, dDn.p, sizeof(double) * K, cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaStreamSynchronize(g_stream));
+  CK(wait_stream(g_stream));
   return GYNC_OK;
 }
 

@@ -88,6 +88,19 @@ GyncSolverOpts to_opts(const gync_solver_opts* o) {
 
 inline unsigned blocks_for(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
+// Wait for a stream WITHOUT spinning: a blocking-sync event puts the host thread to sleep.  The host-buffer entry points
+// wait for hundreds of milliseconds on the solver kernel; a spinning cudaStreamSynchronize burns a core for that long,
+// which on CPU-quota'd hosts showed up as sporadic 100-700 ms stalls of the calling process.
+cudaError_t wait_stream(cudaStream_t s) {
+  cudaEvent_t ev;
+  cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming);
+  if (e != cudaSuccess) return e;
+  e = cudaEventRecord(ev, s);
+  if (e == cudaSuccess) e = cudaEventSynchronize(ev);
+  cudaEventDestroy(ev);
+  return e;
+}
+
 // opt in to the large dynamic shared-memory carve-out the solver kernels need
 template <class K>
 int prep_solver_kernel(K kern, size_t smem, int block) {
@@ -535,7 +548,7 @@ static int loglik_batch_multi(const double* X, int64_t N, const double* data, in
   for (int i = 0; i < nd; ++i) {
     if (parts[i].n == 0) continue;
     if (int rc = use_device(i)) return rc;
-    CK(cudaStreamSynchronize(g_stream));
+    CK(wait_stream(g_stream));
     parts[i] = Part();           // free on the owning device
   }
   return use_device(0);
@@ -569,7 +582,7 @@ int gync_loglik_batch(const double* X, int64_t N, const double* data, int32_t M,
   if (Ymeas) CK(cudaMemcpyAsync(Ymeas, dY.p, sizeof(double) * N * GYNC_NT_MEAS * GYNC_NMEAS, cudaMemcpyDeviceToHost, g_stream));
   if (status) CK(cudaMemcpyAsync(status, dSt.p, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, g_stream));
   if (nsteps) CK(cudaMemcpyAsync(nsteps, dNs.p, sizeof(int32_t) * N * 2, cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaStreamSynchronize(g_stream));
+  CK(wait_stream(g_stream));
   return GYNC_OK;
 }
 
@@ -599,7 +612,7 @@ static int solve_common(const double* X, const double* Y0, const double* P, int6
                                  dY.as<double>(), dSt.as<int32_t>(), g_stream)) return rc;
   CK(cudaMemcpyAsync(Y, dY.p, sizeof(double) * N * nT * GYNC_NY, cudaMemcpyDeviceToHost, g_stream));
   if (status) CK(cudaMemcpyAsync(status, dSt.p, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaStreamSynchronize(g_stream));
+  CK(wait_stream(g_stream));
   return GYNC_OK;
 }
 
@@ -666,7 +679,7 @@ int gync_em_iterate(double* w, const double* L, int64_t K, int32_t M, int32_t ni
   if (rc) return rc;
   CK(cudaMemcpyAsync(w, dw.p, sizeof(double) * K, cudaMemcpyDeviceToHost, g_stream));
   if (history) CK(cudaMemcpyAsync(history, dH.p, sizeof(double) * K * niter, cudaMemcpyDeviceToHost, g_stream));
-  CK(cudaStreamSynchronize(g_stream));
+  CK(wait_stream(g_stream));
   return GYNC_OK;
 }
 
