@@ -13,7 +13,7 @@
 
 #define GYNC_SCHED_NF 117            /* 1 + 116 log-parameters */
 #define GYNC_SCHED_NB 1024           /* cost buckets of the counting sort */
-#define GYNC_SCHED_MAXS 16384        /* samples used for a refit */
+#define GYNC_SCHED_MAXS 4096         /* samples used for a refit (117 unknowns) */
 
 struct GyncSchedModel {              // device-resident
   double beta[GYNC_SCHED_NF];
