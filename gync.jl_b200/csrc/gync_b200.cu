@@ -121,6 +121,7 @@ struct SchedState {
   double *G = nullptr, *b = nullptr, *Phi = nullptr, *target = nullptr, *pred = nullptr;
   int *order = nullptr, *hist = nullptr, *steps = nullptr;
   unsigned long long* minmax = nullptr;
+  cudaEvent_t busy = nullptr;      // last use of these buffers: calls on other streams wait for it
   int64_t cap = 0;
   bool fitted = false;
   int device = -1;
@@ -131,6 +132,7 @@ struct SchedState {
       cudaSetDevice(device);
       for (void* p : {(void*)mdl, (void*)G, (void*)b, (void*)Phi, (void*)target, (void*)pred, (void*)order, (void*)hist, (void*)steps, (void*)minmax})
         if (p) cudaFree(p);
+      if (busy) cudaEventDestroy(busy);
       cudaSetDevice(cur);
     }
     *this = SchedState();
@@ -155,6 +157,7 @@ struct SchedState {
     CK(cudaMalloc((void**)&steps, sizeof(int) * 2 * cap));
     CK(cudaMalloc((void**)&hist, sizeof(int) * GYNC_SCHED_NB));
     CK(cudaMalloc((void**)&minmax, sizeof(unsigned long long) * 2));
+    CK(cudaEventCreateWithFlags(&busy, cudaEventDisableTiming));
     return GYNC_OK;
   }
 };
@@ -173,7 +176,7 @@ int launch_loglik(const double* dX, int64_t N, const double* d_data, const doubl
   const int64_t want = (N + GYNC_TM_NSLOT - 1) / GYNC_TM_NSLOT;
   const int nb = (int)std::min<int64_t>(want, (int64_t)g_num_sms);
   // scheduling pays once there is more than one solve per lane; below that every lane starts at once anyway
-  const bool sched = !getenv("GYNC_NO_SCHED") && 4 * N >= 5 * (int64_t)g_num_sms * GYNC_TM_NSLOT && N < (1LL << 31);
+  bool sched = !getenv("GYNC_NO_SCHED") && 4 * N >= 5 * (int64_t)g_num_sms * GYNC_TM_NSLOT && N < (1LL << 31);
   int* order = nullptr;
   int32_t* steps = d_nsteps;
   SchedState* st = nullptr;
@@ -181,7 +184,14 @@ int launch_loglik(const double* dX, int64_t N, const double* d_data, const doubl
     int slot = 0;
     for (size_t i = 0; i < g_devs.size(); ++i) if (g_devs[i].device == g_device) slot = (int)i;
     st = &g_sched[slot];
-    if (int rc = st->ensure(N, g_device)) return rc;
+    if (st->ensure(N, g_device) != GYNC_OK) {       // no memory for the scheduler: run unordered
+      (void)cudaGetLastError();
+      st->release();
+      sched = false;
+    }
+  }
+  if (sched) {
+    CK(cudaStreamWaitEvent(s, st->busy, 0));        // the buffers are shared by every stream of this device
     if (!steps) steps = st->steps;
     if (st->fitted) {
       CK(cudaMemsetAsync(st->minmax, 0xFF, sizeof(unsigned long long), s));
@@ -207,6 +217,7 @@ int launch_loglik(const double* dX, int64_t N, const double* d_data, const doubl
     gync_sched_fit_kernel<<<1, 128, fit_smem, s>>>(st->G, st->b, st->mdl);
     g_launches += 3;
     st->fitted = true;
+    CK(cudaEventRecord(st->busy, s));
   }
   CK(cudaGetLastError());
   return GYNC_OK;
