@@ -554,3 +554,23 @@ def test_wc_normalize_sharded_kernels(gpu):
     nz = l0 > 0
     assert np.array_equal(Lg == 0, l0 == 0) and relerr(Lg[nz], l0[nz]) < 1e-12
     assert relerr(wg, w0) < 1e-14 and relerr(dg, d0) < 1e-12
+
+
+def test_learned_queue_order_is_result_neutral(gpu):
+    """csrc/gync_sched.cuh: from the second batch on the sample queue is ordered by a cost model refitted on the device;
+    log-likelihoods, step counts and statuses must be bit-identical to the unordered run (GYNC_NO_SCHED=1)."""
+    X = near_set(40_000, 77)
+    X[123, 5] = np.nan                      # a sample that fails at load time is scheduled like any other
+    c = gpu.Config()
+    runs = {}
+    for name, env in (("first", None), ("ordered", None), ("unordered", "1")):
+        if env:
+            os.environ["GYNC_NO_SCHED"] = env
+        try:
+            runs[name] = gpu.loglik_matrix(X, [c.data], [0.1], want_steps=True)
+        finally:
+            os.environ.pop("GYNC_NO_SCHED", None)
+    for name in ("first", "ordered"):
+        for a, b in zip(runs[name], runs["unordered"]):
+            assert np.array_equal(a, b, equal_nan=True), name
+    assert runs["ordered"][1][123] != 0 and runs["ordered"][0][123, 0] == -np.inf
