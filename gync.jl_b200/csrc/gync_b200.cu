@@ -76,6 +76,36 @@ struct DBuf {
   template <class T> T* as() { return static_cast<T*>(p); }
 };
 
+// Grow-only staging buffers of the blocking host-buffer entry points (one set per device slot): repeated calls of the
+// same size reuse them instead of paying cudaMalloc / cudaFree (both synchronise the device) around every batch.
+struct StagePool {
+  void* p[8] = {nullptr};
+  size_t cap[8] = {0};
+  int device = -1;
+  void* get(int id, size_t bytes, int dev) {
+    if (device != dev) { release(); device = dev; }
+    if (cap[id] < bytes || !p[id]) {
+      if (p[id]) cudaFree(p[id]);
+      p[id] = nullptr; cap[id] = 0;
+      const size_t want = bytes ? bytes + bytes / 8 : 8;
+      if (cudaMalloc(&p[id], want) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+      cap[id] = want;
+    }
+    return p[id];
+  }
+  void release() {
+    if (device >= 0) {
+      int cur = 0;
+      cudaGetDevice(&cur);
+      cudaSetDevice(device);
+      for (int i = 0; i < 8; ++i) { if (p[i]) cudaFree(p[i]); p[i] = nullptr; cap[i] = 0; }
+      cudaSetDevice(cur);
+    }
+    device = -1;
+  }
+};
+StagePool g_stage[8];
+
 GyncSolverOpts to_opts(const gync_solver_opts* o) {
   GyncSolverOpts r;
   r.rtol = (o && o->rtol > 0) ? o->rtol : 1e-8;
@@ -474,6 +504,7 @@ int gync_init(int device) {
 void gync_shutdown(void) {
   for (EmLaunchState& st : g_em_local) st.release();
   for (SchedState& st : g_sched) st.release();
+  for (StagePool& sp : g_stage) sp.release();
   if (g_em_scratch.partials) {
     if (g_em_scratch.device >= 0) cudaSetDevice(g_em_scratch.device);
     cudaFree(g_em_scratch.partials);
@@ -574,25 +605,27 @@ int gync_loglik_batch(const double* X, int64_t N, const double* data, int32_t M,
   if (N == 0) return GYNC_OK;
   if (g_devs.size() > 1 && N >= (int64_t)g_devs.size() * 256)
     return loglik_batch_multi(X, N, data, M, sigma_rho, opts, LL, Ymeas, status, nsteps);
-  DBuf dX, dD, dS, dLL, dY, dSt, dNs;
-  CK(dX.alloc(sizeof(double) * N * GYNC_NX));
-  CK(dD.alloc(sizeof(double) * 124 * M));
-  CK(dS.alloc(sizeof(double) * M));
-  CK(dLL.alloc(sizeof(double) * N * M));
-  if (Ymeas) CK(dY.alloc(sizeof(double) * N * GYNC_NT_MEAS * GYNC_NMEAS));
-  CK(dSt.alloc(sizeof(int32_t) * N));
-  if (nsteps) CK(dNs.alloc(sizeof(int32_t) * N * 2));
-  CK(cudaMemcpyAsync(dX.p, X, sizeof(double) * N * GYNC_NX, cudaMemcpyHostToDevice, g_stream));
-  CK(cudaMemcpyAsync(dD.p, data, sizeof(double) * 124 * M, cudaMemcpyHostToDevice, g_stream));
-  CK(cudaMemcpyAsync(dS.p, sigma_rho, sizeof(double) * M, cudaMemcpyHostToDevice, g_stream));
-  int rc = gync_loglik_batch_dev(dX.as<double>(), N, dD.as<double>(), M, dS.as<double>(), opts, dLL.as<double>(),
-                                 Ymeas ? dY.as<double>() : nullptr, dSt.as<int32_t>(),
-                                 nsteps ? dNs.as<int32_t>() : nullptr, g_stream);
+  int slot = 0;
+  for (size_t i = 0; i < g_devs.size(); ++i) if (g_devs[i].device == g_device) slot = (int)i;
+  StagePool& sp = g_stage[slot];
+  double* dX = (double*)sp.get(0, sizeof(double) * N * GYNC_NX, g_device);
+  double* dD = (double*)sp.get(1, sizeof(double) * 124 * M, g_device);
+  double* dS = (double*)sp.get(2, sizeof(double) * M, g_device);
+  double* dLL = (double*)sp.get(3, sizeof(double) * N * M, g_device);
+  double* dY = Ymeas ? (double*)sp.get(4, sizeof(double) * N * GYNC_NT_MEAS * GYNC_NMEAS, g_device) : nullptr;
+  int32_t* dSt = (int32_t*)sp.get(5, sizeof(int32_t) * N, g_device);
+  int32_t* dNs = nsteps ? (int32_t*)sp.get(6, sizeof(int32_t) * N * 2, g_device) : nullptr;
+  if (!dX || !dD || !dS || !dLL || !dSt || (Ymeas && !dY) || (nsteps && !dNs))
+    return fail(GYNC_ERR_NOMEM, "gync_loglik_batch: out of device memory");
+  CK(cudaMemcpyAsync(dX, X, sizeof(double) * N * GYNC_NX, cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemcpyAsync(dD, data, sizeof(double) * 124 * M, cudaMemcpyHostToDevice, g_stream));
+  CK(cudaMemcpyAsync(dS, sigma_rho, sizeof(double) * M, cudaMemcpyHostToDevice, g_stream));
+  int rc = gync_loglik_batch_dev(dX, N, dD, M, dS, opts, dLL, dY, dSt, dNs, g_stream);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(LL, dLL.p, sizeof(double) * N * M, cudaMemcpyDeviceToHost, g_stream));
-  if (Ymeas) CK(cudaMemcpyAsync(Ymeas, dY.p, sizeof(double) * N * GYNC_NT_MEAS * GYNC_NMEAS, cudaMemcpyDeviceToHost, g_stream));
-  if (status) CK(cudaMemcpyAsync(status, dSt.p, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, g_stream));
-  if (nsteps) CK(cudaMemcpyAsync(nsteps, dNs.p, sizeof(int32_t) * N * 2, cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaMemcpyAsync(LL, dLL, sizeof(double) * N * M, cudaMemcpyDeviceToHost, g_stream));
+  if (Ymeas) CK(cudaMemcpyAsync(Ymeas, dY, sizeof(double) * N * GYNC_NT_MEAS * GYNC_NMEAS, cudaMemcpyDeviceToHost, g_stream));
+  if (status) CK(cudaMemcpyAsync(status, dSt, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, g_stream));
+  if (nsteps) CK(cudaMemcpyAsync(nsteps, dNs, sizeof(int32_t) * N * 2, cudaMemcpyDeviceToHost, g_stream));
   CK(wait_stream(g_stream));
   return GYNC_OK;
 }
