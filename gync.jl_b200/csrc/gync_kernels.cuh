@@ -276,11 +276,16 @@ __device__ __forceinline__ double gync_rodas4_step_tm(GyncWorkTm& W, const doubl
   GYNC_TICK(2)
 #pragma unroll 1
   for (int s = 0; s < 5; ++s) {
-    gync_tm_store_vec(W.tm + GYNC_TM_COL_K + 2 * GYNC_NY * s, W.e);      // park k_{s+1}
+    // park k_{s+1} for the later stages (k5 is consumed right here and never read again); its own contribution to
+    // this stage comes from the registers it still sits in — a third of the stage sums' tensor-memory loads
+    if (s < 4) gync_tm_store_vec(W.tm + GYNC_TM_COL_K + 2 * GYNC_NY * s, W.e);
+    {
+      const double a = RD_TA[s][s], c = RD_TC[s][s];
 #pragma unroll
-    for (int i = 0; i < GYNC_NY; ++i) { W.yn[i] = W.y[i]; W.e[i] = 0.0; }
+      for (int i = 0; i < GYNC_NY; ++i) { W.yn[i] = fma(a, W.e[i], W.y[i]); W.e[i] = c * W.e[i]; }
+    }
 #pragma unroll 1
-    for (int j = 0; j <= s; ++j) {
+    for (int j = 0; j < s; ++j) {
       const double a = RD_TA[s][j], c = RD_TC[s][j];
       const uint32_t ta = W.tm + GYNC_TM_COL_K + 2 * GYNC_NY * j;
 #pragma unroll
