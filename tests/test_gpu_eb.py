@@ -50,6 +50,13 @@ def test_likelihoodmat_vs_oracle(gpu):
     ys[2][1, 1] = np.nan
     L = eb.likelihoodmat_nanfast(xs, ys, eb.MatrixNormalCentered(sig))
     assert relerr(L, eo.likelihoodmat_nanfast(xs, ys, sig)) < 1e-11
+    # more entries per sample than the kernel's 1/sigma table holds (D = 600 > 512): the dividing path
+    sig = rng.random((40, 15)) + 0.5
+    xs = [rng.standard_normal((40, 15)) * 0.1 for _ in range(9)]
+    ys = [rng.standard_normal((40, 15)) * 0.1 for _ in range(70)]
+    xs[3][7, 2] = np.nan
+    L = eb.likelihoodmat_nanfast(xs, ys, eb.MatrixNormalCentered(sig))
+    assert relerr(L, eo.likelihoodmat_nanfast(xs, ys, sig)) < 1e-10
 
 
 def test_likelihoodmat_device_strides_and_symmetry(gpu):

@@ -240,3 +240,28 @@ def test_save_load_roundtrip(built, tmp_path):
     assert (v.logf, v.iteration, v.naccept, v.seed, v.m) == (w.logf, w.iteration, w.naccept, w.seed, w.m)
     assert np.array_equal(v.state, w.state) and np.array_equal(v.SigmaL, w.SigmaL) and np.array_equal(v.SigmaLm, w.SigmaLm)
     assert l.config.rtol is None and np.array_equal(l.config.priory0.means, np.ones((31, 33)))
+
+
+def test_eb_host_mirror_argument_checks(built):
+    """Host mirror of src/eb (gync.jl_b200/eb.py): what does not need the device — weights helpers, the pieces that stay
+    on the host, and the refusals (no silent CPU fallback for unsupported measurement-error types / autodiff)."""
+    import eb_oracle as eo
+    from gync_b200 import eb
+    assert np.allclose(eb.uniformweights(4), 0.25) and np.allclose(eb.uniformweights([1, 2, 3, 4, 5]), 0.2)   # likelihoodmodel.jl:22-24
+    w = np.array([0.2, 0.3, 0.5])
+    assert np.array_equal(eb.repeatweights(w, [0] * 6), eo.repeatweights(w, 6))                                # regularizers.jl:16-19
+    g = np.array([1.0, -2.0, 0.5])
+    assert np.allclose(eb.psi_S(w, g), eo.psi_S(w, g)) and abs(eb.psi_S(w, g).sum() - 1) < 1e-15                # projectsimplex.jl:48-53
+    assert np.array_equal(eb.movefromboundary(np.array([0.5, 0.5]), np.array([1.0, 0.0])), [0.75, 0.25])        # gradientascent.jl:19-25
+    assert np.allclose(eb.model_measerrors, [12.0, 1.0, 40.0, 1.5])                                            # model.jl:8
+    d = eb.MatrixNormalCentered(np.ones((31, 4)))
+    assert d == eb.MatrixNormalCentered(np.ones((31, 4))) and hash(d) == hash(eb.MatrixNormalCentered(np.ones((31, 4))))
+    with pytest.raises(NotImplementedError):
+        eb.likelihoodmat([np.zeros((31, 4))], [np.zeros((31, 4))], "MvNormal")      # the reference's element-wise fallback is not ported
+    with pytest.raises(NotImplementedError):
+        eb.gradientascent(lambda w_: w_, w, 3, 0.1, autodiff=True)
+    with pytest.raises(TypeError):
+        eb.projectsimplex_bang([0.5, 0.5])
+    m = eb.LikelihoodModel([0], [np.zeros((31, 4))], [], [np.zeros((31, 4))], "not a MatrixNormalCentered")
+    with pytest.raises(NotImplementedError):
+        m.handle()
