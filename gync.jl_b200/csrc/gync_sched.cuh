@@ -30,9 +30,15 @@ gync_sched_predict_kernel(const double* __restrict__ X, int64_t N, const GyncSch
   double p = 0.0;
   if (n < N) {
     p = mdl->beta[0];
-    for (int f = 1; f < GYNC_SCHED_NF; ++f)
-      p = fma(mdl->beta[f], gync_sched_feature(__ldg(X + n + N * (f - 1))) - mdl->ref[f], p);
-    if (!(p == p)) p = 1e300;                      // NaN inputs: run them first, they fail fast
+    double chk = 0.0;
+    for (int f = 1; f < GYNC_SCHED_NF; ++f) {
+      const double x = __ldg(X + n + N * (f - 1));
+      chk += x * 0.0;                              // NaN / Inf anywhere -> NaN
+      p = fma(mdl->beta[f], gync_sched_feature(x) - mdl->ref[f], p);
+    }
+    // samples that fail at load time (non-finite input, e.g. Metropolis proposals outside the prior) cost nothing:
+    // they go last, where they fill the tail for free
+    if (!(chk == 0.0) || !(p == p)) p = 0.0;
     p = (p > 0.0) ? fmin(p, 1e300) : 0.0;          // non-negative (and never -0.0): the bit patterns order like the values
     pred[n] = p;
   }
@@ -95,19 +101,24 @@ gync_sched_features_kernel(const double* __restrict__ X, int64_t N, int S, int64
                            double* __restrict__ Phi, double* __restrict__ target, GyncSchedModel* __restrict__ mdl) {
   const int s = blockIdx.x;
   const int64_t n = (int64_t)s * stride;
+  // a sample with a non-finite entry never runs a step: it carries no information about the cost of the others and is
+  // left out of the fit (an all-zero row)
+  double chk = 0.0;
+  for (int f = threadIdx.x; f < GYNC_SCHED_NF - 1; f += blockDim.x) chk += __ldg(X + n + N * f) * 0.0;
+  const int bad = __syncthreads_or(!(chk == 0.0));
   for (int f = threadIdx.x; f < GYNC_SCHED_NF; f += blockDim.x) {
-    double v = 1.0;
+    double v = bad ? 0.0 : 1.0;
     if (f > 0) {
       const double r = gync_sched_feature(__ldg(X + N * (f - 1)));          // sample 0 is the offset
-      v = gync_sched_feature(__ldg(X + n + N * (f - 1))) - r;
-      if (!(v == v) || fabs(v) > 1e6) v = 0.0;
-      if (s == 0) mdl->ref[f] = r;
+      v = bad ? 0.0 : gync_sched_feature(__ldg(X + n + N * (f - 1))) - r;
+      if (!(v == v) || fabs(v) > 1e3) v = 0.0;
+      if (s == 0) mdl->ref[f] = (r == r) ? r : 0.0;
     } else if (s == 0) {
       mdl->ref[0] = 0.0;
     }
     Phi[(size_t)s * GYNC_SCHED_NF + f] = v;
   }
-  if (threadIdx.x == 0) target[s] = (double)(nsteps[n] + nsteps[n + N]);
+  if (threadIdx.x == 0) target[s] = bad ? 0.0 : (double)(nsteps[n] + nsteps[n + N]);
 }
 
 // G[i][j] = sum_s Phi[s][i] Phi[s][j],  b[i] = sum_s Phi[s][i] target[s]   (one CTA per row i, fixed order)
