@@ -14,6 +14,14 @@
  *   - there is NO CPU fallback: without a CUDA device every compute call returns GYNC_ERR_CUDA.
  *   - `*_dev` variants take DEVICE pointers and a cudaStream_t (as void*) and do not
  *     synchronise; they are what a host that keeps data resident in HBM calls.
+ *
+ * Environment switches (read per call; for A/B measurements and debugging, never needed for correctness):
+ *   GYNC_NO_SCHED=1        run the solver's sample queue in input order (default: longest-first by a cost model the
+ *                          library refits on the device after every batch; results are bit-identical either way)
+ *   GYNC_MCMC_SPEC=K       speculation depth of the Metropolis rounds (default: fills the sample slots about twice)
+ *   GYNC_DHZ_TWO_PASS=1    dhz as the reference's two matvecs instead of the one-pass row-fused kernel
+ *   GYNC_EM_NO_RESIDENT=1  EM always streams L from HBM (default: shared-memory resident when this GPU's rows fit)
+ *   GYNC_SOLVE_SM=1        gync/forwardsol through the older shared-memory solver kernel
  */
 #ifndef GYNC_B200_H
 #define GYNC_B200_H
