@@ -49,7 +49,8 @@ def near_set(n, seed=SEED):
 def workload_config(n_gpus):
     return {"workload": "batched GynCycle forward solve + log-likelihood, 1e5 synthetic parameter vectors (near set) x 1 "
                         "patient (Lausanne 1) per GPU", "n_samples_per_gpu": N_SAMPLES, "n_patients": 1,
-            "rtol": RTOL, "atol": ATOL, "solver": "RODAS4 adaptive, sparse LU (165 nnz), state in smem+TMEM, 112 samples/SM",
+            "rtol": RTOL, "atol": ATOL, "solver": "RODAS4 adaptive, sparse LU (165 nnz), state in smem+TMEM, 128 samples/SM, persistent lanes, "
+                                                "longest-first sample queue (cost model refitted on the device after every batch)",
             "l2_policy": "solver state lives in shared memory/registers; the 93 MB sample matrix is read once per step "
                          "(each step re-reads it from HBM/L2 — inputs are not larger than L2, a 256 MB buffer is written "
                          "between timed steps to flush it)",
