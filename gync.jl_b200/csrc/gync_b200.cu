@@ -193,6 +193,51 @@ struct SchedState {
 };
 SchedState g_sched[8];
 
+// Order the queue of a batch of N samples X (N x 116) by predicted cost, if a model has been fitted; returns the state to
+// hand to sched_refit after the solver kernel, or NULL when scheduling is off / does not pay / cannot allocate.
+// *steps is replaced by an internal buffer when the caller did not ask for step counts (the refit needs them).
+SchedState* sched_prepare(const double* dX, int64_t N, cudaStream_t s, int** order, int32_t** steps) {
+  *order = nullptr;
+  // scheduling pays once there is more than one solve per lane; below that every lane starts at once anyway
+  if (getenv("GYNC_NO_SCHED") || !dX || 4 * N < 5 * (int64_t)g_num_sms * GYNC_TM_NSLOT || N >= (1LL << 31)) return nullptr;
+  int slot = 0;
+  for (size_t i = 0; i < g_devs.size(); ++i) if (g_devs[i].device == g_device) slot = (int)i;
+  SchedState* st = &g_sched[slot];
+  if (st->ensure(N, g_device) != GYNC_OK) {         // no memory for the scheduler: run unordered
+    (void)cudaGetLastError();
+    st->release();
+    return nullptr;
+  }
+  if (cudaStreamWaitEvent(s, st->busy, 0) != cudaSuccess) return nullptr;     // the buffers are shared by every stream of this device
+  if (!*steps) *steps = st->steps;
+  if (st->fitted) {
+    cudaMemsetAsync(st->minmax, 0xFF, sizeof(unsigned long long), s);
+    cudaMemsetAsync(st->minmax + 1, 0, sizeof(unsigned long long), s);
+    cudaMemsetAsync(st->hist, 0, sizeof(int) * GYNC_SCHED_NB, s);
+    gync_sched_predict_kernel<<<blocks_for(N, 256), 256, 0, s>>>(dX, N, st->mdl, st->pred, st->minmax);
+    gync_sched_hist_kernel<<<blocks_for(N, 256), 256, 0, s>>>(st->pred, N, st->minmax, st->hist);
+    gync_sched_scan_kernel<<<1, GYNC_SCHED_NB, 0, s>>>(st->hist);
+    gync_sched_scatter_kernel<<<blocks_for(N, 256), 256, 0, s>>>(st->pred, N, st->minmax, st->hist, st->order);
+    g_launches += 4;
+    *order = st->order;
+  }
+  return st;
+}
+
+// refit the cost model on this batch's step counts (N x 2: accepted, rejected)
+int sched_refit(SchedState* st, const double* dX, int64_t N, const int32_t* steps, cudaStream_t s) {
+  const int S = (int)std::min<int64_t>(N, GYNC_SCHED_MAXS);
+  const size_t fit_smem = sizeof(double) * (GYNC_SCHED_NF * (GYNC_SCHED_NF + 1) + GYNC_SCHED_NF);
+  CK(cudaFuncSetAttribute(gync_sched_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fit_smem));
+  gync_sched_features_kernel<<<S, 128, 0, s>>>(dX, N, S, N / S, steps, st->Phi, st->target, st->mdl);
+  gync_sched_normal_kernel<<<GYNC_SCHED_NF, 128, 0, s>>>(st->Phi, st->target, S, st->G, st->b);
+  gync_sched_fit_kernel<<<1, 128, fit_smem, s>>>(st->G, st->b, st->mdl);
+  g_launches += 3;
+  st->fitted = true;
+  CK(cudaEventRecord(st->busy, s));
+  return GYNC_OK;
+}
+
 // One launch of the solver kernel: persistent lanes, one CTA (4 warps x 32 samples, state in shared
 // + tensor memory) per SM.  `pat` (nullable) gives every sample its own patient -> LL is N x 1.
 int launch_loglik(const double* dX, int64_t N, const double* d_data, const double* iscale, const int* allnan, int M,
@@ -205,50 +250,13 @@ int launch_loglik(const double* dX, int64_t N, const double* d_data, const doubl
   if (int rc = prep_solver_kernel(gync_loglik_tm_kernel, GyncWorkTm::kSmemBytes, 128)) return rc;
   const int64_t want = (N + GYNC_TM_NSLOT - 1) / GYNC_TM_NSLOT;
   const int nb = (int)std::min<int64_t>(want, (int64_t)g_num_sms);
-  // scheduling pays once there is more than one solve per lane; below that every lane starts at once anyway
-  bool sched = !getenv("GYNC_NO_SCHED") && 4 * N >= 5 * (int64_t)g_num_sms * GYNC_TM_NSLOT && N < (1LL << 31);
   int* order = nullptr;
   int32_t* steps = d_nsteps;
-  SchedState* st = nullptr;
-  if (sched) {
-    int slot = 0;
-    for (size_t i = 0; i < g_devs.size(); ++i) if (g_devs[i].device == g_device) slot = (int)i;
-    st = &g_sched[slot];
-    if (st->ensure(N, g_device) != GYNC_OK) {       // no memory for the scheduler: run unordered
-      (void)cudaGetLastError();
-      st->release();
-      sched = false;
-    }
-  }
-  if (sched) {
-    CK(cudaStreamWaitEvent(s, st->busy, 0));        // the buffers are shared by every stream of this device
-    if (!steps) steps = st->steps;
-    if (st->fitted) {
-      CK(cudaMemsetAsync(st->minmax, 0xFF, sizeof(unsigned long long), s));
-      CK(cudaMemsetAsync(st->minmax + 1, 0, sizeof(unsigned long long), s));
-      CK(cudaMemsetAsync(st->hist, 0, sizeof(int) * GYNC_SCHED_NB, s));
-      gync_sched_predict_kernel<<<blocks_for(N, 256), 256, 0, s>>>(dX, N, st->mdl, st->pred, st->minmax);
-      gync_sched_hist_kernel<<<blocks_for(N, 256), 256, 0, s>>>(st->pred, N, st->minmax, st->hist);
-      gync_sched_scan_kernel<<<1, GYNC_SCHED_NB, 0, s>>>(st->hist);
-      gync_sched_scatter_kernel<<<blocks_for(N, 256), 256, 0, s>>>(st->pred, N, st->minmax, st->hist, st->order);
-      g_launches += 4;
-      order = st->order;
-    }
-  }
+  SchedState* st = sched_prepare(dX, N, s, &order, &steps);
   gync_loglik_tm_kernel<<<nb, 128, GyncWorkTm::kSmemBytes, s>>>(dX, N, d_data, iscale, allnan, M, pat, so, dLL, dYmeas,
                                                                 d_status, steps, counter, order);
   g_launches += 1;
-  if (sched) {                                   // refit the cost model on this batch's step counts
-    const int S = (int)std::min<int64_t>(N, GYNC_SCHED_MAXS);
-    const size_t fit_smem = sizeof(double) * (GYNC_SCHED_NF * (GYNC_SCHED_NF + 1) + GYNC_SCHED_NF);
-    CK(cudaFuncSetAttribute(gync_sched_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fit_smem));
-    gync_sched_features_kernel<<<S, 128, 0, s>>>(dX, N, S, N / S, steps, st->Phi, st->target, st->mdl);
-    gync_sched_normal_kernel<<<GYNC_SCHED_NF, 128, 0, s>>>(st->Phi, st->target, S, st->G, st->b);
-    gync_sched_fit_kernel<<<1, 128, fit_smem, s>>>(st->G, st->b, st->mdl);
-    g_launches += 3;
-    st->fitted = true;
-    CK(cudaEventRecord(st->busy, s));
-  }
+  if (st) if (int rc = sched_refit(st, dX, N, steps, s)) return rc;
   CK(cudaGetLastError());
   return GYNC_OK;
 }
@@ -269,7 +277,12 @@ int launch_solve_grid(const double* dX, const double* dY0, const double* dP, int
     CK(cudaMemsetAsync(cnt.p, 0, sizeof(unsigned long long), s));
     if (int rc = prep_solver_kernel(gync_solve_tm_kernel, GyncWorkTm::kSmemBytes, 128)) return rc;
     const int nb = (int)std::min<int64_t>((N + GYNC_TM_NSLOT - 1) / GYNC_TM_NSLOT, (int64_t)g_num_sms);
-    gync_solve_tm_kernel<<<nb, 128, GyncWorkTm::kSmemBytes, s>>>(dX, dY0, dP, N, d_t, nT, so, dY, d_status, cnt.as<unsigned long long>());
+    int* order = nullptr;
+    int32_t* steps = nullptr;
+    SchedState* st = sched_prepare(dX, N, s, &order, &steps);      // samples given as X only (the cost model's features)
+    gync_solve_tm_kernel<<<nb, 128, GyncWorkTm::kSmemBytes, s>>>(dX, dY0, dP, N, d_t, nT, so, dY, d_status, cnt.as<unsigned long long>(),
+                                                                 order, steps);
+    if (st) if (int rc = sched_refit(st, dX, N, steps, s)) return rc;
   }
   g_launches += 1;
   CK(cudaGetLastError());

@@ -563,7 +563,8 @@ gync_solve_kernel(const double* __restrict__ X, const double* __restrict__ Y0, c
 __global__ void __launch_bounds__(128, 1)
 gync_solve_tm_kernel(const double* __restrict__ X, const double* __restrict__ Y0, const double* __restrict__ P,
                      int64_t N, const double* __restrict__ tgrid, int nT, GyncSolverOpts o,
-                     double* __restrict__ Y, int* __restrict__ status, unsigned long long* __restrict__ counter) {
+                     double* __restrict__ Y, int* __restrict__ status, unsigned long long* __restrict__ counter,
+                     const int* __restrict__ order /* nullable, gync_sched.cuh */, int* __restrict__ nsteps /* nullable, N x 2 */) {
   extern __shared__ double gync_sm[];
   __shared__ uint32_t s_tmem;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -597,6 +598,7 @@ gync_solve_tm_kernel(const double* __restrict__ X, const double* __restrict__ Y0
       if (n >= N) {
         done = true;
       } else {
+        if (order) n = order[n];
         if (X) {
           double T;
           gync_load_sample(W, [&](int k) { return __ldg(X + n + N * k); }, c_refallparms, c_sampledinds, &T);
@@ -661,6 +663,7 @@ gync_solve_tm_kernel(const double* __restrict__ X, const double* __restrict__ Y0
         if (st != GYNC_ST_OK)
           for (int64_t k = 0; k < (int64_t)nT * GYNC_NY; ++k) Y[n + N * k] = NAN;   // gyncycle.jl:18-19
         if (status) status[n] = st;
+        if (nsteps) { nsteps[n] = c.nacc; nsteps[n + N] = c.nrej; }
         active = false;
 #pragma unroll
         for (int i = 0; i < GYNC_NY; ++i) if (!(W.y[i] * 0.0 == 0.0)) W.y[i] = 1.0;
