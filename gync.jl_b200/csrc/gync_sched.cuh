@@ -21,6 +21,11 @@ struct GyncSchedModel {              // device-resident
 };
 
 __device__ __forceinline__ double gync_sched_feature(double x) { return log(fmax(fabs(x), 1e-300)); }
+// feature relative to the offset, clamped: an exact zero (log -> -690) must not become a leverage point of the fit
+__device__ __forceinline__ double gync_sched_rel(double x, double ref) {
+  const double v = gync_sched_feature(x) - ref;
+  return (v == v) ? fmin(fmax(v, -20.0), 20.0) : 0.0;
+}
 
 // predicted cost per sample + its range (as order-preserving integers: predictions are made non-negative)
 __global__ void __launch_bounds__(256)
@@ -34,7 +39,7 @@ gync_sched_predict_kernel(const double* __restrict__ X, int64_t N, const GyncSch
     for (int f = 1; f < GYNC_SCHED_NF; ++f) {
       const double x = __ldg(X + n + N * (f - 1));
       chk += x * 0.0;                              // NaN / Inf anywhere -> NaN
-      p = fma(mdl->beta[f], gync_sched_feature(x) - mdl->ref[f], p);
+      p = fma(mdl->beta[f], gync_sched_rel(x, mdl->ref[f]), p);
     }
     // samples that fail at load time (non-finite input, e.g. Metropolis proposals outside the prior) cost nothing:
     // they go last, where they fill the tail for free
@@ -110,9 +115,9 @@ gync_sched_features_kernel(const double* __restrict__ X, int64_t N, int S, int64
     double v = bad ? 0.0 : 1.0;
     if (f > 0) {
       const double r = gync_sched_feature(__ldg(X + N * (f - 1)));          // sample 0 is the offset
-      v = bad ? 0.0 : gync_sched_feature(__ldg(X + n + N * (f - 1))) - r;
-      if (!(v == v) || fabs(v) > 1e3) v = 0.0;
-      if (s == 0) mdl->ref[f] = (r == r) ? r : 0.0;
+      const double rr = (r == r) ? r : 0.0;
+      v = bad ? 0.0 : gync_sched_rel(__ldg(X + n + N * (f - 1)), rr);
+      if (s == 0) mdl->ref[f] = rr;
     } else if (s == 0) {
       mdl->ref[0] = 0.0;
     }
