@@ -509,10 +509,24 @@ def collapse_duplicates(samplings, burnin=0):
     return S[starts], counts
 
 
+def collapse_duplicates_device(samplings, burnin=0):
+    """weightedchain.jl:31-46 on the device (gync_collapse_duplicates): same result as collapse_duplicates."""
+    lib = _L.load()
+    S = _L.fcol(np.vstack([s.samples[burnin:] for s in samplings]))
+    K = S.shape[0]
+    if K == 0:
+        return S, np.zeros(0, dtype=np.int64)
+    rows = np.empty((K, 116), order="F")
+    counts = np.zeros(K, dtype=np.int64)
+    n = C.c_int64()
+    _L.check(lib.gync_collapse_duplicates(_L.dptr(S), K, _L.dptr(rows), counts.ctypes.data_as(_L.c_int64_p), C.byref(n)))
+    return np.ascontiguousarray(rows[:n.value]), counts[:n.value].copy()
+
+
 def _weightedchain_from_samplings(samplings, burnin=0):
     """WeightedChain(samplings::Vector{Sampling}, burnin) (weightedchain.jl:29-71)."""
     lib = _L.load()
-    samplevec, counts = collapse_duplicates(samplings, burnin)
+    samplevec, counts = collapse_duplicates_device(samplings, burnin)
     c0 = samplings[0].config
     prior = logprior(c0, samplevec)                                             # :49-51
     LL, _ = loglik_matrix(samplevec, [s.config.data for s in samplings],

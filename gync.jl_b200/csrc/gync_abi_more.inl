@@ -224,6 +224,40 @@ int gync_wc_normalize_dev(double* dLL_inout, const double* d_logprior, const int
   return GYNC_OK;
 }
 
+// Duplicate collapse of WeightedChain(samplings, burnin) (weightedchain.jl:31-46) on the device.
+// X: K x 116 (the concatenated chains after burn-in).  rows_out: K x 116 buffer whose first *ngroups rows (leading
+// dimension K) are the collapsed samples; counts_out: K (first *ngroups valid).
+int gync_collapse_duplicates(const double* X, int64_t K, double* rows_out, int64_t* counts_out, int64_t* ngroups) {
+  if (K < 0 || !ngroups || (K > 0 && (!X || !rows_out || !counts_out)) || K >= (1LL << 31))
+    return fail(GYNC_ERR_ARG, "gync_collapse_duplicates: bad arguments");
+  if (int rc = ensure_init()) return rc;
+  *ngroups = 0;
+  if (K == 0) return GYNC_OK;
+  DBuf dX, dOut, dCnt, dFlag, dPos, dN;
+  CK(dX.alloc(sizeof(double) * K * GYNC_NX));
+  CK(dOut.alloc(sizeof(double) * K * GYNC_NX));
+  CK(dCnt.alloc(sizeof(long long) * K));
+  CK(dFlag.alloc(sizeof(int) * K));
+  CK(dPos.alloc(sizeof(int) * K));
+  CK(dN.alloc(sizeof(int)));
+  CK(cudaMemcpyAsync(dX.p, X, sizeof(double) * K * GYNC_NX, cudaMemcpyHostToDevice, g_stream));
+  gync_dedupe_flag_kernel<<<blocks_for(K, 256), 256, 0, g_stream>>>(dX.as<double>(), K, dFlag.as<int>());
+  gync_dedupe_scan_kernel<<<1, 1024, 0, g_stream>>>(dFlag.as<int>(), K, dPos.as<int>(), dN.as<int>());
+  gync_dedupe_scatter_kernel<<<blocks_for(K, 256), 256, 0, g_stream>>>(dX.as<double>(), K, dFlag.as<int>(), dPos.as<int>(),
+                                                                       dOut.as<double>(), dCnt.as<long long>());
+  g_launches += 3;
+  CK(cudaGetLastError());
+  int n = 0;
+  CK(cudaMemcpyAsync(&n, dN.p, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+  CK(wait_stream(g_stream));
+  *ngroups = n;
+  CK(cudaMemcpy2DAsync(rows_out, sizeof(double) * K, dOut.p, sizeof(double) * K, sizeof(double) * n, GYNC_NX,
+                       cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaMemcpyAsync(counts_out, dCnt.p, sizeof(long long) * n, cudaMemcpyDeviceToHost, g_stream));
+  CK(wait_stream(g_stream));
+  return GYNC_OK;
+}
+
 // Row-sharded normalisation (one process per GPU): three phases, the caller's collectives in between.
 int gync_wc_colstats_dev(const double* dLL, const double* d_logprior, const int64_t* d_counts, int64_t K, int32_t M,
                          double* d_stats /* M + 2 */, void* stream) {

@@ -311,3 +311,55 @@ __global__ void __launch_bounds__(256) gync_wc_total_kernel(const double* __rest
     total[0] = t;
   }
 }
+
+// ---- duplicate collapse of WeightedChain(samplings) — weightedchain.jl:31-46: consecutive equal rows of the
+// concatenated sample matrix (K x 116, column-major) become one row with a count.  flag -> scan -> scatter.
+__global__ void __launch_bounds__(256)
+gync_dedupe_flag_kernel(const double* __restrict__ X, int64_t K, int* __restrict__ flag) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  int f = (k == 0);
+  if (k > 0)
+    for (int d = 0; d < GYNC_NX; ++d) f |= (X[k + K * d] != X[k - 1 + K * d]);     // `==` of the reference: NaN != NaN
+  flag[k] = f;
+}
+
+// inclusive scan of the flags by ONE CTA (chunks of blockDim, carry across chunks): pos[k] = index of the row group
+__global__ void __launch_bounds__(1024)
+gync_dedupe_scan_kernel(const int* __restrict__ flag, int64_t K, int* __restrict__ pos, int* __restrict__ ngroups) {
+  __shared__ int s[1024];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < K; base += 1024) {
+    const int64_t k = base + threadIdx.x;
+    s[threadIdx.x] = (k < K) ? flag[k] : 0;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      const int v = ((int)threadIdx.x >= o) ? s[threadIdx.x - o] : 0;
+      __syncthreads();
+      s[threadIdx.x] += v;
+      __syncthreads();
+    }
+    if (k < K) pos[k] = carry + s[threadIdx.x] - 1;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += s[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *ngroups = carry;
+}
+
+// rows: group g <- first row of the group (out is G x 116 with leading dimension K: the caller trims); counts[g]
+__global__ void __launch_bounds__(256)
+gync_dedupe_scatter_kernel(const double* __restrict__ X, int64_t K, const int* __restrict__ flag, const int* __restrict__ pos,
+                           double* __restrict__ out, long long* __restrict__ counts) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  const int g = pos[k];
+  if (flag[k]) {
+    for (int d = 0; d < GYNC_NX; ++d) out[g + K * d] = X[k + K * d];
+    int64_t e = k + 1;
+    while (e < K && !flag[e]) ++e;                 // run length (runs are short compared with K)
+    counts[g] = (long long)(e - k);
+  }
+}

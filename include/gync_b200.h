@@ -234,6 +234,11 @@ int  gync_ebmodel_create_zshard(const double* ys, int64_t K, const double* datas
                                 const double* sig_z, double* scal_out /* 2 */, gync_ebmodel** out);
 int  gync_ebmodel_zshard_finish(gync_ebmodel* m, const double* scal /* 2 */);
 
+/* ---- duplicate collapse at the head of WeightedChain(samplings, burnin) — weightedchain.jl:31-46 --------------------
+ * X: K x 116, the concatenated chains after burn-in.  Consecutive equal rows become one row with a count.
+ * rows_out: K x 116 buffer (leading dimension K) whose first *ngroups rows are the collapsed samples; counts_out: K. */
+int gync_collapse_duplicates(const double* X, int64_t K, double* rows_out, int64_t* counts_out, int64_t* ngroups);
+
 /* Row-sharded form (one process per GPU): each rank holds K_local rows; the caller's collectives sit
  * between the phases:  colstats -> allreduce(max) of d_stats[0..M] (column maxima, max log-prior) and allreduce(sum) of
  * d_stats[M+1] (count total) -> expsum(d_colmax = d_stats) -> allreduce(sum) of the M column sums -> rows (d_stats =

@@ -574,3 +574,26 @@ def test_learned_queue_order_is_result_neutral(gpu):
         for a, b in zip(runs[name], runs["unordered"]):
             assert np.array_equal(a, b, equal_nan=True), name
     assert runs["ordered"][1][123] != 0 and runs["ordered"][0][123, 0] == -np.inf
+
+
+def test_collapse_duplicates_device(gpu):
+    """Head of WeightedChain(samplings) (weightedchain.jl:31-46) on the device vs the oracle / host mirror."""
+    import gync_oracle as o
+    rng = np.random.default_rng(29)
+    base = rng.random((4000, 116)) + 0.1
+    reps = rng.integers(1, 6, 4000)                       # runs of repeated rows, as a Metropolis chain produces them
+    S = np.repeat(base, reps, axis=0)
+    cut = S.shape[0] // 3
+    c = gpu.Config()
+    ss = [gpu.Sampling(S[:cut], c, None), gpu.Sampling(S[cut:], c, None)]     # a run may continue across the chain boundary
+    rows, counts = gpu.api.collapse_duplicates_device(ss)
+    r0, c0 = o.collapse_duplicates([S[:cut], S[cut:]])
+    assert np.array_equal(rows, r0) and np.array_equal(counts, c0) and counts.sum() == S.shape[0]
+    r1, c1 = gpu.api.collapse_duplicates(ss)
+    assert np.array_equal(rows, r1) and np.array_equal(counts, c1)
+    rows, counts = gpu.api.collapse_duplicates_device(ss, burnin=7)
+    r0, c0 = o.collapse_duplicates([S[:cut], S[cut:]], burnin=7)
+    assert np.array_equal(rows, r0) and np.array_equal(counts, c0)
+    one = [gpu.Sampling(S[:1], c, None)]
+    rows, counts = gpu.api.collapse_duplicates_device(one)
+    assert rows.shape == (1, 116) and counts.tolist() == [1]
