@@ -234,8 +234,8 @@ def main():
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
                 "frac": achieved / peak.value if peak.value else None,
                 # DRAM bytes per launch from the ncu --set full capture (profiles/r1_ncu_full_summary.txt:
-                # 15.6 MB read + 0.07 MB written for 16 576 samples = 946 B per sample; algorithmic 928 + 8 B)
-                "traffic": 946.0 * N_SAMPLES,
+                # 17.86 MB read + 0.24 MB written for 18 944 samples = 955 B per sample; algorithmic 928 + 8 B)
+                "traffic": 955.0 * N_SAMPLES,
                 "kernel": "gync_loglik_tm_kernel", "kernel_ms": ms_dev,
                 "how": f"{attempts} RODAS4 step attempts x {fl_step} FP64 flops per step (counted from the generated "
                        "code, DESIGN.md §5) / CUDA-event time; peak = FP64 FMA microbenchmark measured in this run "
