@@ -231,3 +231,24 @@ end
 function projectsimplex!(y::Vector{Float64})
   check(ccall((:gync_projectsimplex, LIBGYNC), Cint, (Ptr{Cdouble}, Int64), y, length(y))); y
 end
+
+# --- WeightedChain(samplings, burnin) (src/gync/weightedchain.jl:29-71): the whole constructor on the device ---
+function collapseduplicates(S::Matrix{Float64})          # weightedchain.jl:31-46 on the concatenated chains
+  K = size(S, 1)
+  rows, counts, n = Array(Float64, K, 116), Array(Int64, K), Int64[0]
+  check(ccall((:gync_collapse_duplicates, LIBGYNC), Cint, (Ptr{Cdouble}, Int64, Ptr{Cdouble}, Ptr{Int64}, Ptr{Int64}),
+              S, K, rows, counts, n))
+  rows[1:n[1], :], counts[1:n[1]]
+end
+
+function WeightedChain(samplings::Vector{Sampling}, burnin=0)
+  S = vcat([s.samples[(1+burnin):end, :] for s in samplings]...)
+  samples, counts = collapseduplicates(S)                                            # :31-46
+  K  = size(samples, 1)
+  lp = Array(Float64, K)
+  check(ccall((:gync_logprior_batch, LIBGYNC), Cint, (Ptr{Cdouble}, Int64, Ptr{Cdouble}, Ptr{Cdouble}),
+              samples, K, priorvector(samplings[1].config), lp))                     # :49-51
+  LL = loglikmatrix(samples, [data(s) for s in samplings], [s.config.sigma_rho for s in samplings])   # :53-56, one solve per sample
+  L, w, d = wcnormalize(LL, lp, counts)                                              # :59-67
+  WeightedChain(samples, L, w, d)                                                    # :69-70
+end
