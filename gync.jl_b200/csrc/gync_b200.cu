@@ -108,8 +108,8 @@ StagePool g_stage[8];
 
 GyncSolverOpts to_opts(const gync_solver_opts* o) {
   GyncSolverOpts r;
-  r.rtol = (o && o->rtol > 0) ? o->rtol : 1e-8;
-  r.atol = (o && o->atol > 0) ? o->atol : 1e-10;
+  r.rtol = (o && o->rtol > 0) ? o->rtol : GYNC_DEFAULT_RTOL;
+  r.atol = (o && o->atol > 0) ? o->atol : GYNC_DEFAULT_ATOL;
   r.h0 = o ? o->h0 : 0.0;
   r.hmax = o ? o->hmax : 0.0;
   r.max_steps = (o && o->max_steps > 0) ? o->max_steps : 200000;

@@ -1,4 +1,4 @@
-// GynCycle stiff forward solve: one RODAS4 (Hairer & Wanner, order 4(3), L-stable, stiffly
+// GynCycle stiff forward solve: one RODAS4P (Steinebach; order 4(3), L-stable, stiffly
 // accurate, 6 stages) step on the generated straight-line RHS / Jacobian / sparse LU, plus the
 // step-size controller.  One parameter vector per thread; everything here is per-thread state.
 //
@@ -55,33 +55,42 @@ struct GyncStepStats {   // per-sample work counters (roofline bookkeeping, SURV
   int nacc, nrej;
 };
 
-// ---- RODAS4 coefficients (Hairer & Wanner, Solving ODEs II, RODAS code; gamma = 1/4)
+// ---- Rosenbrock tableau: RODAS4P (G. Steinebach, "Order-reduction of ROW-methods for DAEs and method of lines
+// applications", 1995; the METH=3 set of Hairer & Wanner's RODAS code; gamma = 1/4, 6 stages, order 4(3), L-stable,
+// stiffly accurate) in the implementation form  W k_i = f(y + sum a_ij k_j) + (1/h) sum c_ij k_j.
+// Round 1 used the classic RODAS4 set (same structure, same cost per step).  On this problem RODAS4 loses order on
+// a few percent of the samples (observed global order 2.8 instead of 4 on the worst near-set sample), which put a
+// heavy tail on the log-likelihood error: 0.08 % of the cases above the 1e-8 parity bound, max 4.6e-8, and 1.7x the
+// steps to remove it by tolerance alone.  RODAS4P satisfies the extra Prothero-Robinson conditions, its tail is 4x
+// shorter (max/median error 70 instead of 270), and it meets the bound for every case of the validation sets at
+// 1.2x the steps of round 1 (tools/tail_study/).  tests/test_host_logic.py checks all eight order
+// conditions up to order 4 for this table (and the order-3 conditions of the embedded weights) to 1e-13.
 #define RD_G   0.25
-#define RD_A21 0.1544e1
-#define RD_A31 0.9466785280815826
-#define RD_A32 0.2557011698983284
-#define RD_A41 0.3314825187068521e1
-#define RD_A42 0.2896124015972201e1
-#define RD_A43 0.9986419139977817
-#define RD_A51 0.1221224509226641e1
-#define RD_A52 0.6019134481288629e1
-#define RD_A53 0.1253708332932087e2
-#define RD_A54 (-0.6878860361058950)
-#define RD_C21 (-0.56688e1)
-#define RD_C31 (-0.2430093356833875e1)
-#define RD_C32 (-0.2063599157091915)
-#define RD_C41 (-0.1073529058151375)
-#define RD_C42 (-0.9594562251023355e1)
-#define RD_C43 (-0.2047028614809616e2)
-#define RD_C51 0.7496443313967647e1
-#define RD_C52 (-0.1024680431464352e2)
-#define RD_C53 (-0.3399990352819905e2)
-#define RD_C54 0.1170890893206160e2
-#define RD_C61 0.8083246795921522e1
-#define RD_C62 (-0.7981132988064893e1)
-#define RD_C63 (-0.3152159432874371e2)
-#define RD_C64 0.1631930543123136e2
-#define RD_C65 (-0.6058818238834054e1)
+#define RD_A21 3.0
+#define RD_A31 1.831036793486759
+#define RD_A32 0.4955183967433795
+#define RD_A41 2.304376582692669
+#define RD_A42 (-0.05249275245743001)
+#define RD_A43 (-1.176798761832782)
+#define RD_A51 (-7.170454962423024)
+#define RD_A52 (-4.741636671481785)
+#define RD_A53 (-16.31002631330971)
+#define RD_A54 (-1.062004044111401)
+#define RD_C21 (-12.0)
+#define RD_C31 (-8.791795173947035)
+#define RD_C32 (-2.207865586973518)
+#define RD_C41 10.81793056857153
+#define RD_C42 6.780270611428266
+#define RD_C43 19.53485944642410
+#define RD_C51 34.19095006749676
+#define RD_C52 15.49671153725963
+#define RD_C53 54.74760875964130
+#define RD_C54 14.16005392148534
+#define RD_C61 34.62605830930532
+#define RD_C62 15.30084976114473
+#define RD_C63 56.99955578662667
+#define RD_C64 18.40807009793095
+#define RD_C65 (-5.714285714285717)
 
 struct GyncWork {          // host layout (tests); the device layout is GyncWorkSm in gync_kernels.cuh
   double q[GYNC_NQ];

@@ -57,7 +57,12 @@ int  gync_abi_version(void);
 void gync_dims(int32_t* ny, int32_t* np, int32_t* nx, int32_t* nq, int32_t* nlu);
 
 /* solver options shared by the solve / likelihood / MCMC entry points.
- * rtol/atol are the `reltol`/`abstol` keywords of gync() (gyncycle.jl:8).  max_steps<=0 -> default. */
+ * rtol/atol are the `reltol`/`abstol` keywords of gync() (gyncycle.jl:8).  max_steps<=0 -> default.
+ * rtol/atol <= 0 (or opts == NULL) select the library defaults below: the tolerance at which every
+ * log-likelihood of the validation sets is within 1e-8 relative of the converged solution
+ * (the reference's own default, 1e-4, is ~1e-3 away from it). */
+#define GYNC_DEFAULT_RTOL 3e-10
+#define GYNC_DEFAULT_ATOL 1e-11
 typedef struct {
   double  rtol, atol;
   double  h0;          /* initial step, <=0 automatic */

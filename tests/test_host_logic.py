@@ -3,6 +3,7 @@ library's symbol table, and the host-side mirror of the reference API.  No compu
 import ctypes as C
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -12,6 +13,7 @@ import gync_oracle as o
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, "tests", "golden")
+PARITY_RTOL, PARITY_ATOL = 3e-10, 1e-11     # library defaults (include/gync_b200.h, api.DEFAULT_RTOL/ATOL)
 dp = C.POINTER(C.c_double)
 P = lambda a: a.ctypes.data_as(dp)  # noqa: E731
 
@@ -63,7 +65,7 @@ def test_rodas4_solver_core_vs_converged_golden(host_shim):
     trajectories within 1e-6, log-likelihood within 1e-8 relative (north-star tolerances)."""
     g = np.load(os.path.join(G, "solution_golden.npz"))
     for i in (0, 1, 2, 9, 34):
-        st, tr, na, nr = host_traj(host_shim, g["X"][i], 1e-8, 1e-10)
+        st, tr, na, nr = host_traj(host_shim, g["X"][i], PARITY_RTOL, PARITY_ATOL)
         assert st == 0 and 300 < na < 20000
         assert relerr(tr, g["traj"][i]) < 1e-6
         for m in range(4):
@@ -71,15 +73,96 @@ def test_rodas4_solver_core_vs_converged_golden(host_shim):
             assert abs(l - g["LL"][i, m]) <= 1e-8 * abs(g["LL"][i, m]), (i, m, l, g["LL"][i, m])
 
 
+def test_solver_core_on_the_parity_tail_fixtures(host_shim):
+    """CPU build of the device solver at the library default tolerance against the frozen near-set log-likelihoods
+    (tests/golden/nearset_llh_golden.npz): a slice of both populations plus the two samples that were above the 1e-8
+    bound in round 1 (RODAS4 at 1e-8/1e-10: 4.6e-8 and 1.1e-8), and a slice of the wide set incl. its failure set.
+    The -m gpu suite runs all 18 432 + 512 cases."""
+    sys.path.insert(0, G)
+    import make_nearset_golden as mg
+    g = np.load(os.path.join(G, "nearset_llh_golden.npz"))
+    la = o.patients()[0]
+    worst = 0.0
+    for name, idx in (("A", list(range(40)) + [187, 963, 740]), ("B", list(range(40)) + [2730, 2929])):
+        seed, n, pats = mg.SETS[name]
+        X = mg.near_set(seed, n)
+        for i in idx:
+            st, tr, _, _ = host_traj(host_shim, X[i], PARITY_RTOL, PARITY_ATOL)
+            assert st == 0
+            for m, pi in enumerate(pats):
+                l = o.llh_from_traj(tr, la[pi], 0.1)
+                worst = max(worst, abs(l - g["LL_" + name][i, m]) / abs(g["LL_" + name][i, m]))
+    assert worst <= 1e-8, worst
+    Xw = mg.wide_set(int(g["seed_W"]), 512)
+    for i in range(64):
+        st, tr, _, _ = host_traj(host_shim, Xw[i], PARITY_RTOL, PARITY_ATOL)
+        assert (st == 0) == bool(np.isfinite(g["LL_W"][i])), i
+        if st == 0:
+            l = o.llh_from_traj(tr, la[0], 0.1)
+            assert abs(l - g["LL_W"][i]) <= 1e-8 * abs(g["LL_W"][i])
+
+
 def test_rodas4_failure_status(host_shim):
     g = np.load(os.path.join(G, "solution_golden.npz"))
     bad = np.flatnonzero(~np.isfinite(g["LL"][:, 0]))[0]
-    st, tr, _, _ = host_traj(host_shim, g["X"][bad], 1e-8, 1e-10)
+    st, tr, _, _ = host_traj(host_shim, g["X"][bad], PARITY_RTOL, PARITY_ATOL)
     assert st != 0 and np.isnan(tr).all()
     x = g["X"][0].copy()
     x[115] = np.nan
     st, tr, _, _ = host_traj(host_shim, x, 1e-6, 1e-6)
     assert st == 4 and np.isnan(tr).all()
+
+
+def _tableau():
+    """RD_* macros of csrc/gync_solver.cuh -> (gamma, A, C) of the 6-stage implementation form."""
+    src = open(os.path.join(ROOT, "gync.jl_b200", "csrc", "gync_solver.cuh")).read()
+    co_ = {m.group(1): float(m.group(2).strip("()")) for m in re.finditer(r"#define RD_([AGC]\d*)\s+(\(?-?[0-9.e+-]+\)?)", src)}
+    s = 6
+    A, Cm = np.zeros((s, s)), np.zeros((s, s))
+    for k, v in co_.items():
+        if k[0] == "A":
+            A[int(k[1]) - 1, int(k[2]) - 1] = v
+        elif k[0] == "C":
+            Cm[int(k[1]) - 1, int(k[2]) - 1] = v
+    A[5, :4] = A[4, :4]
+    A[5, 4] = 1.0          # stage 6 starts from the embedded solution (gync_rodas4_step, RD_TA last row)
+    return co_["G"], A, Cm
+
+
+def test_rosenbrock_tableau_order_conditions():
+    """The solver's coefficient table (RODAS4P) is pinned by the Rosenbrock order conditions themselves
+    (Hairer & Wanner II, Table IV.7.1): all 8 conditions up to order 4 for the propagated weights, the 4 conditions up
+    to order 3 for the embedded weights, stiff accuracy (alpha_6 = 1, last stage weight 1) — a wrong digit in any
+    coefficient breaks them at the 1e-6 level, they hold to 1e-13."""
+    g, A, Cm = _tableau()
+    Gam = np.linalg.inv(np.eye(6) / g - Cm)                  # Gamma: gamma on the diagonal, gamma_ij below
+    assert np.allclose(np.diag(Gam), g, atol=1e-14) and np.allclose(np.triu(Gam, 1), 0, atol=1e-14)
+    al = A @ Gam
+    Gs = Gam - np.diag(np.diag(Gam))
+    be = al + Gs
+    ai, bi = al.sum(1), be.sum(1)
+    assert abs(ai[5] - 1.0) < 1e-13 and abs(ai[4] - 1.0) < 1e-13
+    m = np.array([A[4, 0], A[4, 1], A[4, 2], A[4, 3], 1.0, 1.0])
+
+    def cond(b):
+        return np.array([b.sum() - 1, b @ bi - (0.5 - g), b @ ai ** 2 - 1 / 3, b @ be @ bi - (1 / 6 - g + g * g),
+                         b @ ai ** 3 - 0.25, b @ (ai * (al @ bi)) - (1 / 8 - g / 3), b @ be @ ai ** 2 - (1 / 12 - g / 3),
+                         b @ be @ be @ bi - (1 / 24 - g / 2 + 1.5 * g * g - g ** 3)])
+    assert np.max(np.abs(cond(m @ Gam))) < 1e-13
+    mh = m.copy()
+    mh[5] = 0.0
+    ch = cond(mh @ Gam)
+    assert np.max(np.abs(ch[:4])) < 1e-13 and np.max(np.abs(ch[4:])) > 1e-3     # embedded: order 3, not 4
+
+
+def test_default_tolerances_agree_everywhere():
+    hdr = open(os.path.join(ROOT, "include", "gync_b200.h")).read()
+    rt = float(re.search(r"#define GYNC_DEFAULT_RTOL\s+(\S+)", hdr).group(1))
+    at = float(re.search(r"#define GYNC_DEFAULT_ATOL\s+(\S+)", hdr).group(1))
+    import gync_b200 as g
+    assert (rt, at) == (PARITY_RTOL, PARITY_ATOL) == (g.api.DEFAULT_RTOL, g.api.DEFAULT_ATOL)
+    jl = open(os.path.join(ROOT, "julia", "GynCB200.jl")).read()
+    assert "reltol=3e-10, abstol=1e-11" in jl and "1e-8, 1e-10" not in jl
 
 
 def test_rodas4_generic_grid_and_order(host_shim):

@@ -188,3 +188,16 @@ def test_amm_oracle_step_properties():
     A = rng.standard_normal((5, 5))
     S = A @ A.T + np.eye(5)
     assert np.allclose(o.chol_fullrank(S), np.linalg.cholesky(S), rtol=1e-12)
+
+
+def test_every_golden_is_cross_checked_by_an_independent_integrator(sol_gold):
+    """tests/golden/radau_crosscheck.json (written by tests/golden/crosscheck_radau.py): scipy's Radau IIA at 1e-12 on
+    the restated RHS against the C oracle's extrapolation integrator, for EVERY finite sample of the fixtures."""
+    import json
+    r = json.load(open(os.path.join(G, "radau_crosscheck.json")))
+    fin = np.flatnonzero(np.isfinite(sol_gold["LL"][:, 0]))
+    got = {e["index"]: e for e in r["samples"] if e["llh_rel"] is not None}
+    assert sorted(got) == fin.tolist() and r["n_checked"] == fin.size
+    assert all(np.isfinite(e["llh_rel"]) and e["llh_rel"] < 1e-9 and e["traj_rel"] < 1e-8 for e in got.values())
+    assert r["max_llh_rel"] < 1e-9 and r["max_traj_rel"] < 1e-8
+
