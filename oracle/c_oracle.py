@@ -84,3 +84,17 @@ def emiteration(w, L, mt=False):
 
 def num_threads():
     return lib().orc_num_threads()
+
+
+def set_num_threads(n):
+    """Pin the OpenMP thread count of the batch calls (independent of OMP_NUM_THREADS in the environment)."""
+    lib().orc_set_num_threads(int(n))
+    return num_threads()
+
+
+def host_cores():
+    """Cores this process may run on (affinity mask if the platform has one)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1

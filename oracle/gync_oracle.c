@@ -41,6 +41,14 @@ static const double MEASMAG[4] = {120., 10., 400., 15.};    /* model.jl:10 */
 static double g_refallparms[NP];   /* set by orc_set_reference (data file src/gync/data/refparms.jl) */
 
 void orc_set_reference(const double* refallparms) { memcpy(g_refallparms, refallparms, sizeof(g_refallparms)); }
+/* bench.py pins the thread count itself: launchers such as torchrun export OMP_NUM_THREADS=1 */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 int orc_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();
