@@ -40,8 +40,8 @@ parameternames = _C["parameternames"]
 #: reltol=abstol=1e-4 (gyncycle.jl:8), at which CVODE is ~3e-2 off the converged trajectory;
 #: parity is stated against the converged solution, so the default here is the
 #: tolerance at which log-likelihoods are within 1e-8 relative of it for every case of the
-#: validation sets (18 432 near-set cases, profiles/r2_validation_cpu.json; RODAS4P).
-DEFAULT_RTOL = 3e-10
+#: validation sets (18 432 near-set cases, profiles/r2_validation_cpu.json; Rodas5P).
+DEFAULT_RTOL = 7e-10
 DEFAULT_ATOL = 1e-11
 
 
@@ -299,6 +299,10 @@ class Variate:
     seed: int
     iteration: int = 0
     naccept: int = 0
+    # Philox stream of THIS chain (the draws of a chain are addressed by (seed, chain_id, iteration)): it stays with the
+    # variate through sample_chains groups of any composition, save() / load() and batch(), so a chain resumed alone
+    # continues exactly the stream it would have drawn from inside its group.
+    chain_id: int = None
     # AMMTune adaptation state (Mamba): counter, running mean / second moment of the log-space
     # states, factor of the adapted proposal.  m < 0: adaptation has not started.
     m: int = -1
@@ -320,14 +324,36 @@ class Sampling:
         return self.samples.shape[0]
 
 
-def SamplerVariate(c: Config, seed=0) -> Variate:
-    """model.jl:97-107 — state = log(init(c)); SigmaL = chol(propvar).L."""
-    return Variate(np.log(init(c)), np.nan, np.linalg.cholesky(c.propvar), int(seed))
+_process_seed = []
+_next_chain_id = [0]
 
 
-def new_sampling(c: Config, seed=0) -> Sampling:
+def process_seed() -> int:
+    """The seed of chains created without one: drawn once per process from the OS (the reference's chains use Julia's
+    global RNG, seeded at start-up).  Such chains are told apart by a process-wide chain counter, so chains launched
+    separately — the per-patient workflow of batch.jl — never share their proposal or accept noise."""
+    if not _process_seed:
+        _process_seed.append(int(np.random.SeedSequence().generate_state(1, np.uint64)[0]))
+    return _process_seed[0]
+
+
+def SamplerVariate(c: Config, seed=None, chain_id=None) -> Variate:
+    """model.jl:97-107 — state = log(init(c)); SigmaL = chol(propvar).L.
+    The draws of a chain are addressed by (seed, chain_id, iteration).  seed=None: the process seed and the next value of
+    the process-wide chain counter.  Explicit seed: reproducible; chain_id defaults to the chain's position in the first
+    sample_chains call that advances it (0 for a single chain) and stays with the variate from then on."""
+    if seed is None:
+        seed = process_seed()
+        if chain_id is None:
+            chain_id = _next_chain_id[0]
+            _next_chain_id[0] += 1
+    return Variate(np.log(init(c)), np.nan, np.linalg.cholesky(c.propvar), int(seed),
+                   chain_id=None if chain_id is None else int(chain_id))
+
+
+def new_sampling(c: Config, seed=None, chain_id=None) -> Sampling:
     """Sampling(c) (sampling.jl:53-58)."""
-    return Sampling(np.empty((0, 116)), c, SamplerVariate(c, seed))
+    return Sampling(np.empty((0, 116)), c, SamplerVariate(c, seed, chain_id))
 
 
 def propinit(s: "Sampling"):
@@ -348,6 +374,8 @@ def sample_chains(samplings, iters: int):
     lib = _L.load()
     groups = {}
     for i, s in enumerate(samplings):
+        if s.variate.chain_id is None:
+            s.variate.chain_id = i
         key = (s.config.thin, s.config.adapt, s.variate.SigmaL.tobytes(), s.config.rtol, s.config.atol, s.variate.seed,
                s.variate.iteration, id(s.config.priory0) if s.config.priory0 is not None else 0,
                s.config.priorparms.tobytes())
@@ -372,7 +400,8 @@ def sample_chains(samplings, iters: int):
         nacc = np.zeros(Cn, dtype=np.int64)
         pr = c0.prior()
         o = _L.opts(c0.rtol or DEFAULT_RTOL, c0.atol or DEFAULT_ATOL)
-        # chain id inside the RNG = position in the group + a per-sampling offset held in the seed
+        ids = np.array([s.variate.chain_id for s in ss], dtype=np.uint64)      # each chain's own Philox stream
+        idp = ids.ctypes.data_as(C.POINTER(C.c_uint64))
         if c0.adapt:                                        # Mamba.sample!(variate, adapt=true) (sampling.jl:72)
             am = np.array([s.variate.m for s in ss], dtype=np.int64)
             aMv = np.zeros((Cn, 116))
@@ -382,17 +411,17 @@ def sample_chains(samplings, iters: int):
                 if s.variate.m >= 0:
                     aMv[m], aMvv[m], aLm[m] = s.variate.Mv, s.variate.Mvv, s.variate.SigmaLm
             tune = _L.AmmTune(v0.beta, v0.scale, am.ctypes.data_as(_L.c_int64_p), _L.dptr(aMv), _L.dptr(aMvv), _L.dptr(aLm))
-            _L.check(lib.gync_mcmc_run_amm(_L.dptr(state), _L.dptr(logf), Cn, _L.dptr(chol), float(SL[0, 0]) if diag else 0.0,
-                                           _L.dptr(D), Cn, _L.dptr(sig), pat.ctypes.data_as(_L.c_int32_p), C.byref(pr),
-                                           C.byref(o), iters, thin, v0.seed, v0.iteration, None, None, None, _L.dptr(out),
-                                           nacc.ctypes.data_as(_L.c_int64_p), C.byref(tune)))
+            _L.check(lib.gync_mcmc_run_amm_ids(_L.dptr(state), _L.dptr(logf), Cn, _L.dptr(chol), float(SL[0, 0]) if diag else 0.0,
+                                               _L.dptr(D), Cn, _L.dptr(sig), pat.ctypes.data_as(_L.c_int32_p), C.byref(pr),
+                                               C.byref(o), iters, thin, v0.seed, v0.iteration, idp, None, None, None,
+                                               _L.dptr(out), nacc.ctypes.data_as(_L.c_int64_p), C.byref(tune)))
             for m, s in enumerate(ss):
                 s.variate.m, s.variate.Mv, s.variate.Mvv, s.variate.SigmaLm = int(am[m]), aMv[m].copy(), aMvv[m].copy(), aLm[m].copy()
         else:
-            _L.check(lib.gync_mcmc_run(_L.dptr(state), _L.dptr(logf), Cn, _L.dptr(chol), float(SL[0, 0]) if diag else 0.0,
-                                       _L.dptr(D), Cn, _L.dptr(sig), pat.ctypes.data_as(_L.c_int32_p), C.byref(pr),
-                                       C.byref(o), iters, thin, v0.seed, v0.iteration, None, None, _L.dptr(out),
-                                       nacc.ctypes.data_as(_L.c_int64_p)))
+            _L.check(lib.gync_mcmc_run_ids(_L.dptr(state), _L.dptr(logf), Cn, _L.dptr(chol), float(SL[0, 0]) if diag else 0.0,
+                                           _L.dptr(D), Cn, _L.dptr(sig), pat.ctypes.data_as(_L.c_int32_p), C.byref(pr),
+                                           C.byref(o), iters, thin, v0.seed, v0.iteration, idp, None, None, _L.dptr(out),
+                                           nacc.ctypes.data_as(_L.c_int64_p)))
         for m, s in enumerate(ss):
             s.samples = np.vstack([s.samples, out[:, :, m]])            # sampling.jl:66-68,74
             s.variate.state = state[m].copy()
@@ -407,7 +436,7 @@ def sample_bang(s: Sampling, iters: int) -> Sampling:
     return sample_chains([s], iters)[0]
 
 
-def sample(obj, n, seed=0):
+def sample(obj, n, seed=None):
     """sample(c::Config, iters) (sampling.jl:60)  |  sample(w::WeightedChain, n) (weightedchain.jl:18-26)."""
     if isinstance(obj, Config):
         return sample_bang(new_sampling(obj, seed), n)
@@ -430,7 +459,7 @@ def save(path, s: Sampling):
          "inity0": c.inity0, "priorparms": c.priorparms, "priory0_means": c.priory0.means, "priory0_stds": c.priory0.stds,
          "rtol": np.nan if c.rtol is None else c.rtol, "atol": np.nan if c.atol is None else c.atol,
          "v_state": v.state, "v_logf": v.logf, "v_SigmaL": v.SigmaL, "v_seed": v.seed, "v_iteration": v.iteration,
-         "v_naccept": v.naccept, "v_m": v.m, "v_beta": v.beta, "v_scale": v.scale}
+         "v_naccept": v.naccept, "v_m": v.m, "v_beta": v.beta, "v_scale": v.scale, "v_chain_id": -1 if v.chain_id is None else v.chain_id}
     if v.m >= 0:
         z.update(v_Mv=v.Mv, v_Mvv=v.Mvv, v_SigmaLm=v.SigmaLm)
     with open(path, "wb") as f:                      # np.savez would append ".npz" to the reference's ".jld" file names
@@ -446,13 +475,14 @@ def load(path) -> Sampling:
                priorparms=z["priorparms"], priory0=GaussianMixture(z["priory0_means"], z["priory0_stds"]),
                rtol=nz("rtol"), atol=nz("atol"))
     v = Variate(z["v_state"], float(z["v_logf"]), z["v_SigmaL"], int(z["v_seed"]), int(z["v_iteration"]), int(z["v_naccept"]),
-                int(z["v_m"]), beta=float(z["v_beta"]), scale=float(z["v_scale"]))
+                (int(z["v_chain_id"]) if int(z["v_chain_id"]) >= 0 else None) if "v_chain_id" in z.files else 0, int(z["v_m"]), beta=float(z["v_beta"]),
+                scale=float(z["v_scale"]))
     if v.m >= 0:
         v.Mv, v.Mvv, v.SigmaLm = z["v_Mv"], z["v_Mvv"], z["v_SigmaLm"]
     return Sampling(z["samples"], c, v)
 
 
-def batch(c: Config, iters, path, overwrite=False, seed=0):
+def batch(c: Config, iters, path, overwrite=False, seed=None):
     """batch(c, iters::Vector{Int}, path) (batch.jl:26-46): sample up to each iteration count in `iters`, saving after
     each; an existing file is continued unless `overwrite`.  (The Slurm fan-out of batch.jl:3-22 is replaced by
     sample_chains: many chains in one launch.)"""

@@ -22,11 +22,169 @@ int gync_logprior_batch(const double* X, int64_t N, const gync_prior* prior, dou
   return GYNC_OK;
 }
 
+// ---- K3p host side: one persistent launch per device (gync_mcmc_persist.cuh).  Chains shard over the devices of
+// gync_init_multi in contiguous blocks (independent chains, no data-path collective); every device runs
+// its block asynchronously and the host only waits once, at the end.
+struct McmcStats { unsigned long long solves = 0, steps = 0; };
+static McmcStats g_mcmc_stats;          // last gync_mcmc_run: likelihood solves started / step attempts (all devices)
+static int g_mcmc_K = 0;                // slots per chain round of the last run
+
+namespace {
+struct McmcJob {
+  int64_t lo = 0, n = 0;
+  int K = 1;
+  DBuf dS, dLf, dIt, dAcc, dLeft, dRk, dLfp, dQ, dCtl, dCh, dD, dSig, dPat, dPr, dZ, dU, dOut, dIsc, dNan, dIds;
+  // scratch of the initial log-target evaluation
+  DBuf dXL, dX, dLpr, dLL, dPs;
+  GyncMcmcP P;
+};
+}  // namespace
+
+static int mcmc_persist_impl(double* state, double* logf, int64_t C, const double* chol, double prop_sd, const double* data,
+                             int32_t M, const double* sigma_rho, const int32_t* patient_of_chain, const gync_prior* prior,
+                             const gync_solver_opts* opts, int64_t iters, int32_t thin, uint64_t seed, uint64_t iter_offset,
+                             const uint64_t* chain_ids, const double* inj_z, const double* inj_u, double* samples_out,
+                             int64_t* naccept) {
+  const int64_t n_out = iters / thin;
+  const int nd = (g_devs.size() > 1 && C >= (int64_t)g_devs.size()) ? (int)g_devs.size() : 1;
+  const int home = [&] { for (size_t i = 0; i < g_devs.size(); ++i) if (g_devs[i].device == g_device) return (int)i; return 0; }();
+  const GyncSolverOpts so = to_opts(opts);
+  bool need_init = false;
+  for (int64_t c = 0; c < C; ++c) need_init |= !(logf[c] == logf[c]);
+  std::vector<McmcJob> jobs(nd);
+  g_mcmc_stats = McmcStats();
+  for (int i = 0; i < nd; ++i) {
+    McmcJob& J = jobs[i];
+    J.lo = C * i / nd;
+    J.n = C * (i + 1) / nd - J.lo;
+    if (J.n == 0) continue;
+    if (nd > 1) if (int rc = use_device(i)) return rc;
+    cudaStream_t s = g_stream;
+    const int64_t n = J.n, lanes = (int64_t)g_num_sms * GYNC_TM_NSLOT;
+    // slots per round: enough outstanding work for 1.5 solves per lane (chains run out of step with each other, so a
+    // lane only idles when the queue is empty); fewer slots waste fewer speculative solves after an acceptance
+    double over = 1.5;
+    if (const char* v = getenv("GYNC_MCMC_OVERSUB")) over = std::max(0.25, atof(v));
+    int K = (int)std::max<int64_t>(1, std::min<int64_t>(1024, (int64_t)(over * (double)lanes / (double)n + 0.5)));
+    if (const char* v = getenv("GYNC_MCMC_SPEC")) K = std::max(1, std::min(4096, atoi(v)));
+    K = (int)std::min<int64_t>(K, std::max<int64_t>(iters, 1));
+    J.K = K;
+    g_mcmc_K = K;
+    int qshift = 1;
+    while ((1LL << qshift) < 2 * n * K + 2) ++qshift;
+    CK(J.dS.alloc(sizeof(double) * n * GYNC_NX));
+    CK(J.dLf.alloc(sizeof(double) * n));
+    CK(J.dIt.alloc(sizeof(long long) * n));
+    CK(J.dAcc.alloc(sizeof(long long) * n));
+    CK(J.dLeft.alloc(sizeof(int) * n));
+    CK(J.dRk.alloc(sizeof(int) * n));
+    CK(J.dLfp.alloc(sizeof(double) * n * K));
+    CK(J.dQ.alloc(sizeof(unsigned long long) << qshift));
+    CK(J.dCtl.alloc(sizeof(GyncMcmcCtl)));
+    CK(J.dD.alloc(sizeof(double) * 124 * M));
+    CK(J.dSig.alloc(sizeof(double) * M));
+    CK(J.dPr.alloc(sizeof(gync_prior)));
+    CK(J.dIsc.alloc(sizeof(double) * 4 * M));
+    CK(J.dNan.alloc(sizeof(int) * M));
+    CK(cudaMemcpy2DAsync(J.dS.p, sizeof(double) * n, state + J.lo, sizeof(double) * C, sizeof(double) * n, GYNC_NX,
+                         cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(J.dLf.p, logf + J.lo, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(J.dD.p, data, sizeof(double) * 124 * M, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(J.dSig.p, sigma_rho, sizeof(double) * M, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(J.dPr.p, prior, sizeof(gync_prior), cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(J.dAcc.p, 0, sizeof(long long) * n, s));
+    CK(cudaMemsetAsync(J.dIt.p, 0, sizeof(long long) * n, s));
+    CK(cudaMemsetAsync(J.dQ.p, 0, sizeof(unsigned long long) << qshift, s));
+    CK(cudaMemsetAsync(J.dCtl.p, 0, sizeof(GyncMcmcCtl), s));
+    if (chol) {
+      CK(J.dCh.alloc(sizeof(double) * GYNC_NX * GYNC_NX));
+      CK(cudaMemcpyAsync(J.dCh.p, chol, sizeof(double) * GYNC_NX * GYNC_NX, cudaMemcpyHostToDevice, s));
+    }
+    if (patient_of_chain) {
+      CK(J.dPat.alloc(sizeof(int32_t) * n));
+      CK(cudaMemcpyAsync(J.dPat.p, patient_of_chain + J.lo, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
+    }
+    if (chain_ids) {
+      CK(J.dIds.alloc(sizeof(uint64_t) * n));
+      CK(cudaMemcpyAsync(J.dIds.p, chain_ids + J.lo, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, s));
+    }
+    if (inj_z) {       // iters x 116 x C and iters x C: chain-major, so a block of chains is contiguous
+      CK(J.dZ.alloc(sizeof(double) * iters * GYNC_NX * n));
+      CK(J.dU.alloc(sizeof(double) * iters * n));
+      CK(cudaMemcpyAsync(J.dZ.p, inj_z + iters * GYNC_NX * J.lo, sizeof(double) * iters * GYNC_NX * n, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(J.dU.p, inj_u + iters * J.lo, sizeof(double) * iters * n, cudaMemcpyHostToDevice, s));
+    }
+    if (samples_out && n_out > 0) CK(J.dOut.alloc(sizeof(double) * n_out * GYNC_NX * n));
+    gync_prep_patients_kernel<<<blocks_for(M, 64), 64, 0, s>>>(J.dD.as<double>(), J.dSig.as<double>(), M, J.dIsc.as<double>(), J.dNan.as<int>());
+    g_launches += 1;
+    GyncMcmcP& P = J.P;
+    memset(&P, 0, sizeof(P));
+    P.state = J.dS.as<double>(); P.logf = J.dLf.as<double>(); P.itc = J.dIt.as<long long>(); P.naccept = J.dAcc.as<long long>();
+    P.round_left = J.dLeft.as<int>(); P.round_k = J.dRk.as<int>(); P.lfp = J.dLfp.as<double>();
+    P.queue = J.dQ.as<unsigned long long>(); P.qmask = (1ull << qshift) - 1ull; P.qshift = qshift; P.ctl = J.dCtl.as<GyncMcmcCtl>();
+    P.C = n; P.K = K; P.iters = iters; P.thin = thin;
+    P.chol = chol ? J.dCh.as<double>() : nullptr; P.prop_sd = prop_sd; P.pr = J.dPr.as<GyncPriorDev>();
+    P.seed = seed; P.iter_offset = iter_offset;
+    P.chain_ids = chain_ids ? J.dIds.as<unsigned long long>() : nullptr; P.chain_id_base = (unsigned long long)J.lo;
+    P.inj_z = inj_z ? J.dZ.as<double>() : nullptr; P.inj_u = inj_u ? J.dU.as<double>() : nullptr;
+    P.patient_of_chain = patient_of_chain ? J.dPat.as<int>() : nullptr;
+    P.data = J.dD.as<double>(); P.iscale = J.dIsc.as<double>(); P.allnan = J.dNan.as<int>();
+    P.samples_out = (samples_out && n_out > 0) ? J.dOut.as<double>() : nullptr; P.n_out = n_out;
+    P.o = so;
+    if (need_init) {
+      // log-target of the CURRENT states (a fresh variate carries NaN): one batch through the ordinary kernels
+      CK(J.dXL.alloc(sizeof(double) * n * GYNC_NX));
+      CK(J.dX.alloc(sizeof(double) * n * GYNC_NX));
+      CK(J.dLpr.alloc(sizeof(double) * n));
+      CK(J.dLL.alloc(sizeof(double) * n));
+      CK(J.dPs.alloc(sizeof(int) * n));
+      gync_mcmc_propose_kernel<<<blocks_for(n, 128), 128, 0, s>>>(
+          P.state, P.itc, n, 1, iters, 1, P.chol, prop_sd, P.pr, seed, iter_offset, nullptr, P.patient_of_chain,
+          J.dXL.as<double>(), J.dX.as<double>(), J.dLpr.as<double>(), J.dPs.as<int>());
+      g_launches += 1;
+      CK(cudaGetLastError());
+      if (int rc = launch_loglik(J.dX.as<double>(), n, P.data, P.iscale, P.allnan, M, J.dPs.as<int>(), so, J.dLL.as<double>(),
+                                 nullptr, nullptr, nullptr, s)) return rc;
+      gync_mcmc_accept_kernel<<<blocks_for(n, 128), 128, 0, s>>>(
+          P.state, P.logf, P.itc, n, 1, iters, thin, 1, J.dXL.as<double>(), J.dLpr.as<double>(), J.dLL.as<double>(), seed,
+          iter_offset, nullptr, nullptr, P.naccept, nullptr);
+      g_launches += 1;
+    }
+    if (int rc = prep_solver_kernel(gync_mcmc_persist_kernel, GyncWorkTm::kSmemBytes, 128)) return rc;
+    gync_mcmc_persist_init_kernel<<<blocks_for(n, 128), 128, 0, s>>>(P);
+    const int nb = (int)std::min<int64_t>((n * K + GYNC_TM_NSLOT - 1) / GYNC_TM_NSLOT, (int64_t)g_num_sms);
+    gync_mcmc_persist_kernel<<<nb, 128, GyncWorkTm::kSmemBytes, s>>>(P);
+    g_launches += 2;
+    CK(cudaGetLastError());
+    // results come back on the same stream, behind the kernel
+    CK(cudaMemcpy2DAsync(state + J.lo, sizeof(double) * C, J.dS.p, sizeof(double) * n, sizeof(double) * n, GYNC_NX,
+                         cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(logf + J.lo, J.dLf.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    if (samples_out && n_out > 0)
+      CK(cudaMemcpyAsync(samples_out + n_out * GYNC_NX * J.lo, J.dOut.p, sizeof(double) * n_out * GYNC_NX * n, cudaMemcpyDeviceToHost, s));
+    if (naccept) CK(cudaMemcpyAsync(naccept + J.lo, J.dAcc.p, sizeof(long long) * n, cudaMemcpyDeviceToHost, s));
+  }
+  int rc_all = GYNC_OK;
+  for (int i = 0; i < nd; ++i) {
+    McmcJob& J = jobs[i];
+    if (J.n == 0) continue;
+    if (nd > 1) if (int rc = use_device(i)) return rc;
+    GyncMcmcCtl ctl;
+    cudaError_t e = cudaMemcpyAsync(&ctl, J.dCtl.p, sizeof(ctl), cudaMemcpyDeviceToHost, g_stream);
+    if (e == cudaSuccess) e = wait_stream(g_stream);
+    if (e != cudaSuccess) rc_all = fail(GYNC_ERR_CUDA, std::string("gync_mcmc_run: ") + cudaGetErrorString(e));
+    else { g_mcmc_stats.solves += ctl.solves; g_mcmc_stats.steps += ctl.steps; }
+    J = McmcJob();                // free on the owning device
+  }
+  if (nd > 1) if (int rc = use_device(home)) return rc;
+  return rc_all;
+}
+
 static int mcmc_run_impl(double* state, double* logf, int64_t C, const double* chol, double prop_sd, const double* data,
                   int32_t M, const double* sigma_rho, const int32_t* patient_of_chain, const gync_prior* prior,
                   const gync_solver_opts* opts, int64_t iters, int32_t thin, uint64_t seed, uint64_t iter_offset,
                   const double* inj_z, const double* inj_u, double* samples_out, int64_t* naccept,
-                  const gync_amm_tune* amm, const double* inj_umix) {
+                  const gync_amm_tune* amm, const double* inj_umix, const uint64_t* chain_ids) {
   if (C < 0 || M < 1 || iters < 0 || thin < 1 || !prior || (C > 0 && (!state || !logf || !data || !sigma_rho)))
     return fail(GYNC_ERR_ARG, "gync_mcmc_run: bad arguments");
   if (!chol && !(prop_sd > 0.0)) return fail(GYNC_ERR_ARG, "gync_mcmc_run: need chol or prop_sd > 0");
@@ -36,6 +194,9 @@ static int mcmc_run_impl(double* state, double* logf, int64_t C, const double* c
       if (patient_of_chain[c] < 0 || patient_of_chain[c] >= M) return fail(GYNC_ERR_ARG, "gync_mcmc_run: patient index out of range");
   if (int rc = ensure_init()) return rc;
   if (C == 0) return GYNC_OK;
+  if (!amm && !getenv("GYNC_MCMC_ROUNDS"))      // non-adaptive chains: one persistent launch (gync_mcmc_persist.cuh)
+    return mcmc_persist_impl(state, logf, C, chol, prop_sd, data, M, sigma_rho, patient_of_chain, prior, opts, iters, thin, seed,
+                             iter_offset, chain_ids, inj_z, inj_u, samples_out, naccept);
   const int64_t n_out = iters / thin;
   // speculation depth: fill the solver kernel's sample slots (112 per SM) about twice per round
   int K = (int)std::max<int64_t>(1, std::min<int64_t>(1024, (2 * (int64_t)g_num_sms * GYNC_TM_NSLOT) / C));
@@ -44,7 +205,7 @@ static int mcmc_run_impl(double* state, double* logf, int64_t C, const double* c
   K = (int)std::min<int64_t>(K, std::max<int64_t>(iters, 1));
   const int64_t N = C * K;
   cudaStream_t s = g_stream;
-  DBuf dS, dLf, dCh, dD, dSig, dPat, dPr, dZ, dU, dOut, dAcc, dIsc, dNan, dIt, dXL, dX, dLpr, dLL, dPs, dMin;
+  DBuf dS, dLf, dCh, dD, dSig, dPat, dPr, dZ, dU, dOut, dAcc, dIsc, dNan, dIt, dXL, dX, dLpr, dLL, dPs, dMin, dIds;
   CK(dS.alloc(sizeof(double) * C * GYNC_NX));
   CK(dLf.alloc(sizeof(double) * C));
   CK(dD.alloc(sizeof(double) * 124 * M));
@@ -75,6 +236,11 @@ static int mcmc_run_impl(double* state, double* logf, int64_t C, const double* c
     CK(dPat.alloc(sizeof(int32_t) * C));
     CK(cudaMemcpyAsync(dPat.p, patient_of_chain, sizeof(int32_t) * C, cudaMemcpyHostToDevice, s));
   }
+  if (chain_ids) {
+    CK(dIds.alloc(sizeof(uint64_t) * C));
+    CK(cudaMemcpyAsync(dIds.p, chain_ids, sizeof(uint64_t) * C, cudaMemcpyHostToDevice, s));
+  }
+  const unsigned long long* d_ids = chain_ids ? dIds.as<unsigned long long>() : nullptr;
   if (inj_z) {
     CK(dZ.alloc(sizeof(double) * iters * GYNC_NX * C));
     CK(dU.alloc(sizeof(double) * iters * C));
@@ -127,12 +293,12 @@ static int mcmc_run_impl(double* state, double* logf, int64_t C, const double* c
           dS.as<double>(), dIt.as<long long>(), dAcc.as<long long>(), C, Kr, iters, chol ? dCh.as<double>() : nullptr, prop_sd,
           dPr.as<GyncPriorDev>(), seed, iter_offset, inj_z ? dZ.as<double>() : nullptr, inj_umix ? dUm.as<double>() : nullptr,
           patient_of_chain ? dPat.as<int>() : nullptr, ad, aVirt.as<double>(), aXold.as<double>(), aIt0.as<long long>(),
-          aNacc0.as<long long>(), dXL.as<double>(), dX.as<double>(), dLpr.as<double>(), dPs.as<int>());
+          aNacc0.as<long long>(), dXL.as<double>(), dX.as<double>(), dLpr.as<double>(), dPs.as<int>(), d_ids);
     } else {
       gync_mcmc_propose_kernel<<<blocks_for(Nr, 128), 128, 0, s>>>(
           dS.as<double>(), dIt.as<long long>(), C, Kr, iters, mode, chol ? dCh.as<double>() : nullptr, prop_sd,
           dPr.as<GyncPriorDev>(), seed, iter_offset, inj_z ? dZ.as<double>() : nullptr,
-          patient_of_chain ? dPat.as<int>() : nullptr, dXL.as<double>(), dX.as<double>(), dLpr.as<double>(), dPs.as<int>());
+          patient_of_chain ? dPat.as<int>() : nullptr, dXL.as<double>(), dX.as<double>(), dLpr.as<double>(), dPs.as<int>(), d_ids);
     }
     g_launches += 1;
     CK(cudaGetLastError());
@@ -143,7 +309,7 @@ static int mcmc_run_impl(double* state, double* logf, int64_t C, const double* c
     gync_mcmc_accept_kernel<<<blocks_for(C, 128), 128, 0, s>>>(
         dS.as<double>(), dLf.as<double>(), dIt.as<long long>(), C, Kr, iters, thin, mode, dXL.as<double>(), dLpr.as<double>(),
         dLL.as<double>(), seed, iter_offset, inj_u ? dU.as<double>() : nullptr,
-        (samples_out && n_out > 0) ? dOut.as<double>() : nullptr, dAcc.as<long long>(), dMin.as<long long>());
+        (samples_out && n_out > 0) ? dOut.as<double>() : nullptr, dAcc.as<long long>(), dMin.as<long long>(), d_ids);
     g_launches += 1;
     if (adaptive) {
       gync_amm_commit_kernel<<<(unsigned)C, GYNC_AMM_THREADS, sizeof(GyncAmmSmem), s>>>(
@@ -189,7 +355,16 @@ int gync_mcmc_run(double* state, double* logf, int64_t C, const double* chol, do
                   const gync_solver_opts* opts, int64_t iters, int32_t thin, uint64_t seed, uint64_t iter_offset,
                   const double* inj_z, const double* inj_u, double* samples_out, int64_t* naccept) {
   return mcmc_run_impl(state, logf, C, chol, prop_sd, data, M, sigma_rho, patient_of_chain, prior, opts, iters, thin, seed,
-                       iter_offset, inj_z, inj_u, samples_out, naccept, nullptr, nullptr);
+                       iter_offset, inj_z, inj_u, samples_out, naccept, nullptr, nullptr, nullptr);
+}
+
+int gync_mcmc_run_ids(double* state, double* logf, int64_t C, const double* chol, double prop_sd, const double* data,
+                      int32_t M, const double* sigma_rho, const int32_t* patient_of_chain, const gync_prior* prior,
+                      const gync_solver_opts* opts, int64_t iters, int32_t thin, uint64_t seed, uint64_t iter_offset,
+                      const uint64_t* chain_ids, const double* inj_z, const double* inj_u, double* samples_out,
+                      int64_t* naccept) {
+  return mcmc_run_impl(state, logf, C, chol, prop_sd, data, M, sigma_rho, patient_of_chain, prior, opts, iters, thin, seed,
+                       iter_offset, inj_z, inj_u, samples_out, naccept, nullptr, nullptr, chain_ids);
 }
 
 int gync_mcmc_run_amm(double* state, double* logf, int64_t C, const double* chol, double prop_sd, const double* data,
@@ -197,10 +372,27 @@ int gync_mcmc_run_amm(double* state, double* logf, int64_t C, const double* chol
                       const gync_solver_opts* opts, int64_t iters, int32_t thin, uint64_t seed, uint64_t iter_offset,
                       const double* inj_z, const double* inj_u, const double* inj_umix, double* samples_out,
                       int64_t* naccept, const gync_amm_tune* tune) {
+  return gync_mcmc_run_amm_ids(state, logf, C, chol, prop_sd, data, M, sigma_rho, patient_of_chain, prior, opts, iters, thin,
+                               seed, iter_offset, nullptr, inj_z, inj_u, inj_umix, samples_out, naccept, tune);
+}
+
+int gync_mcmc_run_amm_ids(double* state, double* logf, int64_t C, const double* chol, double prop_sd, const double* data,
+                          int32_t M, const double* sigma_rho, const int32_t* patient_of_chain, const gync_prior* prior,
+                          const gync_solver_opts* opts, int64_t iters, int32_t thin, uint64_t seed, uint64_t iter_offset,
+                          const uint64_t* chain_ids, const double* inj_z, const double* inj_u, const double* inj_umix,
+                          double* samples_out, int64_t* naccept, const gync_amm_tune* tune) {
   if (!tune) return fail(GYNC_ERR_ARG, "gync_mcmc_run_amm: NULL tune");
   if (C > 65535LL * 32768LL) return fail(GYNC_ERR_ARG, "gync_mcmc_run_amm: too many chains");
   return mcmc_run_impl(state, logf, C, chol, prop_sd, data, M, sigma_rho, patient_of_chain, prior, opts, iters, thin, seed,
-                       iter_offset, inj_z, inj_u, samples_out, naccept, tune, inj_umix);
+                       iter_offset, inj_z, inj_u, samples_out, naccept, tune, inj_umix, chain_ids);
+}
+
+// bookkeeping of the last persistent Metropolis run on this thread's library context: likelihood solves started, their
+// Rosenbrock step attempts (summed over the devices), slots per chain round
+void gync_mcmc_last_stats(uint64_t* solves, uint64_t* steps, int32_t* slots_per_round) {
+  if (solves) *solves = g_mcmc_stats.solves;
+  if (steps) *steps = g_mcmc_stats.steps;
+  if (slots_per_round) *slots_per_round = g_mcmc_K;
 }
 
 int gync_wc_normalize_dev(double* dLL_inout, const double* d_logprior, const int64_t* d_counts, int64_t K, int32_t M,

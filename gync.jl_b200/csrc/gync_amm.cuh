@@ -93,7 +93,8 @@ gync_amm_propose_kernel(const double* __restrict__ state, const long long* __res
                         const double* __restrict__ inj_z, const double* __restrict__ inj_umix,
                         const int* __restrict__ patient_of_chain, GyncAmmDev amm, double* __restrict__ virt /* C x (116 + 116^2) */,
                         double* __restrict__ xold /* C x 116 */, long long* __restrict__ it0, long long* __restrict__ nacc0,
-                        double* __restrict__ XL, double* __restrict__ X, double* __restrict__ lpr, int* __restrict__ pat_of_sample) {
+                        double* __restrict__ XL, double* __restrict__ X, double* __restrict__ lpr, int* __restrict__ pat_of_sample,
+                        const unsigned long long* __restrict__ chain_ids = nullptr /* Philox stream per chain; NULL: c */) {
   extern __shared__ __align__(16) unsigned char gync_amm_raw[];
   GyncAmmSmem& sm = *reinterpret_cast<GyncAmmSmem*>(gync_amm_raw);
   const int64_t c = blockIdx.x;
@@ -135,9 +136,10 @@ gync_amm_propose_kernel(const double* __restrict__ state, const long long* __res
       for (int d = tid; d < GYNC_NX; d += GYNC_AMM_THREADS) sm.z[d] = inj_z[it + iters * (d + (int64_t)GYNC_NX * c)];
       umix = inj_umix ? inj_umix[it + iters * c] : 1.0;
     } else {
-      if (tid < GYNC_NX / 2) gync_draw_n2(seed, (uint64_t)c, git, (uint32_t)tid, sm.z[2 * tid], sm.z[2 * tid + 1]);
+      const uint64_t cid = chain_ids ? (uint64_t)chain_ids[c] : (uint64_t)c;
+      if (tid < GYNC_NX / 2) gync_draw_n2(seed, cid, git, (uint32_t)tid, sm.z[2 * tid], sm.z[2 * tid + 1]);
       double u;
-      gync_draw_u2(seed, (uint64_t)c, git, (uint32_t)(GYNC_NX / 2), u, umix);   // u is the accept draw (accept kernel)
+      gync_draw_u2(seed, cid, git, (uint32_t)(GYNC_NX / 2), u, umix);   // u is the accept draw (accept kernel)
     }
     __syncthreads();
     const bool adapted = (m > 2 * GYNC_NX) && (umix >= amm.beta);

@@ -8,6 +8,7 @@
 #include <vector>
 #include "gync_kernels.cuh"
 #include "gync_mcmc.cuh"
+#include "gync_mcmc_persist.cuh"
 #include "gync_amm.cuh"
 #include "gync_sched.cuh"
 #include "../../include/gync_b200.h"
@@ -448,17 +449,27 @@ const char* gync_last_error(void) { return g_err.c_str(); }
 
 int64_t gync_launch_count(void) { return g_launches.load(); }
 
-// FP64 flops of one RODAS4 step attempt: generated-code counts (add+mul; a reciprocal = seed + 3 DFMA = 6,
-// the real power = exp+log ~ 60) + the hand-written stage algebra of gync_rodas4_step
-// (33 x [2+2+4+5+6+7+8+9+1+11+1] for the stage combinations + 33 x 13 for the error norm).
+// FP64 flops of one step attempt of the method the library was built with: generated-code counts (add+mul; a
+// reciprocal = seed + 3 DFMA = 6, the real power = exp+log ~ 60) + the hand-written stage algebra of the step function.
+//   Rodas5P (gync_rodas5p_step_tm): 8 solves, 7 RHS; per element of the 33-vectors: newest-k terms 7 x 3, stored-k sums
+//   (0+1+2+3+4+5+5) x 4, adding the parked correction 7 x 2, absorbing k6 2 x 2, error norm 13.
+//   RODAS4P (gync_rodas4_step_tm): 6 solves, 5 RHS; 33 x [2+2+4+5+6+7+8+9+1+11+1] + 33 x 13.
 double gync_flops_per_step(void) {
   const double rcp = 6.0, pw = 60.0;
   const double rhs = GYNC_OPS_RHS_FLOP + rcp * GYNC_OPS_RHS_RCP + pw * GYNC_OPS_RHS_POW;
   const double rhsw = GYNC_OPS_RHSW_FLOP + rcp * GYNC_OPS_RHSW_RCP + pw * GYNC_OPS_RHSW_POW;
   const double lu = GYNC_OPS_LU_FLOP + rcp * GYNC_OPS_LU_RCP;
+#if GYNC_ROS_ORDER == 5
+  const double stage = 33.0 * (7 * 3 + 20 * 4 + 7 * 2 + 4) + 33.0 * 13.0;
+  return rhsw + 7.0 * rhs + lu + 8.0 * GYNC_OPS_SOLVE_FLOP + stage;
+#else
   const double stage = 33.0 * (2 + 2 + 4 + 5 + 6 + 7 + 8 + 9 + 1 + 11 + 1) + 33.0 * 13.0;
   return rhsw + 5.0 * rhs + lu + 6.0 * GYNC_OPS_SOLVE_FLOP + stage;
+#endif
 }
+
+// 5: Rodas5P (default build), 4: RODAS4P (-DGYNC_ROS_ORDER=4, A/B runs)
+int gync_method_order(void) { return GYNC_ROS_ORDER; }
 
 void gync_dims(int32_t* ny, int32_t* np, int32_t* nx, int32_t* nq, int32_t* nlu) {
   if (ny) *ny = GYNC_NY;
@@ -565,7 +576,10 @@ int gync_loglik_batch_dev(const double* dX, int64_t N, const double* d_data, int
 static int loglik_batch_multi(const double* X, int64_t N, const double* data, int32_t M, const double* sigma_rho,
                               const gync_solver_opts* opts, double* LL, double* Ymeas, int32_t* status, int32_t* nsteps) {
   const int nd = (int)g_devs.size();
-  struct Part { int64_t lo = 0, n = 0; DBuf dX, dD, dS, dLL, dY, dSt, dNs; };
+  // staging buffers come from the grow-only pool of each device slot (as in the single-device path): no cudaMalloc /
+  // cudaFree — both synchronise the device — around a repeated call of the same size
+  struct Part { int64_t lo = 0, n = 0; double *dX = nullptr, *dD = nullptr, *dS = nullptr, *dLL = nullptr, *dY = nullptr;
+                int32_t *dSt = nullptr, *dNs = nullptr; };
   std::vector<Part> parts(nd);
   for (int i = 0; i < nd; ++i) {
     Part& p = parts[i];
@@ -573,38 +587,38 @@ static int loglik_batch_multi(const double* X, int64_t N, const double* data, in
     p.n = N * (i + 1) / nd - p.lo;
     if (p.n == 0) continue;
     if (int rc = use_device(i)) return rc;
-    CK(p.dX.alloc(sizeof(double) * p.n * GYNC_NX));
-    CK(p.dD.alloc(sizeof(double) * 124 * M));
-    CK(p.dS.alloc(sizeof(double) * M));
-    CK(p.dLL.alloc(sizeof(double) * p.n * M));
-    if (Ymeas) CK(p.dY.alloc(sizeof(double) * p.n * GYNC_NT_MEAS * GYNC_NMEAS));
-    CK(p.dSt.alloc(sizeof(int32_t) * p.n));
-    if (nsteps) CK(p.dNs.alloc(sizeof(int32_t) * p.n * 2));
-    CK(cudaMemcpy2DAsync(p.dX.p, sizeof(double) * p.n, X + p.lo, sizeof(double) * N, sizeof(double) * p.n, GYNC_NX,
+    StagePool& sp = g_stage[i];
+    p.dX = (double*)sp.get(0, sizeof(double) * p.n * GYNC_NX, g_device);
+    p.dD = (double*)sp.get(1, sizeof(double) * 124 * M, g_device);
+    p.dS = (double*)sp.get(2, sizeof(double) * M, g_device);
+    p.dLL = (double*)sp.get(3, sizeof(double) * p.n * M, g_device);
+    p.dY = Ymeas ? (double*)sp.get(4, sizeof(double) * p.n * GYNC_NT_MEAS * GYNC_NMEAS, g_device) : nullptr;
+    p.dSt = (int32_t*)sp.get(5, sizeof(int32_t) * p.n, g_device);
+    p.dNs = nsteps ? (int32_t*)sp.get(6, sizeof(int32_t) * p.n * 2, g_device) : nullptr;
+    if (!p.dX || !p.dD || !p.dS || !p.dLL || !p.dSt || (Ymeas && !p.dY) || (nsteps && !p.dNs))
+      return fail(GYNC_ERR_NOMEM, "gync_loglik_batch: out of device memory");
+    CK(cudaMemcpy2DAsync(p.dX, sizeof(double) * p.n, X + p.lo, sizeof(double) * N, sizeof(double) * p.n, GYNC_NX,
                          cudaMemcpyHostToDevice, g_stream));
-    CK(cudaMemcpyAsync(p.dD.p, data, sizeof(double) * 124 * M, cudaMemcpyHostToDevice, g_stream));
-    CK(cudaMemcpyAsync(p.dS.p, sigma_rho, sizeof(double) * M, cudaMemcpyHostToDevice, g_stream));
-    if (int rc = gync_loglik_batch_dev(p.dX.as<double>(), p.n, p.dD.as<double>(), M, p.dS.as<double>(), opts, p.dLL.as<double>(),
-                                       Ymeas ? p.dY.as<double>() : nullptr, p.dSt.as<int32_t>(),
-                                       nsteps ? p.dNs.as<int32_t>() : nullptr, g_stream)) return rc;
+    CK(cudaMemcpyAsync(p.dD, data, sizeof(double) * 124 * M, cudaMemcpyHostToDevice, g_stream));
+    CK(cudaMemcpyAsync(p.dS, sigma_rho, sizeof(double) * M, cudaMemcpyHostToDevice, g_stream));
+    if (int rc = gync_loglik_batch_dev(p.dX, p.n, p.dD, M, p.dS, opts, p.dLL, p.dY, p.dSt, p.dNs, g_stream)) return rc;
   }
   for (int i = 0; i < nd; ++i) {
     Part& p = parts[i];
     if (p.n == 0) continue;
     if (int rc = use_device(i)) return rc;
-    CK(cudaMemcpy2DAsync(LL + p.lo, sizeof(double) * N, p.dLL.p, sizeof(double) * p.n, sizeof(double) * p.n, M,
+    CK(cudaMemcpy2DAsync(LL + p.lo, sizeof(double) * N, p.dLL, sizeof(double) * p.n, sizeof(double) * p.n, M,
                          cudaMemcpyDeviceToHost, g_stream));
-    if (Ymeas) CK(cudaMemcpy2DAsync(Ymeas + p.lo, sizeof(double) * N, p.dY.p, sizeof(double) * p.n, sizeof(double) * p.n,
+    if (Ymeas) CK(cudaMemcpy2DAsync(Ymeas + p.lo, sizeof(double) * N, p.dY, sizeof(double) * p.n, sizeof(double) * p.n,
                                     GYNC_NT_MEAS * GYNC_NMEAS, cudaMemcpyDeviceToHost, g_stream));
-    if (status) CK(cudaMemcpyAsync(status + p.lo, p.dSt.p, sizeof(int32_t) * p.n, cudaMemcpyDeviceToHost, g_stream));
-    if (nsteps) CK(cudaMemcpy2DAsync(nsteps + p.lo, sizeof(int32_t) * N, p.dNs.p, sizeof(int32_t) * p.n, sizeof(int32_t) * p.n, 2,
+    if (status) CK(cudaMemcpyAsync(status + p.lo, p.dSt, sizeof(int32_t) * p.n, cudaMemcpyDeviceToHost, g_stream));
+    if (nsteps) CK(cudaMemcpy2DAsync(nsteps + p.lo, sizeof(int32_t) * N, p.dNs, sizeof(int32_t) * p.n, sizeof(int32_t) * p.n, 2,
                                      cudaMemcpyDeviceToHost, g_stream));
   }
   for (int i = 0; i < nd; ++i) {
     if (parts[i].n == 0) continue;
     if (int rc = use_device(i)) return rc;
     CK(wait_stream(g_stream));
-    parts[i] = Part();           // free on the owning device
   }
   return use_device(0);
 }

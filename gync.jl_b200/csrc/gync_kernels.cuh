@@ -41,7 +41,7 @@ __global__ void gync_prep_patients_kernel(const double* __restrict__ data, const
 // GyncWorkSm keeps everything in shared memory (64 samples per CTA: 216.6 KB of the 227 KB) and is
 // used by the generic time-grid kernel; the likelihood kernel uses the TMEM layout further down.
 #ifndef GYNC_SOLVE_BLOCK
-#define GYNC_SOLVE_BLOCK 64
+#define GYNC_SOLVE_BLOCK 48
 #endif
 
 // Element proxy: reads are VOLATILE shared loads.  Without that the compiler forwards the values
@@ -66,12 +66,12 @@ template <int BLOCK>
 struct GyncWorkSm {
   GyncSmView<BLOCK> q, k, A;
   double y[GYNC_NY], yn[GYNC_NY], e[GYNC_NY];
-  static constexpr int kDoublesPerThread = GYNC_NQ + 5 * GYNC_NY + GYNC_NLU;
+  static constexpr int kDoublesPerThread = GYNC_NQ + 6 * GYNC_NY + GYNC_NLU;
   static constexpr size_t kSmemBytes = sizeof(double) * kDoublesPerThread * BLOCK;
   __device__ __forceinline__ void bind(double* sm, int slot) {
     double* b = sm + slot;
     q.p = b;  b += GYNC_NQ * BLOCK;
-    k.p = b;  b += 5 * GYNC_NY * BLOCK;
+    k.p = b;  b += 6 * GYNC_NY * BLOCK;
     A.p = b;
   }
 };
@@ -327,6 +327,97 @@ __device__ __forceinline__ double gync_rodas4_step_tm(GyncWorkTm& W, const doubl
   return sqrt(sum * (1.0 / GYNC_NY));
 }
 
+// Rodas5P step with the stage storage in TMEM: same arithmetic as gync_rodas5p_step (gync_solver.cuh explains why five
+// stored vectors are enough) up to the order of the sums, and the same code shape as the RODAS4 form above — one rolled
+// stage loop whose body is the proven RHS + triangular solve + two short tensor-memory sums.
+__device__ __forceinline__ double gync_rodas5p_step_tm(GyncWorkTm& W, const double h, const double rtol, const double atol) {
+  const double ih = GYNC_RCP(h);
+  GYNC_TICK_INIT
+  gync_rhs_w(W.y, gync_sm_ro<GYNC_TM_NSLOT>(W.q.p), ih * (1.0 / R5_G), W.e, W.A);
+  GYNC_TICK(0)
+  gync_lu(W.A);
+  GYNC_TICK(1)
+  gync_lusolve(gync_ro(W.A), W.e);
+  GYNC_TICK(2)
+#pragma unroll 1
+  for (int s = 0; s < 7; ++s) {
+    if (s < R5_NSTORE) {
+      // park k_{s+1} for the later stages; its own contribution to this stage comes from the registers it still sits in
+      gync_tm_store_vec(W.tm + GYNC_TM_COL_K + 2 * GYNC_NY * s, W.e);
+    } else if (s == R5_NSTORE) {
+      // absorb k6 into the stored k4 and k5 (see gync_solver.cuh)
+#pragma unroll 1
+      for (int j = 3; j < 5; ++j) {
+        const double f = (j == 3) ? R5_BETA : R5_ALPHA;
+        const uint32_t ta = W.tm + GYNC_TM_COL_K + 2 * GYNC_NY * j;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          double k[8];
+          gync_tm_ld8(ta + 16 * ch, k);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) gync_tm_st1(ta + 16 * ch + 2 * i, fma(f, W.e[8 * ch + i], k[i]));
+        }
+        gync_tm_st1(ta + 64, fma(f, W.e[32], gync_tm_ld1(ta + 64)));
+      }
+      gync_tm_wait_st();
+    }
+    {
+      const double a = R5_OA[s], c = R5_OC[s];
+#pragma unroll
+      for (int i = 0; i < GYNC_NY; ++i) { W.yn[i] = fma(a, W.e[i], W.y[i]); W.e[i] = c * W.e[i]; }
+    }
+    const int ns = s < R5_NSTORE ? s : R5_NSTORE;
+#pragma unroll 1
+    for (int j = 0; j < ns; ++j) {
+      const double a = R5_TA[s][j], c = R5_TC[s][j];
+      const uint32_t ta = W.tm + GYNC_TM_COL_K + 2 * GYNC_NY * j;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        double k[8];
+        gync_tm_ld8(ta + 16 * ch, k);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { W.yn[8 * ch + i] = fma(a, k[i], W.yn[8 * ch + i]); W.e[8 * ch + i] = fma(c, k[i], W.e[8 * ch + i]); }
+      }
+      const double k32 = gync_tm_ld1(ta + 64);
+      W.yn[32] = fma(a, k32, W.yn[32]);
+      W.e[32] = fma(c, k32, W.e[32]);
+    }
+    gync_tm_store_vec(W.tm + GYNC_TM_COL_V, W.e);                          // park the correction
+    GYNC_TICK(3)
+    gync_rhs(W.yn, gync_sm_ro<GYNC_TM_NSLOT>(W.q.p), W.e);
+    GYNC_TICK(4)
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      double v[8];
+      gync_tm_ld8(W.tm + GYNC_TM_COL_V + 16 * ch, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) W.e[8 * ch + i] = fma(ih, v[i], W.e[8 * ch + i]);
+    }
+    W.e[32] = fma(ih, gync_tm_ld1(W.tm + GYNC_TM_COL_V + 64), W.e[32]);
+    GYNC_TICK(5)
+    gync_lusolve(gync_ro(W.A), W.e);
+    GYNC_TICK(2)
+  }
+  double sum = 0.0;
+#pragma unroll
+  for (int i = 0; i < GYNC_NY; ++i) {
+    W.yn[i] += W.e[i];
+    const double sc = atol + rtol * fmax(fabs(W.y[i]), fabs(W.yn[i]));
+    const double r = W.e[i] * GYNC_RCP(sc);
+    sum = fma(r, r, sum);
+  }
+  GYNC_TICK(6)
+  return sqrt(sum * (1.0 / GYNC_NY));
+}
+
+__device__ __forceinline__ double gync_ros_step_tm(GyncWorkTm& W, const double h, const double rtol, const double atol) {
+#if GYNC_ROS_ORDER == 5
+  return gync_rodas5p_step_tm(W, h, rtol, atol);
+#else
+  return gync_rodas4_step_tm(W, h, rtol, atol);
+#endif
+}
+
 __global__ void __launch_bounds__(128, 1)
 gync_loglik_tm_kernel(const double* __restrict__ X, int64_t N, const double* __restrict__ data,
                       const double* __restrict__ iscale, const int* __restrict__ allnan, int M,
@@ -419,7 +510,7 @@ gync_loglik_tm_kernel(const double* __restrict__ X, int64_t N, const double* __r
     if (last) h = rem;
     if (!stepping || !(h > 0.0)) h = 1.0;                  // dummy lanes: any finite positive step
     const double hprop = c.h;
-    const double err = gync_rodas4_step_tm(W, h, o.rtol, o.atol);
+    const double err = gync_ros_step_tm(W, h, o.rtol, o.atol);
     __syncwarp();
     if (stepping) {
       if (budget-- <= 0) {
@@ -635,7 +726,7 @@ gync_solve_tm_kernel(const double* __restrict__ X, const double* __restrict__ Y0
     if (last) h = rem;
     if (!stepping || !(h > 0.0)) h = 1.0;                  // idle lanes: any finite positive step
     const double hprop = c.h;
-    const double err = gync_rodas4_step_tm(W, h, o.rtol, o.atol);
+    const double err = gync_ros_step_tm(W, h, o.rtol, o.atol);
     __syncwarp();
     if (stepping) {
       if (budget-- <= 0) {

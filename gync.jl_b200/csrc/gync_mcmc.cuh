@@ -75,7 +75,8 @@ gync_mcmc_propose_kernel(const double* __restrict__ state /* C x 116 log-space *
                          const double* __restrict__ inj_z, const int* __restrict__ patient_of_chain,
                          double* __restrict__ XL /* N x 116 proposals, log space */, double* __restrict__ X /* exp */,
                          double* __restrict__ lpr /* N: logprior + sum(x), -Inf outside the prior */,
-                         int* __restrict__ pat_of_sample) {
+                         int* __restrict__ pat_of_sample,
+                         const unsigned long long* __restrict__ chain_ids = nullptr /* Philox stream per chain; NULL: c */) {
   const int64_t N = C * K;
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= N) return;
@@ -97,7 +98,8 @@ gync_mcmc_propose_kernel(const double* __restrict__ state /* C x 116 log-space *
       for (int d = 0; d < GYNC_NX; ++d) z[d] = inj_z[it + iters * (d + (int64_t)GYNC_NX * c)];
     } else {
       const uint64_t git = iter_offset + (uint64_t)it;
-      for (int b = 0; b < GYNC_NX / 2; ++b) gync_draw_n2(seed, (uint64_t)c, git, (uint32_t)b, z[2 * b], z[2 * b + 1]);
+      const uint64_t cid = chain_ids ? (uint64_t)chain_ids[c] : (uint64_t)c;
+      for (int b = 0; b < GYNC_NX / 2; ++b) gync_draw_n2(seed, cid, git, (uint32_t)b, z[2 * b], z[2 * b + 1]);
     }
     if (chol) {
       for (int d = 0; d < GYNC_NX; ++d) {
@@ -126,7 +128,8 @@ gync_mcmc_accept_kernel(double* __restrict__ state, double* __restrict__ logf, l
                         int64_t iters, int thin, int mode, const double* __restrict__ XL, const double* __restrict__ lpr,
                         const double* __restrict__ LL /* N */, uint64_t seed, uint64_t iter_offset,
                         const double* __restrict__ inj_u, double* __restrict__ samples_out,
-                        long long* __restrict__ naccept, long long* __restrict__ min_it) {
+                        long long* __restrict__ naccept, long long* __restrict__ min_it,
+                        const unsigned long long* __restrict__ chain_ids = nullptr) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const int64_t N = C * K;
@@ -144,7 +147,7 @@ gync_mcmc_accept_kernel(double* __restrict__ state, double* __restrict__ logf, l
     const double lfp = (lpr[s] > -INFINITY) ? lpr[s] + LL[s] : -INFINITY;
     double u, u1;
     if (inj_u) u = inj_u[it + iters * c];
-    else gync_draw_u2(seed, (uint64_t)c, iter_offset + (uint64_t)it, (uint32_t)(GYNC_NX / 2), u, u1);
+    else gync_draw_u2(seed, chain_ids ? (uint64_t)chain_ids[c] : (uint64_t)c, iter_offset + (uint64_t)it, (uint32_t)(GYNC_NX / 2), u, u1);
     const bool acc = u < exp(lfp - lf);              // Mamba: rand() < exp(logf(x') - logf(x))
     if (acc) {
       for (int d = 0; d < GYNC_NX; ++d) state[c + C * d] = XL[s + N * d];
@@ -161,7 +164,7 @@ gync_mcmc_accept_kernel(double* __restrict__ state, double* __restrict__ logf, l
   itc[c] = it;
   logf[c] = lf;
   naccept[c] = nacc;
-  atomicMin(min_it, it);
+  if (min_it) atomicMin(min_it, it);
 }
 
 // ------------------------------------------------------------------------------------------

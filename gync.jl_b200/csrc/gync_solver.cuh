@@ -96,7 +96,7 @@ struct GyncWork {          // host layout (tests); the device layout is GyncWork
   double q[GYNC_NQ];
   double y[GYNC_NY];
   double yn[GYNC_NY];
-  double k[5 * GYNC_NY];    // stage vectors k1..k5
+  double k[6 * GYNC_NY];    // stage vectors k1..k5 (+ the parked correction of the Rodas5P form)
   double e[GYNC_NY];
   double A[GYNC_NLU];
 };
@@ -188,6 +188,162 @@ GYNC_HD static double gync_rodas4_step(WK& W, const double h, const double rtol,
   return sqrt(sum * (1.0 / GYNC_NY));
 }
 
+// ---- Rodas5P (G. Steinebach, "Construction of Rosenbrock-Wanner method Rodas5P and numerical benchmarks within the
+// Julia Differential Equations package", BIT 63 (2023)): gamma = 0.2119..., 8 stages, order 5(4), stiffly accurate,
+// with the additional Prothero-Robinson / index-1 conditions of the "P" family.  Same implementation form as above.
+// tests/test_host_logic.py checks all 17 order conditions up to order 5 for the propagated weights and the 8 up to
+// order 4 for the embedded ones at round-off (tools/rodas5/order_conditions.py), so a wrong digit cannot hide.
+// Stages 7 and 8 start from the previous stage point plus the previous increment (a_7j = a_6j, a_76 = 1; a_8j = a_7j,
+// a_87 = 1), the new solution is the stage-8 point plus k8 and the error estimate is k8.
+#define R5_G   0.21193756319429014
+#define R5_A21 3.0
+#define R5_A31 2.849394379747939
+#define R5_A32 0.45842242204463923
+#define R5_A41 (-6.954028509809101)
+#define R5_A42 2.489845061869568
+#define R5_A43 (-10.358996098473584)
+#define R5_A51 2.8029986275628964
+#define R5_A52 0.5072464736228206
+#define R5_A53 (-0.3988312541770524)
+#define R5_A54 (-0.04721187230404641)
+#define R5_A61 (-7.502846399306121)
+#define R5_A62 2.561846144803919
+#define R5_A63 (-11.627539656261098)
+#define R5_A64 (-0.18268767659942256)
+#define R5_A65 0.030198172008377946
+#define R5_C21 (-14.155112264123755)
+#define R5_C31 (-17.97296035885952)
+#define R5_C32 (-2.859693295451294)
+#define R5_C41 147.12150275711716
+#define R5_C42 (-1.41221402718213)
+#define R5_C43 71.68940251302358
+#define R5_C51 165.43517024871676
+#define R5_C52 (-0.4592823456491126)
+#define R5_C53 42.90938336958603
+#define R5_C54 (-5.961986721573306)
+#define R5_C61 24.854864614690072
+#define R5_C62 (-3.0009227002832186)
+#define R5_C63 47.4931110020768
+#define R5_C64 5.5814197821558125
+#define R5_C65 (-0.6610691825249471)
+#define R5_C71 30.91273214028599
+#define R5_C72 (-3.1208243349937974)
+#define R5_C73 77.79954646070892
+#define R5_C74 34.28646028294783
+#define R5_C75 (-19.097331116725623)
+#define R5_C76 (-28.087943162872662)
+#define R5_C81 37.80277123390563
+#define R5_C82 (-3.2571969029072276)
+#define R5_C83 112.26918849496327
+#define R5_C84 66.9347231244047
+#define R5_C85 (-40.06618937091002)
+#define R5_C86 (-54.66780262877968)
+#define R5_C87 (-9.48861652309627)
+
+// Storage.  Stage i needs sum_j a_ij k_j and sum_j c_ij k_j over all earlier k_j, which for eight stages would mean
+// seven stored vectors — two more than RODAS4's tensor-memory layout has room for.  Two facts shrink it to FIVE:
+//  * k7 is only ever used by stage 8, where it is still in registers;
+//  * k6 is used by stage 7 (in registers) and by stage 8, where it enters as  1 * k6  in the stage point and  c86 * k6  in
+//    the correction.  Before stage 7 it is ABSORBED into the stored k4 and k5:  k4' = k4 + beta k6,  k5' = k5 + alpha k6
+//    with  a64 beta + a65 alpha = 1  and  c84 beta + c85 alpha = c86, so that stage 8's ordinary sums over (k1, k2, k3,
+//    k4', k5') already contain both k6 terms; stage 7's own sums over the primed vectors pick up (a64 beta + a65 alpha)
+//    k6 = k6 in the point (so its explicit k6 coefficient becomes 0) and (c74 beta + c75 alpha) k6 in the correction
+//    (so its explicit coefficient becomes c76 - c74 beta - c75 alpha).
+// Every stage is then the SAME code: point and correction as sums over at most five stored vectors plus the newest
+// one from registers.  (A first version replaced k1..k5 in place by the three combinations the last stages need; fewer
+// loads, but the extra code paths cost 1.3 KB of register spills in the step body and ran 1.9x slower per step.)
+#define R5_DET   (R5_C84 * R5_A65 - R5_C85 * R5_A64)
+#define R5_BETA  ((R5_C86 * R5_A65 - R5_C85) / R5_DET)      /* onto k4 */
+#define R5_ALPHA ((R5_C84 - R5_A64 * R5_C86) / R5_DET)      /* onto k5 */
+#define R5_NSTORE 5
+// row s serves stage s+2: coefficients of the stored vectors (slots 0..min(s,5)-1), then of the newest k (registers)
+GYNC_TABLE double R5_TA[7][5] = {{0, 0, 0, 0, 0},
+                                 {R5_A31, 0, 0, 0, 0},
+                                 {R5_A41, R5_A42, 0, 0, 0},
+                                 {R5_A51, R5_A52, R5_A53, 0, 0},
+                                 {R5_A61, R5_A62, R5_A63, R5_A64, 0},
+                                 {R5_A61, R5_A62, R5_A63, R5_A64, R5_A65},
+                                 {R5_A61, R5_A62, R5_A63, R5_A64, R5_A65}};
+GYNC_TABLE double R5_TC[7][5] = {{0, 0, 0, 0, 0},
+                                 {R5_C31, 0, 0, 0, 0},
+                                 {R5_C41, R5_C42, 0, 0, 0},
+                                 {R5_C51, R5_C52, R5_C53, 0, 0},
+                                 {R5_C61, R5_C62, R5_C63, R5_C64, 0},
+                                 {R5_C71, R5_C72, R5_C73, R5_C74, R5_C75},
+                                 {R5_C81, R5_C82, R5_C83, R5_C84, R5_C85}};
+GYNC_TABLE double R5_OA[7] = {R5_A21, R5_A32, R5_A43, R5_A54, R5_A65, 0.0, 1.0};
+GYNC_TABLE double R5_OC[7] = {R5_C21, R5_C32, R5_C43, R5_C54, R5_C65, R5_C76 - R5_C74 * R5_BETA - R5_C75 * R5_ALPHA, R5_C87};
+
+// One Rodas5P step attempt (generic storage: W.k holds SIX 33-vectors: slots 0..4 = k1..k5 (k4, k5 primed from stage 7
+// on), slot 5 = the correction of the stage in flight while the RHS overwrites the work vector).
+template <class WK>
+GYNC_HD static double gync_rodas5p_step(WK& W, const double h, const double rtol, const double atol) {
+  const double ih = GYNC_RCP(h);
+  gync_rhs_w(W.y, gync_ro(W.q), ih * (1.0 / R5_G), W.e, W.A);
+  gync_lu(W.A);
+  gync_lusolve(gync_ro(W.A), W.e);
+#pragma unroll 1
+  for (int s = 0; s < 7; ++s) {
+    if (s < R5_NSTORE) {
+#pragma unroll
+      for (int i = 0; i < GYNC_NY; ++i) W.k[s * GYNC_NY + i] = W.e[i];
+    } else if (s == R5_NSTORE) {
+#pragma unroll
+      for (int i = 0; i < GYNC_NY; ++i) {
+        W.k[3 * GYNC_NY + i] = fma(R5_BETA, W.e[i], (double)W.k[3 * GYNC_NY + i]);
+        W.k[4 * GYNC_NY + i] = fma(R5_ALPHA, W.e[i], (double)W.k[4 * GYNC_NY + i]);
+      }
+    }
+    {
+      const double a = R5_OA[s], c = R5_OC[s];
+#pragma unroll
+      for (int i = 0; i < GYNC_NY; ++i) { W.yn[i] = fma(a, W.e[i], W.y[i]); W.e[i] = c * W.e[i]; }
+    }
+    const int ns = s < R5_NSTORE ? s : R5_NSTORE;
+#pragma unroll 1
+    for (int j = 0; j < ns; ++j) {
+      const double a = R5_TA[s][j], c = R5_TC[s][j];
+#pragma unroll
+      for (int i = 0; i < GYNC_NY; ++i) {
+        const double kj = W.k[j * GYNC_NY + i];
+        W.yn[i] = fma(a, kj, W.yn[i]);
+        W.e[i] = fma(c, kj, W.e[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < GYNC_NY; ++i) W.k[5 * GYNC_NY + i] = W.e[i];
+    gync_rhs(W.yn, gync_ro(W.q), W.e);
+#pragma unroll
+    for (int i = 0; i < GYNC_NY; ++i) W.e[i] = fma(ih, (double)W.k[5 * GYNC_NY + i], W.e[i]);
+    gync_lusolve(gync_ro(W.A), W.e);
+  }
+  double sum = 0.0;
+#pragma unroll
+  for (int i = 0; i < GYNC_NY; ++i) {
+    W.yn[i] += W.e[i];
+    const double sc = atol + rtol * fmax(fabs(W.y[i]), fabs(W.yn[i]));
+    const double r = W.e[i] * GYNC_RCP(sc);
+    sum = fma(r, r, sum);
+  }
+  return sqrt(sum * (1.0 / GYNC_NY));
+}
+
+// Which method the library steps with: 5 = Rodas5P (default), 4 = RODAS4P (kept for A/B runs and the order tests).
+#ifndef GYNC_ROS_ORDER
+#define GYNC_ROS_ORDER 5
+#endif
+#if GYNC_ROS_ORDER == 5
+#  ifndef GYNC_ERR_ROOT
+#  define GYNC_ERR_ROOT(err) exp(0.2 * log(err))         /* embedded order 4: err ~ h^5 */
+#  endif
+template <class WK>
+GYNC_HD static double gync_ros_step(WK& W, const double h, const double rtol, const double atol) { return gync_rodas5p_step(W, h, rtol, atol); }
+#else
+#  define GYNC_ERR_ROOT(err) sqrt(sqrt(err))            /* embedded order 3: err ~ h^4 */
+template <class WK>
+GYNC_HD static double gync_ros_step(WK& W, const double h, const double rtol, const double atol) { return gync_rodas4_step(W, h, rtol, atol); }
+#endif
+
 // Step-size controller state (Hairer's RODAS controller with Gustafsson's predictive term).
 struct GyncCtrl {
   double h;        // next step to try
@@ -205,11 +361,11 @@ GYNC_HD static bool gync_ctrl_update(GyncCtrl& c, const double h, double err, co
     c.rej_last = 1;
     return false;
   }
-  double fac = fmax(FAC2, fmin(FAC1, sqrt(sqrt(err)) * (1.0 / SAFE)));
+  double fac = fmax(FAC2, fmin(FAC1, GYNC_ERR_ROOT(err) * (1.0 / SAFE)));
   double hnew = h / fac;
   if (err <= 1.0) {
     if (c.nacc > 0) {
-      double facgus = (c.hacc / h) * sqrt(sqrt(err * err / c.erracc)) * (1.0 / SAFE);
+      double facgus = (c.hacc / h) * GYNC_ERR_ROOT(err * err / c.erracc) * (1.0 / SAFE);
       facgus = fmax(FAC2, fmin(FAC1, facgus));
       fac = fmax(fac, facgus);
       hnew = h / fac;
@@ -278,7 +434,7 @@ GYNC_HD static int gync_attempt(WK& W, GyncCtrl& c, double& t, const double tend
   if (last) h = rem;
   if (!(h > 1e-14 * fmax(1.0, fabs(t)))) return -GYNC_ST_HMIN;
   const double hprop = c.h;
-  const double err = gync_rodas4_step(W, h, o.rtol, o.atol);
+  const double err = gync_ros_step(W, h, o.rtol, o.atol);
   const bool fin = gync_all_finite(W.yn, GYNC_NY);
   if (gync_ctrl_update(c, h, err, fin)) {
     t = last ? tend : t + h;

@@ -20,6 +20,33 @@ def shard_bounds(n: int, world: int, rank: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def sample_chains_sharded(samplings, iters, advance=None, rank=None, world=None, gather=True):
+    """sample!(s, iters) for MANY chains over the ranks (BASELINE configs[3]: 4096 chains over 8 GPUs; replaces the Slurm
+    fan-out of batch.jl:3-22).  Chains are independent, so each rank advances a contiguous block with its own persistent
+    kernel and there is NO data-path collective; the only communication is the optional gather of the finished
+    chains at the end (every rank then holds all of them, e.g. to build the WeightedChain).
+    Every chain gets its Philox stream id from its GLOBAL position before the split, so the chains do not depend on how
+    many ranks ran them.  `advance(local_samplings, iters)` defaults to api.sample_chains (the C ABI)."""
+    import torch.distributed as dist
+    if world is None:
+        world, rank = dist.get_world_size(), dist.get_rank()
+    for i, s in enumerate(samplings):
+        if s.variate.chain_id is None:
+            s.variate.chain_id = i
+    lo, hi = shard_bounds(len(samplings), world, rank)
+    if advance is None:
+        from . import api
+        advance = api.sample_chains
+    local = list(samplings[lo:hi])
+    if local:
+        advance(local, iters)
+    if not gather or world == 1:
+        return local
+    parts = [None] * world
+    dist.all_gather_object(parts, local)
+    return [s for part in parts for s in part]
+
+
 def em_iterate_sharded(niter, norms_fn, step_fn, allreduce):
     """EM on row shards.  norms_fn() -> local partial denominators (M);  step_fn(global_norms) ->
     local partial denominators of the NEXT iteration after updating the local weights in place;

@@ -61,7 +61,7 @@ void gync_dims(int32_t* ny, int32_t* np, int32_t* nx, int32_t* nq, int32_t* nlu)
  * rtol/atol <= 0 (or opts == NULL) select the library defaults below: the tolerance at which every
  * log-likelihood of the validation sets is within 1e-8 relative of the converged solution
  * (the reference's own default, 1e-4, is ~1e-3 away from it). */
-#define GYNC_DEFAULT_RTOL 3e-10
+#define GYNC_DEFAULT_RTOL 7e-10
 #define GYNC_DEFAULT_ATOL 1e-11
 typedef struct {
   double  rtol, atol;
@@ -123,6 +123,21 @@ int gync_mcmc_run(double* state, double* logf, int64_t C, const double* chol, do
                   const double* inj_z, const double* inj_u,
                   double* samples_out, int64_t* naccept);
 
+/* The same with an explicit Philox stream id per chain (chain_ids[c]; NULL = position c in this call), so that a chain
+ * keeps its own random stream when it is advanced in a different group or alone (resume, batch.jl:26-46).
+ * Non-adaptive chains run as ONE persistent launch per device (propose / solve / accept / re-propose on the device, no
+ * host round trip between rounds); under gync_init_multi the chains are sharded over the devices in contiguous blocks. */
+int gync_mcmc_run_ids(double* state, double* logf, int64_t C, const double* chol, double prop_sd,
+                      const double* data, int32_t M, const double* sigma_rho,
+                      const int32_t* patient_of_chain, const gync_prior* prior,
+                      const gync_solver_opts* opts, int64_t iters, int32_t thin,
+                      uint64_t seed, uint64_t iter_offset, const uint64_t* chain_ids,
+                      const double* inj_z, const double* inj_u,
+                      double* samples_out, int64_t* naccept);
+/* Likelihood solves started and Rosenbrock step attempts of the last gync_mcmc_run* call (all devices), and the number of
+ * speculative slots per chain round it used: iterations / solves is the efficiency of the speculation. */
+void gync_mcmc_last_stats(uint64_t* solves, uint64_t* steps, int32_t* slots_per_round);
+
 /* ---- the same with Mamba's adaptation switched on (Config.adapt = true; model.jl:104-106, sampling.jl:72) ----------
  * AMMTune state per chain, in/out so that a Sampling can be continued (sampling.jl:62-68) and propadapt() read
  * (sampling.jl:26-29).  m[c] < 0 on entry: adaptation starts here (m = 0, Mv = v, Mvv = v v', SigmaLm = SigmaL).
@@ -142,6 +157,13 @@ int gync_mcmc_run_amm(double* state, double* logf, int64_t C, const double* chol
                       uint64_t seed, uint64_t iter_offset,
                       const double* inj_z, const double* inj_u, const double* inj_umix /* iters x C */,
                       double* samples_out, int64_t* naccept, const gync_amm_tune* tune);
+int gync_mcmc_run_amm_ids(double* state, double* logf, int64_t C, const double* chol, double prop_sd,
+                          const double* data, int32_t M, const double* sigma_rho,
+                          const int32_t* patient_of_chain, const gync_prior* prior,
+                          const gync_solver_opts* opts, int64_t iters, int32_t thin,
+                          uint64_t seed, uint64_t iter_offset, const uint64_t* chain_ids,
+                          const double* inj_z, const double* inj_u, const double* inj_umix /* iters x C */,
+                          double* samples_out, int64_t* naccept, const gync_amm_tune* tune);
 
 /* ---- emiteration!(w,L) / emiterations — em.jl:27-41, em.jl:5 ----------------------------
  * L: K x M, w: K (updated in place, niter times).  history (nullable): K x niter, column i =
@@ -255,8 +277,10 @@ int gync_wc_rows_dev(double* dL_inout, const double* d_logprior, const int64_t* 
                      const double* d_stats, double* d_weights, double* d_density, double* d_total, void* stream);
 int gync_wc_scale_dev(double* d_density, int64_t K, const double* d_total, void* stream);
 
-/* FP64 flops of one RODAS4 step attempt (counted from the generated code; roofline bookkeeping). */
+/* FP64 flops of one Rosenbrock step attempt (counted from the generated code; roofline bookkeeping), and the order of
+ * the method the library was built with (5: Rodas5P, the default; 4: RODAS4P). */
 double gync_flops_per_step(void);
+int gync_method_order(void);
 /* FP64 FMA peak microbenchmark (TFLOP/s) used as the solver's roofline denominator. */
 int gync_fp64_peak(double* tflops);
 

@@ -41,7 +41,7 @@ function check(rc::Cint)
 end
 
 # --- gync(y0,p,t;reltol,abstol)  (src/gync/gyncycle.jl:8-26) -------------------------------
-function gync(y0::Vector, p::Vector, t::Vector; reltol=3e-10, abstol=1e-11)
+function gync(y0::Vector, p::Vector, t::Vector; reltol=7e-10, abstol=1e-11)
   Y  = Array(Float64, length(t), length(y0))           # N = 1: exactly the reference's nT x 33 layout
   st = Cint[0]
   o  = Ref(SolverOpts(reltol, abstol))
@@ -52,7 +52,7 @@ function gync(y0::Vector, p::Vector, t::Vector; reltol=3e-10, abstol=1e-11)
 end
 
 # --- llh(c,x) (model.jl:128-155), llh(s::Sampling) (sampling.jl:32) --------------------------
-function loglikmatrix(X::Matrix{Float64}, datas::Vector{Matrix{Float64}}, sigmas::Vector{Float64}; reltol=3e-10, abstol=1e-11)
+function loglikmatrix(X::Matrix{Float64}, datas::Vector{Matrix{Float64}}, sigmas::Vector{Float64}; reltol=7e-10, abstol=1e-11)
   N, M = size(X, 1), length(datas)
   D  = cat(3, datas...)                                # 31 x 4 x M, NaN = missing
   LL = Array(Float64, N, M)
@@ -105,7 +105,7 @@ function sample!(s::Sampling, iters::Int)
   nacc  = Int64[0]
   state = reshape(copy(v.state), 1, 116)
   lf    = [v.logf]
-  o     = Ref(SolverOpts(3e-10, 1e-11))
+  o     = Ref(SolverOpts(7e-10, 1e-11))
   if c.adapt                                            # Mamba.sample!(variate, adapt=true) (sampling.jl:72, model.jl:104-106)
     tune = Ref(AmmTune(0.05, 2.38, pointer(v.m), pointer(v.Mv), pointer(v.Mvv), pointer(v.SigmaLm)))
     check(ccall((:gync_mcmc_run_amm, LIBGYNC), Cint,
@@ -175,7 +175,7 @@ function phi(xs::Vector{Vector{Float64}})
   X  = vcat([x' for x in xs]...)                        # N x 116
   Y  = Array(Float64, 124, length(xs))
   st = Array(Cint, length(xs))
-  o  = Ref(SolverOpts(3e-10, 1e-11))
+  o  = Ref(SolverOpts(7e-10, 1e-11))
   check(ccall((:gync_phi_batch, LIBGYNC), Cint, (Ptr{Cdouble}, Int64, Ptr{SolverOpts}, Ptr{Cdouble}, Ptr{Cint}),
               X, length(xs), o, Y, st))
   [reshape(Y[:, n], 31, 4) for n in 1:length(xs)]       # NaN matrix on solver failure (gyncycle.jl:18-19)

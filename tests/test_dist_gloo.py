@@ -164,3 +164,64 @@ def test_sharded_mple_gloo_world2(tmp_path):
                        capture_output=True, text=True, env=env, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("ok") == 2
+
+
+WORKER_CHAINS = r'''
+import os, sys
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "oracle"))
+from gync_b200.dist import shard_bounds, sample_chains_sharded
+from gync_b200 import api
+import gync_oracle as o
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+g = np.load(os.path.join({root!r}, "tests", "golden", "solution_golden.npz"))
+means, stds = g["gmm_means"], g["gmm_stds"]
+
+def advance(ss, iters):
+    """Stand-in for the device sampler: the oracle's Metropolis step on a cheap surrogate of the target (log-prior +
+    Jacobian term, no solve), randomness addressed by (seed, chain_id, iteration) like the device's Philox streams."""
+    for s in ss:
+        v = s.variate
+        logf = lambda xl: o.logprior(np.exp(xl), means, stds) + xl.sum()
+        cur = logf(v.state) if np.isnan(v.logf) else v.logf
+        rows = []
+        for it in range(v.iteration, v.iteration + iters):
+            r = np.random.Generator(np.random.Philox(key=[v.seed, v.chain_id], counter=it))
+            v.state, cur, a = o.metropolis_step(v.state, cur, v.SigmaL, r.standard_normal(116), r.random(), logf)
+            v.naccept += int(a)
+            rows.append(np.exp(v.state))
+        v.logf, v.iteration = cur, v.iteration + iters
+        s.samples = np.vstack([s.samples, np.array(rows)])
+
+mk = lambda: [api.new_sampling(api.Config(propvar=api.uniformpropvar(0.03)), seed=77) for _ in range(7)]   # 2 ranks: blocks of 4 and 3
+allc = sample_chains_sharded(mk(), 15, advance=advance)
+assert len(allc) == 7 and [s.variate.chain_id for s in allc] == list(range(7))
+lo, hi = shard_bounds(7, world, rank)
+mine = sample_chains_sharded(mk(), 15, advance=advance, gather=False)
+assert len(mine) == hi - lo
+ref = mk()
+for i, s in enumerate(ref):
+    s.variate.chain_id = i
+advance(ref, 15)                                                              # the unsharded run
+for a, b in zip(allc, ref):
+    assert np.array_equal(a.samples, b.samples) and a.variate.naccept == b.variate.naccept
+moved = [s for s in allc if s.variate.naccept > 0]
+assert len(moved) >= 2 and len({{s.samples.tobytes() for s in moved}}) == len(moved)     # same seed, distinct streams
+print("rank", rank, "ok")
+dist.destroy_process_group()
+'''
+
+
+def test_sharded_chains_gloo_world2(tmp_path):
+    """Chain sharding (SURVEY 8e, K3 row): contiguous blocks, no data-path collective, results independent of the world
+    size because every chain carries its own stream id."""
+    script = tmp_path / "worker_chains.py"
+    script.write_text(WORKER_CHAINS.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29564", str(script)],
+                       capture_output=True, text=True, env=env, timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ok") == 2

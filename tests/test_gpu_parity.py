@@ -98,7 +98,16 @@ def test_wide_set_failure_set_and_values(gpu):
     assert 0.1 < fin.mean() < 0.5
     assert np.array_equal(st == 0, fin), np.flatnonzero((st == 0) != fin)
     assert np.all(LL[~fin, 0] == -np.inf)
-    assert relerr(LL[fin, 0], g["LL_W"][fin]) <= RTOL_LLH
+    # the oracle's own conditioning of each fixture value: its 1e-12 and 1e-13 runs (tests/golden/add_wide_conditioning.py)
+    with np.errstate(invalid="ignore"):
+        unc = np.abs(g["LL_W_1e13"] - g["LL_W"]) / np.abs(g["LL_W"])
+        E = np.abs(LL[:, 0] - g["LL_W"]) / np.abs(g["LL_W"])
+    well = fin & (unc <= 1e-10)
+    assert well.sum() >= 100
+    assert E[well].max() <= RTOL_LLH, E[well].max()
+    # 12 of the 117 solvable draws amplify integration error so much that the ORACLE moves by 1e-10 .. 1.1e-8 between its
+    # two tightest settings; there the fixture cannot carry a 1e-8 bound, the check is 3e-8
+    assert E[fin & ~well].max() <= 3e-8, E[fin & ~well].max()
 
 
 def test_loglik_epilogue_in_isolation(gpu, gold):
@@ -530,6 +539,104 @@ def test_sample_api_shapes_and_reproducibility(gpu):
     assert w.likelihoods.shape[1] == 2 and abs(w.weights.sum() - 1) < 1e-12
     assert gpu.sample(w, 10).shape == (10, 116)
     gpu.emiteration_bang(w)
+
+
+def test_persistent_kernel_equals_round_loop(gpu):
+    """The persistent Metropolis kernel (gync_mcmc_persist.cuh: chains advance out of step, rounds re-proposed on the
+    device) produces bit-identical chains to the round-1 host loop of separate propose / solve / accept launches
+    (GYNC_MCMC_ROUNDS=1), for one chain and for several chains with different patients, thinned and not."""
+    for thin, iters, pats in ((1, 40, (1,)), (3, 45, (1, 2, 3, 4, 5))):
+        runs = []
+        for rounds in (False, True):
+            if rounds:
+                os.environ["GYNC_MCMC_ROUNDS"] = "1"
+            try:
+                ss = gpu.sample_chains([gpu.new_sampling(gpu.Config(gpu.Lausanne(i), thin=thin), seed=21) for i in pats], iters)
+            finally:
+                os.environ.pop("GYNC_MCMC_ROUNDS", None)
+            runs.append(ss)
+        for a, b in zip(*runs):
+            assert a.samples.shape == (iters // thin, 116)
+            assert np.array_equal(a.samples, b.samples) and a.variate.naccept == b.variate.naccept
+            assert a.variate.logf == b.variate.logf and np.array_equal(a.variate.state, b.variate.state)
+        assert sum(x.variate.naccept for x in runs[0]) > 0
+    solves, steps, k = C.c_uint64(), C.c_uint64(), C.c_int32()
+    gpu.lib.load().gync_mcmc_last_stats(C.byref(solves), C.byref(steps), C.byref(k))
+    assert k.value >= 1        # the last call above was a round-loop run: the counters belong to the persistent run before it
+
+
+def test_chain_keeps_its_random_stream_when_resumed_alone(gpu, tmp_path):
+    """A chain advanced inside a group and later resumed ALONE (sample!, batch, load) continues the stream it would have
+    drawn from inside the group: the Philox stream id is the variate's chain_id, persisted by save/load, not the
+    position in the call.  Chains of one group started with the same seed do not share their noise."""
+    mk = lambda: [gpu.new_sampling(gpu.Config(gpu.Lausanne(i)), seed=9) for i in (1, 1, 2)]
+    ref = gpu.sample_chains(mk(), 24)
+    assert [x.variate.chain_id for x in ref] == [0, 1, 2]
+    assert not np.array_equal(ref[0].samples, ref[1].samples)            # same patient, same seed, different stream
+    ss = gpu.sample_chains(mk(), 12)
+    path = str(tmp_path / "chain2.jld")
+    gpu.api.save(path, ss[2])
+    alone = gpu.sample_bang(gpu.api.load(path), 12)                       # position 0 of its own call, stream 2
+    assert alone.variate.chain_id == 2
+    assert np.array_equal(alone.samples, ref[2].samples) and alone.variate.naccept == ref[2].variate.naccept
+    pair = gpu.sample_chains([ss[1], ss[0]], 12)                          # regrouped in another order
+    assert np.array_equal(pair[0].samples, ref[1].samples) and np.array_equal(pair[1].samples, ref[0].samples)
+    # chains created without a seed get the process seed and distinct stream ids
+    a, b = gpu.new_sampling(gpu.Config()), gpu.new_sampling(gpu.Config())
+    assert a.variate.seed == b.variate.seed and a.variate.chain_id != b.variate.chain_id
+
+
+def test_mcmc_statistics_vs_independent_cpu_metropolis(gpu, gold):
+    """the chains are not only step-exact with injected draws, they are the right Markov
+    chain with their OWN randomness.  512 device chains (Philox) and 32 independent CPU chains (numpy PCG64, the oracle's
+    metropolis_step, log-target through the C oracle at 1e-8) start from the reference point on the real target
+    (Lausanne 1, sigma_rho = 0.1) and run 150 iterations; acceptance counts, the squared displacement and every
+    coordinate's mean of the final state must agree within Monte-Carlo error (independent chains: MCSE = s / sqrt(n))."""
+    import c_oracle as co
+    import gync_oracle as o
+    means, stds = gold["gmm_means"], gold["gmm_stds"]
+    data = o.patients()[0][0]
+    iters, n_gpu, n_cpu = 150, 512, 32
+    cfg = gpu.Config(gpu.Patient(data, "l1"), priory0=gpu.api.GaussianMixture(means, stds))
+    ss = gpu.sample_chains([gpu.new_sampling(cfg, seed=123) for _ in range(n_gpu)], iters)
+    x0 = np.log(o.init_x())
+    XG = np.log(np.array([s_.samples[-1] for s_ in ss]))
+    AG = np.array([s_.variate.naccept for s_ in ss], dtype=float)
+
+    rng = np.random.Generator(np.random.PCG64(2024))
+    sd = np.sqrt(np.log(1.01))
+    SL = np.eye(116) * sd
+    x = np.tile(x0, (n_cpu, 1))
+
+    def logf_batch(XL):
+        X = np.exp(XL)
+        lp = np.array([o.logprior(v, means, stds) for v in X])
+        out = np.full(len(X), -np.inf)
+        ok = np.isfinite(lp)
+        if ok.any():
+            out[ok] = lp[ok] + co.llh_batch(X[ok], [data], [0.1], 1, 1e-8, 1e-8)[:, 0] + XL[ok].sum(1)
+        return out
+    cur = logf_batch(x)
+    AC = np.zeros(n_cpu)
+    for _ in range(iters):
+        z, u = rng.standard_normal((n_cpu, 116)), rng.random(n_cpu)
+        lpn = logf_batch(x + z @ SL.T)
+        for c_ in range(n_cpu):
+            x[c_], cur[c_], a = o.metropolis_step(x[c_], cur[c_], SL, z[c_], u[c_], lambda v, c_=c_: lpn[c_])
+            AC[c_] += a
+
+    def close(g_, c_, what, k=4.5):
+        se = np.sqrt(g_.var(ddof=1) / len(g_) + c_.var(ddof=1) / len(c_))
+        assert abs(g_.mean() - c_.mean()) <= k * se, (what, g_.mean(), c_.mean(), se)
+    assert 0.02 < AG.mean() / iters < 0.5
+    close(AG, AC, "acceptance count")
+    close(((XG - x0) ** 2).sum(1), ((x - x0) ** 2).sum(1), "squared displacement")
+    se = np.sqrt(XG.var(0, ddof=1) / n_gpu + x.var(0, ddof=1) / n_cpu)
+    zscore = np.abs(XG.mean(0) - x.mean(0)) / se
+    assert zscore.max() < 5.0, (int(zscore.argmax()), float(zscore.max()))          # 116 coordinates: max |z| ~ 3 expected
+    assert np.mean(zscore ** 2) < 1.6                                               # and the z-scores are N(0,1)-sized as a set
+    vr = XG.var(0, ddof=1).sum() / x.var(0, ddof=1).sum()
+    assert 0.6 < vr < 1.6, vr                                                       # total variance of the final states
 
 
 def test_wc_normalize_vs_oracle(gpu):

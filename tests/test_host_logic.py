@@ -13,7 +13,7 @@ import gync_oracle as o
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, "tests", "golden")
-PARITY_RTOL, PARITY_ATOL = 3e-10, 1e-11     # library defaults (include/gync_b200.h, api.DEFAULT_RTOL/ATOL)
+PARITY_RTOL, PARITY_ATOL = 7e-10, 1e-11     # library defaults (include/gync_b200.h, api.DEFAULT_RTOL/ATOL)
 dp = C.POINTER(C.c_double)
 P = lambda a: a.ctypes.data_as(dp)  # noqa: E731
 
@@ -162,7 +162,7 @@ def test_default_tolerances_agree_everywhere():
     import gync_b200 as g
     assert (rt, at) == (PARITY_RTOL, PARITY_ATOL) == (g.api.DEFAULT_RTOL, g.api.DEFAULT_ATOL)
     jl = open(os.path.join(ROOT, "julia", "GynCB200.jl")).read()
-    assert "reltol=3e-10, abstol=1e-11" in jl and "1e-8, 1e-10" not in jl
+    assert "reltol=7e-10, abstol=1e-11" in jl and "1e-8, 1e-10" not in jl
 
 
 def test_rodas4_generic_grid_and_order(host_shim):

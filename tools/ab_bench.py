@@ -1,5 +1,5 @@
 """A/B timing of several builds of libgync_b200.so in ONE process on ONE box (boxes differ by ~10 %).
-   GYNC_LIBS=a.so,b.so,...  N=32768 REPS=3 python tools/ab_bench.py"""
+   GYNC_LIBS=a.so,b.so,...  [GYNC_TOLS=rtol:atol,rtol:atol,...]  N=32768 REPS=3 python tools/ab_bench.py"""
 import ctypes as C, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -17,7 +17,8 @@ dX = torch.from_numpy(np.ascontiguousarray(X.T)).cuda()
 dD = torch.from_numpy(np.ascontiguousarray(data.T)).cuda()
 dS = torch.tensor([0.1], dtype=torch.float64, device="cuda")
 st = torch.cuda.current_stream().cuda_stream
-op = L.opts(rtol, atol)
+tols = [tuple(float(v) for v in t.split(":")) for t in os.environ["GYNC_TOLS"].split(",")] if os.environ.get("GYNC_TOLS") else [(rtol, atol)] * len(libs)
+ops = [L.opts(rt, at) for rt, at in tols]
 handles = []
 for p in libs:
     h = C.CDLL(os.path.join(ROOT, p) if not os.path.isabs(p) else p)
@@ -27,7 +28,7 @@ for p in libs:
 outs = [torch.empty(N, dtype=torch.float64, device="cuda") for _ in libs]
 res = {p: [] for p in libs}
 for r in range(reps + 1):
-    for p, h, o in zip(libs, handles, outs):
+    for p, h, o, op in zip(libs, handles, outs, ops):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         rc = h.gync_loglik_batch_dev(dX.data_ptr(), N, dD.data_ptr(), 1, dS.data_ptr(), C.byref(op), o.data_ptr(), None, None, None, st)

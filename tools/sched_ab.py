@@ -14,7 +14,7 @@ dX = torch.from_numpy(np.ascontiguousarray(X.T)).cuda()
 dD = torch.from_numpy(np.ascontiguousarray(api.Lausanne(1).data.T)).cuda()
 dS = torch.tensor([0.1], dtype=torch.float64, device="cuda")
 st = torch.cuda.current_stream().cuda_stream
-op = L.opts(3e-10, 1e-11)
+op = L.opts(7e-10, 1e-11)
 flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")
 outs = {}
 for name, env in (("sched", None), ("no-sched", "1"), ("sched again", None)):

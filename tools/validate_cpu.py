@@ -30,10 +30,10 @@ def traj(x, rt, at):
 
 
 if __name__ == "__main__":
-    tols = [tuple(float(v) for v in a.split(":")) for a in sys.argv[1:]] or [(3e-10, 1e-11)]
+    tols = [tuple(float(v) for v in a.split(":")) for a in sys.argv[1:]] or [(7e-10, 1e-11)]
     g = np.load(os.path.join(ROOT, "tests", "golden", "nearset_llh_golden.npz"))
     la = o.patients()[0]
-    out = {"how": "python tools/validate_cpu.py " + " ".join(sys.argv[1:]) + "  (CPU build of csrc/gync_solver.cuh, RODAS4P)"}
+    out = {"how": "python tools/validate_cpu.py " + " ".join(sys.argv[1:]) + "  (CPU build of csrc/gync_solver.cuh, Rodas5P)"}
     for rt, at in tols:
         key = f"rtol{rt:g}_atol{at:g}"
         out[key] = {}
