@@ -25,7 +25,7 @@ int gync_logprior_batch(const double* X, int64_t N, const gync_prior* prior, dou
 // ---- K3p host side: one persistent launch per device (gync_mcmc_persist.cuh).  Chains shard over the devices of
 // gync_init_multi in contiguous blocks (independent chains, no data-path collective); every device runs
 // its block asynchronously and the host only waits once, at the end.
-struct McmcStats { unsigned long long solves = 0, steps = 0; };
+struct McmcStats { unsigned long long solves = 0, steps = 0, cancelled = 0, failed = 0, hist[24] = {0}; };
 static McmcStats g_mcmc_stats;          // last gync_mcmc_run: likelihood solves started / step attempts (all devices)
 static int g_mcmc_K = 0;                // slots per chain round of the last run
 
@@ -33,7 +33,7 @@ namespace {
 struct McmcJob {
   int64_t lo = 0, n = 0;
   int K = 1;
-  DBuf dS, dLf, dIt, dAcc, dLeft, dRk, dLfp, dQ, dCtl, dCh, dD, dSig, dPat, dPr, dZ, dU, dOut, dIsc, dNan, dIds;
+  DBuf dS, dLf, dIt, dTl, dAcc, dGen, dPend, dIss, dNc, dLfp, dSt, dDt, dQ, dCtl, dCh, dD, dSig, dPat, dPr, dZ, dU, dOut, dIsc, dNan, dIds;
   // scratch of the initial log-target evaluation
   DBuf dXL, dX, dLpr, dLL, dPs;
   GyncMcmcP P;
@@ -48,7 +48,8 @@ static int mcmc_persist_impl(double* state, double* logf, int64_t C, const doubl
   const int64_t n_out = iters / thin;
   const int nd = (g_devs.size() > 1 && C >= (int64_t)g_devs.size()) ? (int)g_devs.size() : 1;
   const int home = [&] { for (size_t i = 0; i < g_devs.size(); ++i) if (g_devs[i].device == g_device) return (int)i; return 0; }();
-  const GyncSolverOpts so = to_opts(opts);
+  GyncSolverOpts so = to_opts(opts);
+  if (const char* v = getenv("GYNC_MCMC_MAXSTEPS")) so.max_steps = std::max(100, atoi(v));
   bool need_init = false;
   for (int64_t c = 0; c < C; ++c) need_init |= !(logf[c] == logf[c]);
   std::vector<McmcJob> jobs(nd);
@@ -61,24 +62,34 @@ static int mcmc_persist_impl(double* state, double* logf, int64_t C, const doubl
     if (nd > 1) if (int rc = use_device(i)) return rc;
     cudaStream_t s = g_stream;
     const int64_t n = J.n, lanes = (int64_t)g_num_sms * GYNC_TM_NSLOT;
-    // slots per round: enough outstanding work for 1.5 solves per lane (chains run out of step with each other, so a
-    // lane only idles when the queue is empty); fewer slots waste fewer speculative solves after an acceptance
-    double over = 1.5;
+    // proposals in flight per chain: 1.1 per lane in total (a lane only idles when the queue is empty; more in flight
+    // only adds solves that the next acceptance cancels); look-ahead ring: 4x that
+    double over = 1.1;
     if (const char* v = getenv("GYNC_MCMC_OVERSUB")) over = std::max(0.25, atof(v));
     int K = (int)std::max<int64_t>(1, std::min<int64_t>(1024, (int64_t)(over * (double)lanes / (double)n + 0.5)));
     if (const char* v = getenv("GYNC_MCMC_SPEC")) K = std::max(1, std::min(4096, atoi(v)));
     K = (int)std::min<int64_t>(K, std::max<int64_t>(iters, 1));
     J.K = K;
     g_mcmc_K = K;
+    const bool fixedK = getenv("GYNC_MCMC_SPEC") != nullptr;             // tests pin the depth: no growth
+    const int64_t ring_cap = std::max<int64_t>(8, (512LL << 20) / (48 * n));        // ring storage <= 512 MB per device
+    if (K > ring_cap / 2) { K = (int)(ring_cap / 2); J.K = K; g_mcmc_K = K; }
+    const int Kmax = fixedK ? K : (int)std::min<int64_t>(std::min<int64_t>(1024, ring_cap / 2), std::max<int64_t>(iters, 1));
+    const int R = (int)std::min<int64_t>(std::max<int64_t>(2 * (int64_t)Kmax, std::max<int64_t>(4 * (int64_t)K, 8)), std::max<int64_t>(iters, 1));
     int qshift = 1;
-    while ((1LL << qshift) < 2 * n * K + 2) ++qshift;
+    while ((1LL << qshift) < 4 * (n * K + (int64_t)(over * (double)lanes) + n) + 2) ++qshift;
     CK(J.dS.alloc(sizeof(double) * n * GYNC_NX));
     CK(J.dLf.alloc(sizeof(double) * n));
     CK(J.dIt.alloc(sizeof(long long) * n));
     CK(J.dAcc.alloc(sizeof(long long) * n));
-    CK(J.dLeft.alloc(sizeof(int) * n));
-    CK(J.dRk.alloc(sizeof(int) * n));
-    CK(J.dLfp.alloc(sizeof(double) * n * K));
+    CK(J.dTl.alloc(sizeof(long long) * n));
+    CK(J.dGen.alloc(sizeof(int) * n));
+    CK(J.dPend.alloc(sizeof(int) * n));
+    CK(J.dIss.alloc(sizeof(int) * n));
+    CK(J.dNc.alloc(sizeof(int) * 2 * n));
+    CK(J.dLfp.alloc(sizeof(double) * n * 2 * R));
+    CK(J.dSt.alloc(sizeof(unsigned long long) * n * 2 * R));
+    CK(J.dDt.alloc(sizeof(unsigned long long) * n * 2 * R));
     CK(J.dQ.alloc(sizeof(unsigned long long) << qshift));
     CK(J.dCtl.alloc(sizeof(GyncMcmcCtl)));
     CK(J.dD.alloc(sizeof(double) * 124 * M));
@@ -94,6 +105,13 @@ static int mcmc_persist_impl(double* state, double* logf, int64_t C, const doubl
     CK(cudaMemcpyAsync(J.dPr.p, prior, sizeof(gync_prior), cudaMemcpyHostToDevice, s));
     CK(cudaMemsetAsync(J.dAcc.p, 0, sizeof(long long) * n, s));
     CK(cudaMemsetAsync(J.dIt.p, 0, sizeof(long long) * n, s));
+    CK(cudaMemsetAsync(J.dTl.p, 0, sizeof(long long) * n, s));
+    CK(cudaMemsetAsync(J.dGen.p, 0, sizeof(int) * n, s));
+    CK(cudaMemsetAsync(J.dPend.p, 0, sizeof(int) * n, s));
+    CK(cudaMemsetAsync(J.dIss.p, 0, sizeof(int) * n, s));
+    CK(cudaMemsetAsync(J.dNc.p, 0, sizeof(int) * 2 * n, s));
+    CK(cudaMemsetAsync(J.dSt.p, 0, sizeof(unsigned long long) * n * 2 * R, s));
+    CK(cudaMemsetAsync(J.dDt.p, 0, sizeof(unsigned long long) * n * 2 * R, s));
     CK(cudaMemsetAsync(J.dQ.p, 0, sizeof(unsigned long long) << qshift, s));
     CK(cudaMemsetAsync(J.dCtl.p, 0, sizeof(GyncMcmcCtl), s));
     if (chol) {
@@ -120,9 +138,12 @@ static int mcmc_persist_impl(double* state, double* logf, int64_t C, const doubl
     GyncMcmcP& P = J.P;
     memset(&P, 0, sizeof(P));
     P.state = J.dS.as<double>(); P.logf = J.dLf.as<double>(); P.itc = J.dIt.as<long long>(); P.naccept = J.dAcc.as<long long>();
-    P.round_left = J.dLeft.as<int>(); P.round_k = J.dRk.as<int>(); P.lfp = J.dLfp.as<double>();
+    P.tailc = J.dTl.as<long long>(); P.gen = J.dGen.as<int>(); P.pending = J.dPend.as<int>(); P.issued = J.dIss.as<int>(); P.ncomp = J.dNc.as<int>(); P.lfp = J.dLfp.as<double>();
+    P.slot_tag = J.dSt.as<unsigned long long>(); P.done_tag = J.dDt.as<unsigned long long>();
+    P.idle_limit = 60LL * 1900000000LL;      // ~60 s of SM clock
     P.queue = J.dQ.as<unsigned long long>(); P.qmask = (1ull << qshift) - 1ull; P.qshift = qshift; P.ctl = J.dCtl.as<GyncMcmcCtl>();
-    P.C = n; P.K = K; P.iters = iters; P.thin = thin;
+    P.C = n; P.W = K; P.Wmax = Kmax; P.inflight_target = fixedK ? (long long)n * K : (long long)std::max<double>(over * (double)lanes, (double)n);
+    P.total_iters = (unsigned long long)n * (unsigned long long)iters; P.R = R; P.iters = iters; P.thin = thin;
     P.chol = chol ? J.dCh.as<double>() : nullptr; P.prop_sd = prop_sd; P.pr = J.dPr.as<GyncPriorDev>();
     P.seed = seed; P.iter_offset = iter_offset;
     P.chain_ids = chain_ids ? J.dIds.as<unsigned long long>() : nullptr; P.chain_id_base = (unsigned long long)J.lo;
@@ -172,8 +193,17 @@ static int mcmc_persist_impl(double* state, double* logf, int64_t C, const doubl
     GyncMcmcCtl ctl;
     cudaError_t e = cudaMemcpyAsync(&ctl, J.dCtl.p, sizeof(ctl), cudaMemcpyDeviceToHost, g_stream);
     if (e == cudaSuccess) e = wait_stream(g_stream);
+#ifdef GYNC_MCMC_PROFILE
+    if (e == cudaSuccess) fprintf(stderr, "[mcmc profile] device slot %d: lane-trips active %llu idle %llu | sleeps %llu | cycles/lane-trip: fetch %.0f step %.0f complete %.0f\n",
+            i, ctl.trips_active, ctl.trips_idle, ctl.sleeps,
+            (double)ctl.cyc_fetch / (double)(ctl.trips_active + ctl.trips_idle + ctl.sleeps + 1),
+            (double)ctl.cyc_step / (double)(ctl.trips_active + ctl.trips_idle + 1),
+            (double)ctl.cyc_complete / (double)(ctl.trips_active + ctl.trips_idle + 1));
+#endif
     if (e != cudaSuccess) rc_all = fail(GYNC_ERR_CUDA, std::string("gync_mcmc_run: ") + cudaGetErrorString(e));
-    else { g_mcmc_stats.solves += ctl.solves; g_mcmc_stats.steps += ctl.steps; }
+    else if (ctl.abort) rc_all = fail(GYNC_ERR_CUDA, "gync_mcmc_run: the persistent kernel's watchdog fired (no progress)");
+    else { g_mcmc_stats.solves += ctl.solves; g_mcmc_stats.steps += ctl.steps; g_mcmc_stats.cancelled += ctl.cancelled;
+           g_mcmc_stats.failed += ctl.failed; for (int b = 0; b < 24; ++b) g_mcmc_stats.hist[b] += ctl.hist[b]; }
     J = McmcJob();                // free on the owning device
   }
   if (nd > 1) if (int rc = use_device(home)) return rc;
@@ -393,6 +423,12 @@ void gync_mcmc_last_stats(uint64_t* solves, uint64_t* steps, int32_t* slots_per_
   if (solves) *solves = g_mcmc_stats.solves;
   if (steps) *steps = g_mcmc_stats.steps;
   if (slots_per_round) *slots_per_round = g_mcmc_K;
+}
+uint64_t gync_mcmc_last_cancelled(void) { return g_mcmc_stats.cancelled; }
+// completed solves of the last run by floor(log2(step attempts)) (24 bins), and how many of them failed
+void gync_mcmc_last_histogram(uint64_t* hist24, uint64_t* failed) {
+  if (hist24) for (int b = 0; b < 24; ++b) hist24[b] = g_mcmc_stats.hist[b];
+  if (failed) *failed = g_mcmc_stats.failed;
 }
 
 int gync_wc_normalize_dev(double* dLL_inout, const double* d_logprior, const int64_t* d_counts, int64_t K, int32_t M,

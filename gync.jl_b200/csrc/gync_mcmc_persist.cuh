@@ -1,50 +1,85 @@
 // K3p: many-chain Metropolis as ONE persistent kernel — propose, solve, score, accept and re-propose on the device, with
-// no kernel boundary, host copy or synchronisation between rounds.
+// no kernel boundary, host copy or synchronisation anywhere inside the run.
 //
-// Replaces the round loop of Mamba.sample! behind sample!(s::Sampling, iters) (reference src/gync/sampling.jl:62-79,
-// target src/gync/model.jl:97-107) for non-adaptive chains.  Same speculative scheme as gync_mcmc.cuh (the proposals of
-// iterations i .. i+K-1 of a chain are evaluated at once from its current state; an ordered scan keeps everything up to
-// and including the first acceptance — exactly the sequential chain, for every K), but the rounds of different chains
-// are no longer in lock step:
+// Replaces the loop of Mamba.sample! behind sample!(s::Sampling, iters) (reference src/gync/sampling.jl:62-79, target
+// src/gync/model.jl:97-107) for non-adaptive chains.  The speculation is the one of gync_mcmc.cuh — the proposals of
+// the next iterations of a chain are evaluated from its current state, and an ORDERED scan keeps everything up to and
+// including the first acceptance, which is exactly the sequential chain for every window size — but nothing here is
+// in lock step:
 //
-//   * the solver lanes (the tensor-memory layout of K1: 128 lanes per SM, one sample each, persistent) pull WORK ITEMS
-//     (chain c, slot k) from a ring queue in global memory;
-//   * the lane that picks an item up builds the proposal itself: x' = x_c + SigmaL z(seed, chain, iteration) with the
+//   * every chain keeps W proposals IN FLIGHT (queued or being integrated), taken from a look-ahead ring of R >= W
+//     undecided iterations.  The solver lanes (the tensor-memory layout of K1: 128 lanes per SM, one sample each,
+//     persistent) pull work items (chain, iteration) from a ring queue in global memory;
+//   * the lane that picks an item up builds the proposal itself: x' = x_c + SigmaL z(seed, stream, iteration) with the
 //     addressable Philox draws, exp, log-prior, parameter packing — then integrates it like any other sample and
 //     accumulates the patient's residuals in a register;
-//   * the lane that finishes the LAST outstanding slot of a chain's round runs that chain's accept scan, writes the
-//     thinned output rows, and immediately enqueues the chain's next round.  Nobody waits for the slowest chain; a lane
-//     is idle only when the queue is empty.
+//   * a lane that finishes an item records the proposal's log-target and ADVANCES its chain: while the oldest
+//     undecided iteration has its result, apply the Metropolis rule to it (in iteration order, so the chain is the
+//     sequential one); then top the number of proposals in flight up to W again from the far end of the ring.  Issue is
+//     decoupled from retirement: a slow solve at the head of the ring delays the decisions behind it, not the work —
+//     results that arrive out of order wait in their ring slots and cost nothing.  An acceptance moves the chain and
+//     bumps its generation, which cancels every younger item of the old generation: not-yet-started ones are dropped
+//     at pick-up, running ones give up at their next step; W proposals from the new state are issued at once.
+//     Advancing is serialised per chain by a combining counter (the lane that finds it busy leaves its result for the
+//     current advancer), never by a lock that spins.
 //
-// Round 1 ran propose / solve / accept as separate launches per round with a device->host copy and a host
-// synchronisation after each (gync_abi_more.inl), every round ending with the slowest of its C*K solves.
+// No lane ever waits for another chain, for the slowest solve of a batch, or for the host; a lane is idle only when
+// the queue is empty.  Round 1 ran propose / solve / accept as separate launches per round with a device->host copy
+// and a host synchronisation after each (still in gync_abi_more.inl, GYNC_MCMC_ROUNDS=1, and used by the adaptive
+// sampler), every round ending with the slowest of its C*K solves.
 #pragma once
 #include "gync_mcmc.cuh"
 
 struct GyncMcmcCtl {                 // one per launch, zero-initialised
   unsigned long long head;           // consumer tickets handed out
   unsigned long long tail;           // queue entries reserved by producers
-  int chains_done;                   // chains that have completed all their iterations
-  int pad;
-  unsigned long long solves;         // likelihood solves started (bookkeeping: speculative efficiency)
-  unsigned long long steps;          // Rosenbrock step attempts of those solves
+  unsigned long long decided;        // iterations decided so far, all chains
+  int chains_done;                   // chains that have decided all their iterations
+  int abort;                         // watchdog: a lane saw no progress for too long (never expected)
+  unsigned long long solves;         // likelihood solves started (bookkeeping: cost of the speculation)
+  unsigned long long steps;          // Rosenbrock step attempts spent, cancelled solves included
+  unsigned long long cancelled;      // solves given up or dropped because their chain had moved on
+  unsigned long long failed;         // completed solves with a non-zero status (their proposal scores -Inf)
+  unsigned long long hist[24];       // completed solves by floor(log2(step attempts))
+  // -DGYNC_MCMC_PROFILE builds only: where the lanes' time goes (summed over lanes)
+  unsigned long long trips_active, trips_idle, cyc_fetch, cyc_complete, cyc_step, sleeps;
 };
+#ifdef GYNC_MCMC_PROFILE
+#  define GYNC_MP(...) __VA_ARGS__
+#else
+#  define GYNC_MP(...)
+#endif
+
+#define GYNC_MCMC_GEN_MASK 0xFFFFFFull          /* generation counter, 24 bits inside a slot tag */
 
 struct GyncMcmcP {
   // chains (state is C x 116 log space, column-major like everywhere else)
   double* state;
   double* logf;
-  long long* itc;                    // next iteration of each chain
+  long long* itc;                    // head: next iteration to decide = iterations decided so far
+  long long* tailc;                  // next iteration to enqueue (head <= tail <= head + R)
+  int* gen;                          // bumped by every acceptance
+  int* pending;                      // combining counter of the advance
+  int* issued;                       // items enqueued under the current generation (written by the advancer only)
+  int* ncomp;                        // C x 2, by generation parity: items of that generation that have reported back
+                                     // (result or cancellation); issued - ncomp = proposals in flight
   long long* naccept;
-  int* round_left;                   // outstanding slots of the chain's current round
-  int* round_k;                      // slots of the current round
-  double* lfp;                       // C x K: log-target of the proposals of the current round
-  unsigned long long* queue;         // ring of (generation + 1) << 40 | item,  item = c * K + k
-  unsigned long long qmask;          // capacity - 1 (power of two, > 2 C K)
+  // ring slots: 2 R per chain, slot = (generation & 1) * R + iteration mod R.  The items an acceptance cancels cover
+  // the same iterations as the items issued after it; the generation parity keeps a cancelled item that is just
+  // finishing from writing into its successor's slot.
+  double* lfp;                       // C x 2R: log-target of the proposal
+  unsigned long long* slot_tag;      // C x 2R: identity (generation << 40 | iteration + 1) of the item that owns the slot
+  unsigned long long* done_tag;      // C x 2R: same identity once the slot's result is valid
+  unsigned long long* queue;         // ring of (ticket generation + 1) << 40 | item,  item = c * 2R + slot
+  unsigned long long qmask;          // capacity - 1 (power of two, > 4 C W: at most two generations of a chain are queued)
   int qshift;                        // log2(capacity)
   GyncMcmcCtl* ctl;
   int64_t C;
-  int K;
+  int W;                             // proposals in flight per chain when all chains have equally far to go
+  int Wmax;                          // ... and at most
+  long long inflight_target;         // proposals in flight over all chains (a little more than there are lanes)
+  unsigned long long total_iters;    // C * iters minus what was already decided at launch
+  int R;                             // look-ahead ring (undecided iterations per chain), >= 2 Wmax
   int64_t iters;
   int thin;
   const double* chol;                // 116 x 116 lower factor, column-major; NULL: isotropic prop_sd
@@ -61,11 +96,17 @@ struct GyncMcmcP {
   const int* allnan;                 // M
   double* samples_out;               // n_out x 116 x C or NULL
   int64_t n_out;
+  long long idle_limit;              // watchdog: clock64 ticks a lane may see the queue's tail unchanged before it raises ctl->abort
   GyncSolverOpts o;
 };
 
 __device__ __forceinline__ unsigned long long gync_ld_vol_u64(const unsigned long long* p) { return *(const volatile unsigned long long*)p; }
-
+__device__ __forceinline__ unsigned long long gync_mcmc_tag(int gen, long long it) {
+  return (((unsigned long long)gen & GYNC_MCMC_GEN_MASK) << 40) | (unsigned long long)(it + 1);
+}
+__device__ __forceinline__ int64_t gync_mcmc_slot(const GyncMcmcP& P, int64_t c, int gen, long long it) {
+  return c * (2 * (int64_t)P.R) + (int64_t)(gen & 1) * P.R + (int64_t)(it % P.R);
+}
 __device__ __forceinline__ uint64_t gync_mcmc_chain_id(const GyncMcmcP& P, int64_t c) {
   return P.chain_ids ? (uint64_t)P.chain_ids[c] : (uint64_t)(P.chain_id_base + (unsigned long long)c);
 }
@@ -90,75 +131,132 @@ __device__ __noinline__ void gync_mcmc_proposal(const GyncMcmcP& P, int64_t c, l
   }
 }
 
-// enqueue the next round of chain c (iterations it .. it+kk-1); caller has published the chain state
-__device__ __forceinline__ void gync_mcmc_push_round(const GyncMcmcP& P, int64_t c, long long it) {
-  const int kk = (int)min((long long)P.K, (long long)P.iters - it);
-  P.round_k[c] = kk;
-  P.round_left[c] = kk;
+// enqueue iterations [t0, t1) of chain c under generation g (the chain's state and generation are already published)
+__device__ __forceinline__ void gync_mcmc_enqueue(const GyncMcmcP& P, int64_t c, int g, long long t0, long long t1) {
+  if (t1 <= t0) return;
+  for (long long it = t0; it < t1; ++it) __stcg(P.slot_tag + gync_mcmc_slot(P, c, g, it), gync_mcmc_tag(g, it));
   __threadfence();
-  const unsigned long long t0 = atomicAdd(&P.ctl->tail, (unsigned long long)kk);
-  for (int j = 0; j < kk; ++j) {
-    const unsigned long long t = t0 + j;
-    *(volatile unsigned long long*)(P.queue + (t & P.qmask)) = (((t >> P.qshift) + 1ull) << 40) | (unsigned long long)(c * P.K + j);
+  const unsigned long long q0 = atomicAdd(&P.ctl->tail, (unsigned long long)(t1 - t0));
+  for (long long it = t0; it < t1; ++it) {
+    const unsigned long long t = q0 + (unsigned long long)(it - t0);
+    *(volatile unsigned long long*)(P.queue + (t & P.qmask)) =
+        (((t >> P.qshift) + 1ull) << 40) | (unsigned long long)gync_mcmc_slot(P, c, g, it);
   }
 }
 
-// accept scan of chain c's finished round (the sequential Metropolis rule over the slots, in iteration order)
-__device__ __noinline__ void gync_mcmc_scan(const GyncMcmcP& P, int64_t c) {
+// Decide as many iterations of chain c as have their result (the sequential Metropolis rule, in iteration order), then
+// top the proposals in flight up to W.  Called by exactly one lane at a time per chain (gync_mcmc_try_advance).
+__device__ __noinline__ void gync_mcmc_advance(const GyncMcmcP& P, int64_t c) {
   // chain words were last written by another lane, possibly on another SM: read them from L2, never from this SM's L1
-  long long it = __ldcg(P.itc + c);
+  long long h = __ldcg(P.itc + c);
+  if (h >= P.iters) return;
+  long long t = __ldcg(P.tailc + c);
+  int g = __ldcg(P.gen + c);
+  int issued = __ldcg(P.issued + c);
   double lf = __ldcg(P.logf + c);
   long long nacc = __ldcg(P.naccept + c);
-  const int kk = __ldcg(P.round_k + c);
   const uint64_t cid = gync_mcmc_chain_id(P, c);
-  for (int k = 0; k < kk; ++k, ++it) {
-    const double lfp = __ldcg(P.lfp + c * P.K + k);
+  const long long h0 = h;
+  while (h < P.iters) {
+    const int64_t slot = gync_mcmc_slot(P, c, g, h);
+    if (h >= t || __ldcg(P.done_tag + slot) != gync_mcmc_tag(g, h)) break;
+    const double lfp = __ldcg(P.lfp + slot);
     double u, u1;
-    if (P.inj_u) u = P.inj_u[it + P.iters * c];
-    else gync_draw_u2(P.seed, cid, P.iter_offset + (uint64_t)it, (uint32_t)(GYNC_NX / 2), u, u1);
+    if (P.inj_u) u = P.inj_u[h + P.iters * c];
+    else gync_draw_u2(P.seed, cid, P.iter_offset + (uint64_t)h, (uint32_t)(GYNC_NX / 2), u, u1);
     const bool acc = u < exp(lfp - lf);              // Mamba: rand() < exp(logf(x') - logf(x))
     if (acc) {
+      g = (int)(((unsigned)g + 1u) & (unsigned)GYNC_MCMC_GEN_MASK);
+      __stcg(P.ncomp + 2 * c + (g & 1), 0);          // the new generation's report counter (its last users are long gone)
+      __threadfence();
+      __stcg(P.gen + c, g);                          // cancels every younger item of the old generation
+      __threadfence();
       double prop[GYNC_NX];
-      gync_mcmc_proposal(P, c, it, prop);            // the same draws the slot was built from
-      for (int d = 0; d < GYNC_NX; ++d) P.state[c + P.C * d] = prop[d];
+      gync_mcmc_proposal(P, c, h, prop);             // the same draws the item was built from
+      for (int d = 0; d < GYNC_NX; ++d) __stcg(P.state + c + P.C * d, prop[d]);
       lf = lfp;
       ++nacc;
+      issued = 0;
     }
-    if ((it + 1) % P.thin == 0) {
-      const int64_t row = (it + 1) / P.thin - 1;
+    if ((h + 1) % P.thin == 0) {
+      const int64_t row = (h + 1) / P.thin - 1;
       if (P.samples_out && row < P.n_out)
         for (int d = 0; d < GYNC_NX; ++d)
           P.samples_out[row + P.n_out * (d + (int64_t)GYNC_NX * c)] = exp(__ldcg(P.state + c + P.C * d));   // sampling.jl:74
     }
-    if (acc) { ++it; break; }                        // later slots were proposed from the old state
+    ++h;
+    if (acc) { t = h; break; }                       // nothing of the new generation exists yet
   }
-  P.itc[c] = it;
-  P.logf[c] = lf;
-  P.naccept[c] = nacc;
-  if (it >= P.iters) {
+  if (h != h0) {
+    __stcg(P.logf + c, lf);
+    __stcg(P.naccept + c, nacc);
+    __stcg(P.itc + c, h);
+    atomicAdd(&P.ctl->decided, (unsigned long long)(h - h0));
+  }
+  if (h >= P.iters) {
+    if (h != h0) { __threadfence(); atomicAdd(&P.ctl->chains_done, 1); }
+    return;
+  }
+  // issue: keep this chain's share of proposals in flight, no further ahead of the oldest undecided iteration than the
+  // ring allows.  The share is proportional to the chain's REMAINING iterations: chains differ in cost per iteration by
+  // tens of percent, a fixed share would let the cheap ones finish early and leave their lanes idle while each slow chain
+  // could use no more than its own share; this way a chain that falls behind gets more lanes and all finish together.
+  const unsigned long long dec = gync_ld_vol_u64(&P.ctl->decided);
+  const double rem_all = (double)(P.total_iters > dec ? P.total_iters - dec : 1ull);
+  const long long share = (long long)ceil((double)P.inflight_target * (double)(P.iters - h) / rem_all);
+  const long long want = min((long long)P.Wmax, max(1ll, share));
+  const int inflight = issued - __ldcg(P.ncomp + 2 * c + (g & 1));
+  const long long room = min(h + (long long)P.R, (long long)P.iters) - t;
+  const long long n_new = min(want - (long long)inflight, room);
+  if (n_new > 0) {
+    __stcg(P.tailc + c, t + n_new);
+    __stcg(P.issued + c, issued + (int)n_new);
     __threadfence();
-    atomicAdd(&P.ctl->chains_done, 1);
-  } else {
-    gync_mcmc_push_round(P, c, it);
+    gync_mcmc_enqueue(P, c, g, t, t + n_new);
+  } else if (h != h0) {
+    __stcg(P.tailc + c, t);
+    __stcg(P.issued + c, issued);
   }
 }
 
-// a slot's log-target is known: record it; the last finisher of the round scans and re-proposes
-__device__ __forceinline__ void gync_mcmc_complete(const GyncMcmcP& P, int64_t c, int k, double lfp) {
-  __stcg(P.lfp + c * P.K + k, lfp);
+// a lane has news for chain c: become the advancer, or leave the news to the lane that already is
+__device__ __forceinline__ void gync_mcmc_try_advance(const GyncMcmcP& P, int64_t c) {
+  if (atomicAdd(P.pending + c, 1) != 0) return;
+  for (;;) {
+    const int seen = *(volatile int*)(P.pending + c);
+    __threadfence();
+    gync_mcmc_advance(P, c);
+    __threadfence();
+    if (atomicSub(P.pending + c, seen) == seen) break;
+  }
+}
+
+// an item's log-target is known
+__device__ __forceinline__ void gync_mcmc_complete(const GyncMcmcP& P, int64_t item, unsigned long long tag, double lfp) {
+  const int64_t c = item / (2 * (int64_t)P.R);
+  __stcg(P.lfp + item, lfp);
   __threadfence();
-  if (atomicSub(P.round_left + c, 1) == 1) {
-    __threadfence();
-    gync_mcmc_scan(P, c);
-  }
+  __stcg(P.done_tag + item, tag);
+  __threadfence();
+  atomicAdd(P.ncomp + 2 * c + (int)((tag >> 40) & 1ull), 1);
+  gync_mcmc_try_advance(P, c);
+}
+// an item was dropped or given up: it only reports that it is no longer in flight
+__device__ __forceinline__ void gync_mcmc_cancelled(const GyncMcmcP& P, int64_t c, int gen) {
+  atomicAdd(P.ncomp + 2 * c + (gen & 1), 1);
+  atomicAdd(&P.ctl->cancelled, 1ull);
 }
 
-// first round of every chain (after the initial log-targets are known)
+// first window of every chain (after the initial log-targets are known)
 __global__ void gync_mcmc_persist_init_kernel(GyncMcmcP P) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= P.C) return;
-  if (P.itc[c] >= P.iters) atomicAdd(&P.ctl->chains_done, 1);
-  else gync_mcmc_push_round(P, c, P.itc[c]);
+  const long long h = P.itc[c];
+  if (h >= P.iters) { atomicAdd(&P.ctl->chains_done, 1); return; }
+  const long long t1 = min(h + (long long)P.W, (long long)P.iters);
+  P.tailc[c] = t1;
+  P.issued[c] = (int)(t1 - h);
+  gync_mcmc_enqueue(P, c, P.gen[c], h, t1);
 }
 
 struct GyncLlhSinkReg {              // one patient per sample, residuals accumulated in a register
@@ -206,66 +304,97 @@ gync_mcmc_persist_kernel(const GyncMcmcP P) {
   const GyncSolverOpts o = P.o;
   const double big = 1.0e300;
   bool active = false, done = false;
-  long long ticket = -1;
-  int64_t c = 0;
-  int kslot = 0;
+  long long ticket = -1, idle_since = 0;
+  unsigned long long idle_tail = ~0ull;
+  int64_t c = 0, item = 0;
+  unsigned long long tag = 0;
+  int mygen = 0;
   double T = 0.0, t = 0.0, tn = 0.0, lpr = 0.0;
   int i0 = 0, i1 = 0, budget = 0, st = GYNC_ST_OK, mpat = 0;
   GyncCtrl ctl;
   gync_ctrl_init(ctl, 1e-3);
   GyncLlhSinkReg sink = {P.data, P.iscale, 0.0};
+  GYNC_MP(unsigned long long p_act = 0, p_idle = 0, p_fetch = 0, p_comp = 0, p_step = 0, p_sleep = 0;)
   for (;;) {
+    GYNC_MP(const long long p_t0 = clock64();)
     if (!active && !done) {
       if (ticket < 0) ticket = (long long)atomicAdd(&P.ctl->head, 1ull);
       const unsigned long long ent = gync_ld_vol_u64(P.queue + ((unsigned long long)ticket & P.qmask));
       if ((ent >> 40) == (((unsigned long long)ticket >> P.qshift) + 1ull)) {
         __threadfence();
-        const int64_t item = (int64_t)(ent & ((1ull << 40) - 1ull));
+        item = (int64_t)(ent & ((1ull << 40) - 1ull));
         ticket = -1;
-        c = item / P.K;
-        kslot = (int)(item % P.K);
-        const long long it = __ldcg((const long long*)P.itc + c) + kslot;
+        idle_tail = ~0ull;
+        c = item / (2 * (int64_t)P.R);
+        tag = __ldcg(P.slot_tag + item);
+        mygen = (int)((tag >> 40) & GYNC_MCMC_GEN_MASK);
+        const long long it = (long long)(tag & ((1ull << 40) - 1ull)) - 1;
+        bool live = (__ldcg(P.gen + c) == mygen);
         double x[GYNC_NX];
-        gync_mcmc_proposal(P, c, it, x);
-        double sumx = 0.0;
-        for (int d = 0; d < GYNC_NX; ++d) { sumx += x[d]; x[d] = exp(x[d]); }
-        const double lp = gync_logprior(x, P.pr);          // logf(x) = logpost(c, exp(x)) + sum(x)   (model.jl:102)
-        mpat = P.patient_of_chain ? P.patient_of_chain[c] : 0;
-        if (!(lp > -INFINITY) || P.allnan[mpat]) {
-          // outside the prior the likelihood is skipped (model.jl:121); an all-missing table scores -Inf (model.jl:161)
-          gync_mcmc_complete(P, c, kslot, -INFINITY);
+        if (live) {
+          gync_mcmc_proposal(P, c, it, x);
+          __threadfence();
+          live = (*(volatile int*)(P.gen + c) == mygen);      // the state was not replaced while it was being read
+        }
+        if (!live) {
+          gync_mcmc_cancelled(P, c, mygen);                   // its chain has moved on: nothing to solve
         } else {
-          lpr = lp + sumx;
-          gync_load_sample(W, [&](int k) { return x[k]; }, c_refallparms, c_sampledinds, &T);
-          sink.data = P.data + (size_t)GYNC_NDAYS * GYNC_NMEAS * mpat;
-          sink.iscale = P.iscale + GYNC_NMEAS * mpat;
-          sink.acc = 0.0;
-          i0 = i1 = 0;
-          budget = o.max_steps;
-          t = fmin(1.0, 1.0 + T);
-          tn = t;
-          st = (gync_all_finite(W.y, GYNC_NY) && gync_all_finite(W.q, GYNC_NQ) && (T * 0.0 == 0.0)) ? GYNC_ST_OK
-                                                                                                   : GYNC_ST_NONFINITE;
-          gync_ctrl_init(ctl, (st == GYNC_ST_OK) ? ((o.h0 > 0.0) ? o.h0 : gync_initial_step(W, o.rtol, o.atol)) : 1.0);
-          active = true;
-          atomicAdd(&P.ctl->solves, 1ull);
-          if (st == GYNC_ST_OK) {
-            for (;;) {
-              const double tA = (i0 < GYNC_NDAYS) ? (double)(i0 + 1) : big;
-              const double tB = (i1 < GYNC_NDAYS) ? (double)(i1 + 1) + T : big;
-              tn = fmin(tA, tB);
-              if (tn > t) break;
-              if (tA == tn) { sink(0, i0, W.y); ++i0; }
-              if (tB == tn) { sink(1, i1, W.y); ++i1; }
+          double sumx = 0.0;
+          for (int d = 0; d < GYNC_NX; ++d) { sumx += x[d]; x[d] = exp(x[d]); }
+          const double lp = gync_logprior(x, P.pr);          // logf(x) = logpost(c, exp(x)) + sum(x)   (model.jl:102)
+          mpat = P.patient_of_chain ? P.patient_of_chain[c] : 0;
+          if (!(lp > -INFINITY) || P.allnan[mpat]) {
+            // outside the prior the likelihood is skipped (model.jl:121); an all-missing table scores -Inf (model.jl:161)
+            gync_mcmc_complete(P, item, tag, -INFINITY);
+          } else {
+            lpr = lp + sumx;
+            gync_load_sample(W, [&](int k) { return x[k]; }, c_refallparms, c_sampledinds, &T);
+            sink.data = P.data + (size_t)GYNC_NDAYS * GYNC_NMEAS * mpat;
+            sink.iscale = P.iscale + GYNC_NMEAS * mpat;
+            sink.acc = 0.0;
+            i0 = i1 = 0;
+            budget = o.max_steps;
+            t = fmin(1.0, 1.0 + T);
+            tn = t;
+            st = (gync_all_finite(W.y, GYNC_NY) && gync_all_finite(W.q, GYNC_NQ) && (T * 0.0 == 0.0)) ? GYNC_ST_OK
+                                                                                                     : GYNC_ST_NONFINITE;
+            gync_ctrl_init(ctl, (st == GYNC_ST_OK) ? ((o.h0 > 0.0) ? o.h0 : gync_initial_step(W, o.rtol, o.atol)) : 1.0);
+            active = true;
+            atomicAdd(&P.ctl->solves, 1ull);
+            if (st == GYNC_ST_OK) {
+              for (;;) {
+                const double tA = (i0 < GYNC_NDAYS) ? (double)(i0 + 1) : big;
+                const double tB = (i1 < GYNC_NDAYS) ? (double)(i1 + 1) + T : big;
+                tn = fmin(tA, tB);
+                if (tn > t) break;
+                if (tA == tn) { sink(0, i0, W.y); ++i0; }
+                if (tB == tn) { sink(1, i1, W.y); ++i1; }
+              }
             }
           }
         }
-      } else if (*(volatile int*)&P.ctl->chains_done >= (int)P.C) {
-        done = true;
+      } else {
+        if (*(volatile int*)&P.ctl->chains_done >= (int)P.C || *(volatile int*)&P.ctl->abort) {
+          done = true;
+        } else {
+          // watchdog (never expected to fire): nothing was enqueued anywhere for idle_limit ticks while work is outstanding
+          const unsigned long long qt = gync_ld_vol_u64(&P.ctl->tail);
+          const long long now = clock64();
+          if (qt != idle_tail) { idle_tail = qt; idle_since = now; }
+          else if (now - idle_since > P.idle_limit) { atomicExch(&P.ctl->abort, 1); done = true; }
+        }
       }
     }
+    GYNC_MP(p_fetch += (unsigned long long)(clock64() - p_t0);)
     __syncwarp();
     if (__all_sync(0xffffffffu, done)) break;
+    if (!__any_sync(0xffffffffu, active)) {               // nobody in this warp has a sample: do not burn a step on it
+      __nanosleep(2000);
+      GYNC_MP(++p_sleep;)
+      continue;
+    }
+    GYNC_MP(if (active) ++p_act; else ++p_idle;)
+    GYNC_MP(const long long p_t1 = clock64();)
     // ---- one step attempt, executed by ALL lanes of the warp (TMEM ops are warp-collective)
     const bool stepping = active && st == GYNC_ST_OK && tn > t;
     double h = ctl.h;
@@ -275,8 +404,12 @@ gync_mcmc_persist_kernel(const GyncMcmcP P) {
     if (last) h = rem;
     if (!stepping || !(h > 0.0)) h = 1.0;                  // idle lanes: any finite positive step
     const double hprop = ctl.h;
+    // has this item's chain moved on?  (asked before the step, read after it: the L2 round trip hides behind the step)
+    const int gen_now = active ? __ldcg(P.gen + c) : mygen;
     const double err = gync_ros_step_tm(W, h, o.rtol, o.atol);
     __syncwarp();
+    GYNC_MP(p_step += (unsigned long long)(clock64() - p_t1);)
+    GYNC_MP(const long long p_t2 = clock64();)
     if (stepping) {
       if (budget-- <= 0) {
         st = GYNC_ST_MAXSTEPS;
@@ -294,7 +427,8 @@ gync_mcmc_persist_kernel(const GyncMcmcP P) {
     }
     if (active) {
       bool finished = (st != GYNC_ST_OK);
-      if (!finished && t >= tn) {
+      const bool cancelled = (gen_now != mygen) || *(volatile int*)&P.ctl->abort;
+      if (!finished && !cancelled && t >= tn) {
         for (;;) {
           const double tA = (i0 < GYNC_NDAYS) ? (double)(i0 + 1) : big;
           const double tB = (i1 < GYNC_NDAYS) ? (double)(i1 + 1) + T : big;
@@ -305,16 +439,24 @@ gync_mcmc_persist_kernel(const GyncMcmcP P) {
         }
         if (i0 >= GYNC_NDAYS && i1 >= GYNC_NDAYS) finished = true;
       }
-      if (finished) {
+      if (finished || cancelled) {
         atomicAdd(&P.ctl->steps, (unsigned long long)(ctl.nacc + ctl.nrej));
+        if (!cancelled) {
+          atomicAdd(&P.ctl->hist[min(23, 31 - __clz(max(1, ctl.nacc + ctl.nrej)))], 1ull);
+          if (st != GYNC_ST_OK) atomicAdd(&P.ctl->failed, 1ull);
+        }
+        if (cancelled || __ldcg(P.gen + c) != mygen) gync_mcmc_cancelled(P, c, mygen);
         // failed solve -> NaN trajectory -> -Inf (gyncycle.jl:18-19, model.jl:138-141)
-        gync_mcmc_complete(P, c, kslot, (st == GYNC_ST_OK) ? __dadd_rn(lpr, __dmul_rn(-0.5, sink.acc)) : -INFINITY);
+        else gync_mcmc_complete(P, item, tag, (st == GYNC_ST_OK) ? __dadd_rn(lpr, __dmul_rn(-0.5, sink.acc)) : -INFINITY);
         active = false;
 #pragma unroll
         for (int i = 0; i < GYNC_NY; ++i) if (!(W.y[i] * 0.0 == 0.0)) W.y[i] = 1.0;
       }
     }
+    GYNC_MP(__syncwarp(); p_comp += (unsigned long long)(clock64() - p_t2);)
   }
+  GYNC_MP(atomicAdd(&P.ctl->trips_active, p_act); atomicAdd(&P.ctl->trips_idle, p_idle); atomicAdd(&P.ctl->cyc_fetch, p_fetch);
+          atomicAdd(&P.ctl->cyc_complete, p_comp); atomicAdd(&P.ctl->cyc_step, p_step); atomicAdd(&P.ctl->sleeps, p_sleep);)
   __syncthreads();
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem_base) : "memory");

@@ -135,8 +135,12 @@ int gync_mcmc_run_ids(double* state, double* logf, int64_t C, const double* chol
                       const double* inj_z, const double* inj_u,
                       double* samples_out, int64_t* naccept);
 /* Likelihood solves started and Rosenbrock step attempts of the last gync_mcmc_run* call (all devices), and the number of
- * speculative slots per chain round it used: iterations / solves is the efficiency of the speculation. */
+ * undecided iterations each chain keeps in flight (its window): iterations / solves is the efficiency of the speculation. */
 void gync_mcmc_last_stats(uint64_t* solves, uint64_t* steps, int32_t* slots_per_round);
+/* solves dropped or given up because their chain had accepted an earlier proposal */
+uint64_t gync_mcmc_last_cancelled(void);
+/* completed solves of the last run by floor(log2(step attempts)) (24 bins), and how many of them failed */
+void gync_mcmc_last_histogram(uint64_t* hist24, uint64_t* failed);
 
 /* ---- the same with Mamba's adaptation switched on (Config.adapt = true; model.jl:104-106, sampling.jl:72) ----------
  * AMMTune state per chain, in/out so that a Sampling can be continued (sampling.jl:62-68) and propadapt() read
