@@ -571,6 +571,7 @@ struct gync_em_comm {
   size_t flag_off = 0;
 };
 
+void gync_em_comm_destroy(gync_em_comm* c);
 int gync_em_comm_create(int32_t world, int32_t rank, void* handle_out /* 64 bytes */, gync_em_comm** out) {
   if (world < 1 || world > 8 || rank < 0 || rank >= world || !handle_out || !out)
     return fail(GYNC_ERR_ARG, "gync_em_comm_create: bad arguments (world <= 8)");
@@ -580,19 +581,29 @@ int gync_em_comm_create(int32_t world, int32_t rank, void* handle_out /* 64 byte
   const size_t mail_bytes = sizeof(double) * 2 * world * c->MT;
   c->flag_off = (mail_bytes + 255) / 256 * 256;
   const size_t total = c->flag_off + sizeof(unsigned long long) * 2 * world;
-  void* base = nullptr;
-  CK(cudaMalloc(&base, total));
-  CK(cudaMemset(base, 0, total));
-  c->mail = (double*)base;
-  c->flag = (unsigned long long*)((char*)base + c->flag_off);
-  if (int rc = c->st.alloc()) return rc;
-  cudaIpcMemHandle_t h;
-  CK(cudaIpcGetMemHandle(&h, base));
-  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t size");
-  memcpy(handle_out, &h, 64);
-  c->peer.world = world; c->peer.rank = rank;
-  c->peer.mail[rank] = c->mail; c->peer.flag[rank] = c->flag;
-  CK(cudaDeviceSynchronize());
+  // every failure path below releases what was allocated so far (gync_em_comm_destroy copes with a half-built object)
+  auto body = [&]() -> int {
+    void* base = nullptr;
+    CK(cudaMalloc(&base, total));
+    c->mail = (double*)base;
+    c->flag = (unsigned long long*)((char*)base + c->flag_off);
+    CK(cudaMemset(base, 0, total));
+    if (int rc = c->st.alloc()) return rc;
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, base));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t size");
+    memcpy(handle_out, &h, 64);
+    c->peer.world = world; c->peer.rank = rank;
+    c->peer.mail[rank] = c->mail; c->peer.flag[rank] = c->flag;
+    CK(cudaDeviceSynchronize());
+    return GYNC_OK;
+  };
+  if (int rc = body()) {
+    const std::string why = g_err;
+    gync_em_comm_destroy(c);
+    g_err = why;
+    return rc;
+  }
   *out = c;
   return GYNC_OK;
 }
@@ -667,9 +678,27 @@ int gync_em_iterate_multi(double* w, const double* L, int64_t K, int32_t M, int3
         parts[i].comm->peer.mail[j] = parts[j].comm->mail;
         parts[i].comm->peer.flag[j] = parts[j].comm->flag;
       }
+    int launched = 0;
     for (int i = 0; i < nd && !rc; ++i) {          // all launches are asynchronous: the kernels meet on the GPUs
       if ((rc = use_device(i))) break;
       rc = gync_em_iterate_fused_dev(parts[i].comm, parts[i].dw.as<double>(), parts[i].dL.as<double>(), parts[i].n, M, niter, g_stream);
+      if (!rc) launched = i + 1;
+    }
+    if (rc && launched > 0) {
+      // a later device failed to launch: tell the kernels already running (they are waiting for its mailbox) to stop
+      // now instead of running into their spin time-out — their error word is polled inside every spin
+      const std::string why = g_err;
+      for (int i = 0; i < launched; ++i) {
+        if (use_device(i)) continue;
+        cudaStream_t side = nullptr;
+        if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) == cudaSuccess) {
+          const int one = 1;
+          cudaMemcpyAsync(parts[i].comm->st.err, &one, sizeof(int), cudaMemcpyHostToDevice, side);
+          cudaStreamSynchronize(side);
+          cudaStreamDestroy(side);
+        }
+      }
+      g_err = why;
     }
     for (int i = 0; i < nd && !rc; ++i) {
       if ((rc = use_device(i))) break;

@@ -303,6 +303,10 @@ struct EmLaunchState {          // synchronisation words + scratch of one (devic
   int* err = nullptr;
   unsigned long long seq = 1, arrive0 = 0;
   int device = -1;
+  // The arrival counter, the partials and the published denominators are ONE set per (device, communicator): two launches
+  // that overlap on different streams would share them.  Every launch therefore waits for the previous one's event and
+  // records its own — launches through this state are serialised on the device whatever stream they were given.
+  cudaEvent_t busy = nullptr;
   int alloc() {
     CK(cudaMalloc((void**)&sync_words, 2 * sizeof(unsigned long long)));
     CK(cudaMemset(sync_words, 0, 2 * sizeof(unsigned long long)));
@@ -310,12 +314,24 @@ struct EmLaunchState {          // synchronisation words + scratch of one (devic
     CK(cudaMalloc((void**)&gnorm, sizeof(double) * 2 * 64));
     CK(cudaMalloc((void**)&err, sizeof(int)));
     CK(cudaMemset(err, 0, sizeof(int)));
+    CK(cudaEventCreateWithFlags(&busy, cudaEventDisableTiming));
     CK(cudaGetDevice(&device));
+    return GYNC_OK;
+  }
+  // blocking callers: did a spin time out inside the last launches?  (the kernel then stops updating and raises this)
+  int check_error(cudaStream_t s, const char* who) {
+    int e = 0;
+    CK(cudaMemcpyAsync(&e, err, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(wait_stream(s));
+    if (e) {
+      cudaMemsetAsync(err, 0, sizeof(int), s);
+      return fail(GYNC_ERR_CUDA, std::string(who) + ": a synchronisation spin inside the EM kernel timed out");
+    }
     return GYNC_OK;
   }
   void release() {
     if (device >= 0) { int cur; cudaGetDevice(&cur); cudaSetDevice(device);
-      cudaFree(sync_words); cudaFree(partials); cudaFree(gnorm); cudaFree(err); cudaSetDevice(cur); }
+      cudaFree(sync_words); cudaFree(partials); cudaFree(gnorm); cudaFree(err); if (busy) cudaEventDestroy(busy); cudaSetDevice(cur); }
     *this = EmLaunchState();
   }
 };
@@ -347,7 +363,9 @@ int em_launch_variant(EmLaunchState& st, const GyncEmPeer& peer, double* dw, con
   GyncEmPeer pr = peer;
   int Ri = (int)R;
   void* args[] = {&dw, &dL, &K, &M, &niter, &Ri, &st.partials, &st.gnorm, &sync, &pr, &st.err, &d_hist};
+  if (st.busy) CK(cudaStreamWaitEvent(s, st.busy, 0));
   CK(cudaLaunchCooperativeKernel((void*)gync_em_kernel<MH, FULL, RESIDENT>, dim3(nb), dim3(GYNC_EM_THREADS), args, smem, s));
+  if (st.busy) CK(cudaEventRecord(st.busy, s));
   st.seq += (unsigned long long)niter + 1ull;
   st.arrive0 += (unsigned long long)nb * ((unsigned long long)niter + 1ull);
   g_launches += 1;
@@ -382,6 +400,7 @@ struct EmScratch {   // scratch for the sharded step kernels (on the device that
   double* partials = nullptr;
   size_t doubles = 0;
   int device = -1;
+  cudaEvent_t busy = nullptr;   // one scratch per device: users on different streams are serialised through this event
 } g_em_scratch;
 
 int em_grid(int64_t K) {
@@ -394,10 +413,13 @@ int em_scratch(size_t doubles) {
   if (g_em_scratch.partials && g_em_scratch.doubles >= doubles && g_em_scratch.device == g_device) return GYNC_OK;
   if (g_em_scratch.partials) {
     cudaSetDevice(g_em_scratch.device);
-    cudaFree(g_em_scratch.partials);
+    cudaFree(g_em_scratch.partials);              // synchronises the device: no user of the old buffer is left
+    if (g_em_scratch.busy) cudaEventDestroy(g_em_scratch.busy);
     cudaSetDevice(g_device);
   }
   g_em_scratch.partials = nullptr;
+  g_em_scratch.busy = nullptr;
+  CK(cudaEventCreateWithFlags(&g_em_scratch.busy, cudaEventDisableTiming));
   CK(cudaMalloc((void**)&g_em_scratch.partials, sizeof(double) * doubles));
   g_em_scratch.doubles = doubles;
   g_em_scratch.device = g_device;
@@ -408,8 +430,10 @@ template <int MH, bool FULL>
 int em_norms_launch(const double* dw, const double* dL, int64_t K, int M, double* d_out, cudaStream_t s) {
   const int nb = em_grid(K);
   if (int rc = em_scratch((size_t)nb * 2 * MH)) return rc;
+  CK(cudaStreamWaitEvent(s, g_em_scratch.busy, 0));
   gync_em_norms_kernel<MH, FULL><<<nb, GYNC_EM_THREADS, 0, s>>>(dw, dL, K, M, g_em_scratch.partials);
   gync_em_finish_kernel<MH><<<1, GYNC_EM_THREADS, 0, s>>>(g_em_scratch.partials, nb, M, d_out);
+  CK(cudaEventRecord(g_em_scratch.busy, s));
   g_launches += 2;
   CK(cudaGetLastError());
   return GYNC_OK;
@@ -419,8 +443,10 @@ template <int MH, bool FULL>
 int em_step_launch(double* dw, const double* dL, int64_t K, int M, const double* d_in, double* d_out, cudaStream_t s) {
   const int nb = em_grid(K);
   if (int rc = em_scratch((size_t)nb * 2 * MH)) return rc;
+  CK(cudaStreamWaitEvent(s, g_em_scratch.busy, 0));
   gync_em_step_kernel<MH, FULL><<<nb, GYNC_EM_THREADS, 0, s>>>(dw, dL, K, M, d_in, g_em_scratch.partials);
   gync_em_finish_kernel<MH><<<1, GYNC_EM_THREADS, 0, s>>>(g_em_scratch.partials, nb, M, d_out);
+  CK(cudaEventRecord(g_em_scratch.busy, s));
   g_launches += 2;
   CK(cudaGetLastError());
   return GYNC_OK;
@@ -532,6 +558,7 @@ void gync_shutdown(void) {
   if (g_em_scratch.partials) {
     if (g_em_scratch.device >= 0) cudaSetDevice(g_em_scratch.device);
     cudaFree(g_em_scratch.partials);
+    if (g_em_scratch.busy) cudaEventDestroy(g_em_scratch.busy);
     g_em_scratch = EmScratch();
   }
   for (DevCtx& d : g_devs)
@@ -751,6 +778,12 @@ int gync_em_iterate(double* w, const double* L, int64_t K, int32_t M, int32_t ni
   CK(cudaMemcpyAsync(w, dw.p, sizeof(double) * K, cudaMemcpyDeviceToHost, g_stream));
   if (history) CK(cudaMemcpyAsync(history, dH.p, sizeof(double) * K * niter, cudaMemcpyDeviceToHost, g_stream));
   CK(wait_stream(g_stream));
+  {
+    int slot = 0;
+    for (size_t i = 0; i < g_devs.size(); ++i) if (g_devs[i].device == g_device) slot = (int)i;
+    if (g_em_local[slot].device == g_device)
+      if (int rc2 = g_em_local[slot].check_error(g_stream, "gync_em_iterate")) return rc2;
+  }
   return GYNC_OK;
 }
 

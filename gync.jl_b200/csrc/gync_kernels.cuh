@@ -925,6 +925,23 @@ struct GyncEmPeer {
 // publishes 1/denominators plus a sequence flag; all blocks poll that flag.  Compared with two
 // cooperative-groups grid barriers plus 148 redundant gathers this removes ~5 us per iteration.
 // RESIDENT: this GPU's rows of L are loaded into shared memory once (when they fit).
+// Bounded spin on a monotonically increasing word.  Gives up — and raises *err_flag for everybody — after ~2 s of SM
+// clock, or as soon as somebody else has raised the flag: a rank that failed to launch, a peer that died or a mismatched
+// iteration count must not leave the other blocks / ranks spinning for (iterations x timeout).
+#define GYNC_EM_SPIN_LIMIT (4000000000ll)
+__device__ __forceinline__ bool gync_em_spin(const volatile unsigned long long* word, unsigned long long want, int* err_flag) {
+  const long long t0 = clock64();
+  int polls = 0;
+  while (*word < want) {
+    if ((++polls & 255) == 0 && (*(volatile int*)err_flag || clock64() - t0 > GYNC_EM_SPIN_LIMIT)) {
+      *(volatile int*)err_flag = 1;
+      __threadfence_system();
+      return false;
+    }
+  }
+  return true;
+}
+
 struct GyncEmSync {
   unsigned long long* arrive;   // monotonically increasing arrival counter (device memory)
   unsigned long long* ready;    // sequence number of the denominators currently published in gnorm
@@ -1015,21 +1032,17 @@ gync_em_kernel(double* __restrict__ w, const double* __restrict__ L, int64_t K, 
       // everywhere) — two L2 round trips shorter than publish-and-poll through block 0
       if (threadIdx.x == 0) {
         const unsigned long long want = sync.arrive0 + (unsigned long long)nb * (unsigned long long)(it + 2);
-        volatile unsigned long long* a = sync.arrive;
-        long long spins = 0;
-        while (*a < want) { if (++spins > (1ll << 31)) { *err_flag = 1; break; } }
+        gync_em_spin(sync.arrive, want, err_flag);
         __threadfence();
       }
-      __syncthreads();
+      if (__syncthreads_or(threadIdx.x == 0 && *(volatile int*)err_flag != 0)) break;
       em_gather_partials<MH>(partials + (size_t)((it + 1) & 1) * nb * MT, nb, M, sm, sm.rinv, true);
       continue;
     }
     if (blockIdx.x == 0) {
       if (threadIdx.x == 0) {
         const unsigned long long want = sync.arrive0 + (unsigned long long)nb * (unsigned long long)(it + 2);
-        volatile unsigned long long* a = sync.arrive;
-        long long spins = 0;
-        while (*a < want) { if (++spins > (1ll << 31)) { *err_flag = 1; break; } }
+        gync_em_spin(sync.arrive, want, err_flag);
         __threadfence();
       }
       __syncthreads();
@@ -1044,9 +1057,7 @@ gync_em_kernel(double* __restrict__ w, const double* __restrict__ L, int64_t K, 
         if (threadIdx.x < peer.world) {
           volatile unsigned long long* f = peer.flag[threadIdx.x] + (size_t)slot * peer.world + peer.rank;
           *f = seq;
-          volatile unsigned long long* g = peer.flag[peer.rank] + (size_t)slot * peer.world + threadIdx.x;
-          long long spins = 0;
-          while (*g < seq) { if (++spins > (1ll << 31)) { *err_flag = 1; break; } }
+          gync_em_spin(peer.flag[peer.rank] + (size_t)slot * peer.world + threadIdx.x, seq, err_flag);
         }
         __threadfence_system();
         __syncthreads();
@@ -1065,12 +1076,12 @@ gync_em_kernel(double* __restrict__ w, const double* __restrict__ L, int64_t K, 
     }
     // ---- everybody: wait for the published denominators
     if (threadIdx.x == 0) {
-      volatile unsigned long long* rd = sync.ready;
-      long long spins = 0;
-      while (*rd < seq) { if (++spins > (1ll << 31)) { *err_flag = 1; break; } }
+      gync_em_spin(sync.ready, seq, err_flag);
       __threadfence();
     }
-    __syncthreads();
+    // a timed-out spin anywhere (this GPU or, through the flag its block 0 raises, a peer) ends the loop for every block
+    // of this launch instead of iterating on stale denominators
+    if (__syncthreads_or(threadIdx.x == 0 && *(volatile int*)err_flag != 0)) break;
     if (threadIdx.x < MT) sm.rinv[threadIdx.x] = __ldcg(gnorm + slot * MT + threadIdx.x);
     __syncthreads();
   }

@@ -18,6 +18,7 @@
 struct GyncSchedModel {              // device-resident
   double beta[GYNC_SCHED_NF];
   double ref[GYNC_SCHED_NF];         // feature offset: log|x| of the first training sample (conditioning)
+  double ref_new[GYNC_SCHED_NF];     // offset of the fit in progress: becomes `ref` only together with its `beta`
 };
 
 __device__ __forceinline__ double gync_sched_feature(double x) { return log(fmax(fabs(x), 1e-300)); }
@@ -117,9 +118,9 @@ gync_sched_features_kernel(const double* __restrict__ X, int64_t N, int S, int64
       const double r = gync_sched_feature(__ldg(X + N * (f - 1)));          // sample 0 is the offset
       const double rr = (r == r) ? r : 0.0;
       v = bad ? 0.0 : gync_sched_rel(__ldg(X + n + N * (f - 1)), rr);
-      if (s == 0) mdl->ref[f] = rr;
+      if (s == 0) mdl->ref_new[f] = rr;
     } else if (s == 0) {
-      mdl->ref[0] = 0.0;
+      mdl->ref_new[0] = 0.0;
     }
     Phi[(size_t)s * GYNC_SCHED_NF + f] = v;
   }
@@ -185,6 +186,6 @@ gync_sched_fit_kernel(const double* __restrict__ G, const double* __restrict__ b
     }
     bool fin = true;
     for (int i = 0; i < n; ++i) fin = fin && (x[i] == x[i]) && fabs(x[i]) < 1e300;
-    if (fin) for (int i = 0; i < n; ++i) mdl->beta[i] = x[i];
+    if (fin) for (int i = 0; i < n; ++i) { mdl->beta[i] = x[i]; mdl->ref[i] = mdl->ref_new[i]; }   // (beta, ref) change together or not at all
   }
 }
