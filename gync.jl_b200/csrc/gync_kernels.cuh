@@ -315,16 +315,9 @@ __device__ __forceinline__ double gync_rodas4_step_tm(GyncWorkTm& W, const doubl
     gync_lusolve(gync_ro(W.A), W.e);
     GYNC_TICK(2)
   }
-  double sum = 0.0;
-#pragma unroll
-  for (int i = 0; i < GYNC_NY; ++i) {
-    W.yn[i] += W.e[i];
-    const double sc = atol + rtol * fmax(fabs(W.y[i]), fabs(W.yn[i]));
-    const double r = W.e[i] * GYNC_RCP(sc);
-    sum = fma(r, r, sum);
-  }
+  const double err = gync_finish_step(W, rtol, atol);
   GYNC_TICK(6)
-  return sqrt(sum * (1.0 / GYNC_NY));
+  return err;
 }
 
 // Rodas5P step with the stage storage in TMEM: same arithmetic as gync_rodas5p_step (gync_solver.cuh explains why five
@@ -398,16 +391,9 @@ __device__ __forceinline__ double gync_rodas5p_step_tm(GyncWorkTm& W, const doub
     gync_lusolve(gync_ro(W.A), W.e);
     GYNC_TICK(2)
   }
-  double sum = 0.0;
-#pragma unroll
-  for (int i = 0; i < GYNC_NY; ++i) {
-    W.yn[i] += W.e[i];
-    const double sc = atol + rtol * fmax(fabs(W.y[i]), fabs(W.yn[i]));
-    const double r = W.e[i] * GYNC_RCP(sc);
-    sum = fma(r, r, sum);
-  }
+  const double err = gync_finish_step(W, rtol, atol);
   GYNC_TICK(6)
-  return sqrt(sum * (1.0 / GYNC_NY));
+  return err;
 }
 
 __device__ __forceinline__ double gync_ros_step_tm(GyncWorkTm& W, const double h, const double rtol, const double atol) {
@@ -518,8 +504,7 @@ gync_loglik_tm_kernel(const double* __restrict__ X, int64_t N, const double* __r
       } else if (!(h > 1e-14 * fmax(1.0, fabs(t)))) {
         st = GYNC_ST_HMIN;
       } else {
-        const bool fin = gync_all_finite(W.yn, GYNC_NY);
-        if (gync_ctrl_update(c, h, err, fin)) {
+        if (gync_ctrl_update(c, h, err, true)) {         // a non-finite candidate arrives as err = NaN
           t = last ? tn : t + h;
 #pragma unroll
           for (int i = 0; i < GYNC_NY; ++i) W.y[i] = W.yn[i];
@@ -734,8 +719,7 @@ gync_solve_tm_kernel(const double* __restrict__ X, const double* __restrict__ Y0
       } else if (!(h > 1e-14 * fmax(1.0, fabs(t)))) {
         st = GYNC_ST_HMIN;
       } else {
-        const bool fin = gync_all_finite(W.yn, GYNC_NY);
-        if (gync_ctrl_update(c, h, err, fin)) {
+        if (gync_ctrl_update(c, h, err, true)) {         // a non-finite candidate arrives as err = NaN
           t = last ? tn : t + h;
 #pragma unroll
           for (int i = 0; i < GYNC_NY; ++i) W.y[i] = W.yn[i];

@@ -19,7 +19,7 @@ GYNC_HD static int gync_run_meas_grid(WK& W, const double T, const GyncSolverOpt
     return GYNC_ST_NONFINITE;
   GyncCtrl c;
   c.h = (o.h0 > 0.0) ? o.h0 : gync_initial_step(W, o.rtol, o.atol);
-  c.hacc = c.h; c.erracc = 1.0; c.nacc = 0; c.nrej = 0; c.rej_last = 0;
+  c.hacc = c.h; c.rootacc = 1.0; c.nacc = 0; c.nrej = 0; c.rej_last = 0;
   int budget = o.max_steps;
   int i0 = 0, i1 = 0;
   const double big = 1.0e300;
@@ -47,7 +47,7 @@ GYNC_HD static int gync_run_time_grid(WK& W, const double* tgrid, const int nT,
   if (!gync_all_finite(W.y, GYNC_NY) || !gync_all_finite(W.q, GYNC_NQ)) return GYNC_ST_NONFINITE;
   GyncCtrl c;
   c.h = (o.h0 > 0.0) ? o.h0 : gync_initial_step(W, o.rtol, o.atol);
-  c.hacc = c.h; c.erracc = 1.0; c.nacc = 0; c.nrej = 0; c.rej_last = 0;
+  c.hacc = c.h; c.rootacc = 1.0; c.nacc = 0; c.nrej = 0; c.rej_last = 0;
   int budget = o.max_steps;
   double t = tgrid[0];
   int status = GYNC_ST_OK;

@@ -416,8 +416,7 @@ gync_mcmc_persist_kernel(const GyncMcmcP P) {
       } else if (!(h > 1e-14 * fmax(1.0, fabs(t)))) {
         st = GYNC_ST_HMIN;
       } else {
-        const bool fin = gync_all_finite(W.yn, GYNC_NY);
-        if (gync_ctrl_update(ctl, h, err, fin)) {
+        if (gync_ctrl_update(ctl, h, err, true)) {       // a non-finite candidate arrives as err = NaN
           t = last ? tn : t + h;
 #pragma unroll
           for (int i = 0; i < GYNC_NY; ++i) W.y[i] = W.yn[i];

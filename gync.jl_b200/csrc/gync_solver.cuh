@@ -92,6 +92,14 @@ struct GyncStepStats {   // per-sample work counters (roofline bookkeeping, SURV
 #define RD_C64 18.40807009793095
 #define RD_C65 (-5.714285714285717)
 
+// study hooks (tools/rodas5/errweights.cpp only): per-species weights in / statistics of the error norm
+#ifndef GYNC_ERRW
+#  define GYNC_ERRW(i)
+#endif
+#ifndef GYNC_ERRSTAT
+#  define GYNC_ERRSTAT(i, r)
+#endif
+
 struct GyncWork {          // host layout (tests); the device layout is GyncWorkSm in gync_kernels.cuh
   double q[GYNC_NQ];
   double y[GYNC_NY];
@@ -136,6 +144,24 @@ GYNC_TABLE double RD_TC[5][5] = {{RD_C21, 0, 0, 0, 0},
 template <class T>
 GYNC_HD static const T& gync_ro(const T& a) { return a; }
 
+// Finish a step attempt: W.yn (the last stage point) += W.e (the last increment = the error estimate); returns the scaled
+// RMS norm of the estimate, or NaN when the candidate is not finite (the controller then shrinks hard).  Three partial
+// sums: a single accumulator is a chain of 33 dependent FMAs, and nothing else runs in this warp to hide it.
+template <class WK>
+GYNC_HD static double gync_finish_step(WK& W, const double rtol, const double atol) {
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, chk0 = 0.0, chk1 = 0.0;
+#pragma unroll
+  for (int i = 0; i < GYNC_NY; ++i) {
+    W.yn[i] += W.e[i];
+    const double sc = atol + rtol * fmax(fabs(W.y[i]), fabs(W.yn[i]));
+    const double r = W.e[i] * GYNC_RCP(sc) GYNC_ERRW(i);
+    if (i % 3 == 0) s0 = fma(r, r, s0); else if (i % 3 == 1) s1 = fma(r, r, s1); else s2 = fma(r, r, s2);
+    if (i & 1) chk1 = fma(W.yn[i], 0.0, chk1); else chk0 = fma(W.yn[i], 0.0, chk0);     // Inf/NaN -> NaN
+    GYNC_ERRSTAT(i, r)
+  }
+  return sqrt(((s0 + s1) + s2) * (1.0 / GYNC_NY)) + (chk0 + chk1);
+}
+
 // One step attempt of size h from W.y; on return W.yn = y(t+h) candidate, returns the scaled
 // error norm (RMS over the 33 species of e_i / (atol + rtol*max(|y_i|,|yn_i|))).
 // Storage: W.q, W.A, W.k may be shared-memory views (every read a real load); W.y, W.yn and the
@@ -176,16 +202,9 @@ GYNC_HD static double gync_rodas4_step(WK& W, const double h, const double rtol,
     gync_lusolve(gync_ro(W.A), W.e);
     GYNC_TICK(2)
   }
-  double sum = 0.0;
-#pragma unroll
-  for (int i = 0; i < GYNC_NY; ++i) {
-    W.yn[i] += W.e[i];
-    const double sc = atol + rtol * fmax(fabs(W.y[i]), fabs(W.yn[i]));
-    const double r = W.e[i] * GYNC_RCP(sc);
-    sum = fma(r, r, sum);
-  }
+  const double err = gync_finish_step(W, rtol, atol);
   GYNC_TICK(6)
-  return sqrt(sum * (1.0 / GYNC_NY));
+  return err;
 }
 
 // ---- Rodas5P (G. Steinebach, "Construction of Rosenbrock-Wanner method Rodas5P and numerical benchmarks within the
@@ -317,15 +336,7 @@ GYNC_HD static double gync_rodas5p_step(WK& W, const double h, const double rtol
     for (int i = 0; i < GYNC_NY; ++i) W.e[i] = fma(ih, (double)W.k[5 * GYNC_NY + i], W.e[i]);
     gync_lusolve(gync_ro(W.A), W.e);
   }
-  double sum = 0.0;
-#pragma unroll
-  for (int i = 0; i < GYNC_NY; ++i) {
-    W.yn[i] += W.e[i];
-    const double sc = atol + rtol * fmax(fabs(W.y[i]), fabs(W.yn[i]));
-    const double r = W.e[i] * GYNC_RCP(sc);
-    sum = fma(r, r, sum);
-  }
-  return sqrt(sum * (1.0 / GYNC_NY));
+  return gync_finish_step(W, rtol, atol);
 }
 
 // Which method the library steps with: 5 = Rodas5P (default), 4 = RODAS4P (kept for A/B runs and the order tests).
@@ -336,10 +347,12 @@ GYNC_HD static double gync_rodas5p_step(WK& W, const double h, const double rtol
 #  ifndef GYNC_ERR_ROOT
 #  define GYNC_ERR_ROOT(err) exp(0.2 * log(err))         /* embedded order 4: err ~ h^5 */
 #  endif
+#  define GYNC_ERR_ROOT_1E2 0.39810717055349725           /* (1e-2)^(1/5) */
 template <class WK>
 GYNC_HD static double gync_ros_step(WK& W, const double h, const double rtol, const double atol) { return gync_rodas5p_step(W, h, rtol, atol); }
 #else
 #  define GYNC_ERR_ROOT(err) sqrt(sqrt(err))            /* embedded order 3: err ~ h^4 */
+#  define GYNC_ERR_ROOT_1E2 0.31622776601683794           /* (1e-2)^(1/4) */
 template <class WK>
 GYNC_HD static double gync_ros_step(WK& W, const double h, const double rtol, const double atol) { return gync_rodas4_step(W, h, rtol, atol); }
 #endif
@@ -347,12 +360,15 @@ GYNC_HD static double gync_ros_step(WK& W, const double h, const double rtol, co
 // Step-size controller state (Hairer's RODAS controller with Gustafsson's predictive term).
 struct GyncCtrl {
   double h;        // next step to try
-  double hacc, erracc;
+  double hacc;     // size of the last accepted step
+  double rootacc;  // max(1e-2, its error)^(1/(p+1)), p = order of the embedded solution
   int    nacc, nrej, rej_last;
 };
 
 // Decide on a step attempt of size h with scaled error err.  Returns true if accepted.
-// Updates c.h with the proposal for the next attempt.
+// Updates c.h with the proposal for the next attempt.  One logarithm and one exponential per attempt: the predictive
+// factor (hacc/h) (err^2/erracc)^(1/(p+1)) is root^2 / rootacc with root = err^(1/(p+1)), and rootacc is kept from the
+// previous accepted step (a lone warp per sub-partition pays every dependent instruction of this scalar code in full).
 GYNC_HD static bool gync_ctrl_update(GyncCtrl& c, const double h, double err, const bool finite) {
   const double SAFE = 0.9, FAC1 = 5.0, FAC2 = 1.0 / 6.0;
   if (!finite || !(err == err)) {          // NaN/Inf in the stage values: shrink hard
@@ -361,17 +377,17 @@ GYNC_HD static bool gync_ctrl_update(GyncCtrl& c, const double h, double err, co
     c.rej_last = 1;
     return false;
   }
-  double fac = fmax(FAC2, fmin(FAC1, GYNC_ERR_ROOT(err) * (1.0 / SAFE)));
-  double hnew = h / fac;
+  const double root = GYNC_ERR_ROOT(err);
+  double fac = fmax(FAC2, fmin(FAC1, root * (1.0 / SAFE)));
   if (err <= 1.0) {
     if (c.nacc > 0) {
-      double facgus = (c.hacc / h) * GYNC_ERR_ROOT(err * err / c.erracc) * (1.0 / SAFE);
+      double facgus = (c.hacc * GYNC_RCP(h)) * (root * root) * GYNC_RCP(c.rootacc) * (1.0 / SAFE);
       facgus = fmax(FAC2, fmin(FAC1, facgus));
       fac = fmax(fac, facgus);
-      hnew = h / fac;
     }
+    double hnew = h * GYNC_RCP(fac);
     c.hacc = h;
-    c.erracc = fmax(1.0e-2, err);
+    c.rootacc = fmax(GYNC_ERR_ROOT_1E2, root);
     if (c.rej_last) hnew = fmin(hnew, h);
     c.rej_last = 0;
     c.nacc++;
@@ -380,7 +396,7 @@ GYNC_HD static bool gync_ctrl_update(GyncCtrl& c, const double h, double err, co
   }
   c.nrej++;
   c.rej_last = 1;
-  c.h = hnew;
+  c.h = h * GYNC_RCP(fac);
   return false;
 }
 
@@ -435,8 +451,7 @@ GYNC_HD static int gync_attempt(WK& W, GyncCtrl& c, double& t, const double tend
   if (!(h > 1e-14 * fmax(1.0, fabs(t)))) return -GYNC_ST_HMIN;
   const double hprop = c.h;
   const double err = gync_ros_step(W, h, o.rtol, o.atol);
-  const bool fin = gync_all_finite(W.yn, GYNC_NY);
-  if (gync_ctrl_update(c, h, err, fin)) {
+  if (gync_ctrl_update(c, h, err, true)) {          // a non-finite candidate arrives as err = NaN (gync_finish_step)
     t = last ? tend : t + h;
 #pragma unroll
     for (int i = 0; i < GYNC_NY; ++i) W.y[i] = W.yn[i];
@@ -460,5 +475,5 @@ GYNC_HD static int gync_advance(WK& W, GyncCtrl& c, double& t, const double tend
 }
 
 GYNC_HD static void gync_ctrl_init(GyncCtrl& c, double h) {
-  c.h = h; c.hacc = h; c.erracc = 1.0; c.nacc = 0; c.nrej = 0; c.rej_last = 0;
+  c.h = h; c.hacc = h; c.rootacc = 1.0; c.nacc = 0; c.nrej = 0; c.rej_last = 0;
 }
