@@ -81,6 +81,8 @@ type B200Variate
   SigmaL::Matrix{Float64}       # chol(propvar).L (model.jl:104)
   seed::UInt64
   iteration::UInt64
+  chain_id::UInt64              # Philox stream of this chain: draws are addressed by (seed, chain_id, iteration), so a chain
+                                # keeps its stream through batch()/save/load and whatever group it is advanced in
   # AMMTune adaptation state (used when c.adapt; m < 0: adaptation not started)
   m::Vector{Int64}              # length 1
   Mv::Vector{Float64}           # 116
@@ -108,18 +110,18 @@ function sample!(s::Sampling, iters::Int)
   o     = Ref(SolverOpts(7e-10, 1e-11))
   if c.adapt                                            # Mamba.sample!(variate, adapt=true) (sampling.jl:72, model.jl:104-106)
     tune = Ref(AmmTune(0.05, 2.38, pointer(v.m), pointer(v.Mv), pointer(v.Mvv), pointer(v.SigmaLm)))
-    check(ccall((:gync_mcmc_run_amm, LIBGYNC), Cint,
+    check(ccall((:gync_mcmc_run_amm_ids, LIBGYNC), Cint,
                 (Ptr{Cdouble}, Ptr{Cdouble}, Int64, Ptr{Cdouble}, Cdouble, Ptr{Cdouble}, Cint, Ptr{Cdouble}, Ptr{Cint},
-                 Ptr{Cdouble}, Ptr{SolverOpts}, Int64, Cint, UInt64, UInt64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble},
+                 Ptr{Cdouble}, Ptr{SolverOpts}, Int64, Cint, UInt64, UInt64, Ptr{UInt64}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble},
                  Ptr{Cdouble}, Ptr{Int64}, Ptr{AmmTune}),
                 state, lf, 1, v.SigmaL, 0.0, data(c), 1, [c.sigma_rho], Cint[0], priorvector(c), o,
-                iters, thin, v.seed, v.iteration, C_NULL, C_NULL, C_NULL, out, nacc, tune))
+                iters, thin, v.seed, v.iteration, UInt64[v.chain_id], C_NULL, C_NULL, C_NULL, out, nacc, tune))
   else
-  check(ccall((:gync_mcmc_run, LIBGYNC), Cint,
+  check(ccall((:gync_mcmc_run_ids, LIBGYNC), Cint,           # one persistent launch; chains shard over gync_init_multi's devices
               (Ptr{Cdouble}, Ptr{Cdouble}, Int64, Ptr{Cdouble}, Cdouble, Ptr{Cdouble}, Cint, Ptr{Cdouble}, Ptr{Cint},
-               Ptr{Cdouble}, Ptr{SolverOpts}, Int64, Cint, UInt64, UInt64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Int64}),
+               Ptr{Cdouble}, Ptr{SolverOpts}, Int64, Cint, UInt64, UInt64, Ptr{UInt64}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Int64}),
               state, lf, 1, v.SigmaL, 0.0, data(c), 1, [c.sigma_rho], Cint[0], priorvector(c), o,
-              iters, thin, v.seed, v.iteration, C_NULL, C_NULL, out, nacc))
+              iters, thin, v.seed, v.iteration, UInt64[v.chain_id], C_NULL, C_NULL, out, nacc))
   end
   v.state, v.logf, v.iteration = vec(state), lf[1], v.iteration + iters
   s.samples = vcat(s.samples, out)                      # sampling.jl:66-68,74
