@@ -578,7 +578,7 @@ int gync_em_comm_create(int32_t world, int32_t rank, void* handle_out /* 64 byte
   if (int rc = ensure_init()) return rc;
   gync_em_comm* c = new gync_em_comm();
   c->world = world; c->rank = rank;
-  const size_t mail_bytes = sizeof(double) * 2 * world * c->MT;
+  const size_t mail_bytes = sizeof(double) * 2 * world * c->MT * 2;      // [2 slots][world][MT] values x 2 self-validating words
   c->flag_off = (mail_bytes + 255) / 256 * 256;
   const size_t total = c->flag_off + sizeof(unsigned long long) * 2 * world;
   // every failure path below releases what was allocated so far (gync_em_comm_destroy copes with a half-built object)

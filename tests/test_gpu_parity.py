@@ -565,6 +565,57 @@ def test_persistent_kernel_equals_round_loop(gpu):
     assert k.value >= 1        # the last call above was a round-loop run: the counters belong to the persistent run before it
 
 
+def test_persistent_kernel_high_acceptance_and_edge_cases(gpu):
+    """The cancellation machinery under stress and the corners: a small proposal (acceptance ~50 %: almost every window is
+    cancelled and re-issued, generations turn over every other iteration) for one chain with a deep window and for many
+    chains with a shallow one, bit-identical to the round loop; thin > iters (no output rows); an all-missing patient
+    table (every proposal scores -Inf: the chain never moves, model.jl:161); zero iterations."""
+    small = gpu.api.uniformpropvar(0.002)
+    nan_patient = gpu.Patient(np.full((31, 4), np.nan), "none")
+    for pats, iters, thin in (((1,), 60, 1), (tuple(range(1, 25)), 30, 2)):
+        runs = []
+        for rounds in (False, True):
+            if rounds:
+                os.environ["GYNC_MCMC_ROUNDS"] = "1"
+            try:
+                ss = gpu.sample_chains([gpu.new_sampling(gpu.Config(gpu.Lausanne(i), propvar=small, thin=thin), seed=33) for i in pats], iters)
+            finally:
+                os.environ.pop("GYNC_MCMC_ROUNDS", None)
+            runs.append(ss)
+        for a, b in zip(*runs):
+            assert np.array_equal(a.samples, b.samples) and a.variate.naccept == b.variate.naccept and a.variate.logf == b.variate.logf
+        acc = np.mean([x.variate.naccept for x in runs[0]]) / iters
+        assert 0.2 < acc < 0.9, acc
+    s = gpu.sample(gpu.Config(gpu.Lausanne(1), thin=50), 20, seed=2)
+    assert s.samples.shape == (0, 116) and s.variate.iteration == 20
+    s = gpu.sample_bang(s, 30)
+    assert s.samples.shape == (0, 116) and s.variate.iteration == 50          # floor(30/50) rows per call, like the reference
+    dead = gpu.sample(gpu.Config(nan_patient), 15, seed=2)
+    assert dead.variate.naccept == 0 and dead.variate.logf == -np.inf
+    assert np.allclose(dead.samples, np.tile(gpu.api.init(dead.config), (15, 1)), rtol=1e-15)
+    z = gpu.sample(gpu.Config(), 0, seed=2)
+    assert z.samples.shape == (0, 116)
+
+
+def test_chains_sharded_over_devices_in_one_process(gpu):
+    """gync_init_multi: the library gives every device a contiguous block of the chains and its own persistent kernel; the
+    chains are bit-identical to the same chains on one device (their Philox streams belong to them).  Needs >= 2 GPUs."""
+    import torch
+    nd = torch.cuda.device_count()
+    if nd < 2:
+        pytest.skip("needs at least two GPUs")
+    lib, L = gpu.lib.load(), gpu.lib
+    mk = lambda: [gpu.new_sampling(gpu.Config(gpu.Lausanne(1 + i % 5), thin=2), seed=8) for i in range(3 * nd + 1)]
+    one = gpu.sample_chains(mk(), 20)
+    L.check(lib.gync_init_multi(nd, None))
+    try:
+        many = gpu.sample_chains(mk(), 20)
+    finally:
+        L.check(lib.gync_init(0))
+    for a, b in zip(one, many):
+        assert np.array_equal(a.samples, b.samples) and a.variate.naccept == b.variate.naccept and a.variate.logf == b.variate.logf
+
+
 def test_chain_keeps_its_random_stream_when_resumed_alone(gpu, tmp_path):
     """A chain advanced inside a group and later resumed ALONE (sample!, batch, load) continues the stream it would have
     drawn from inside the group: the Philox stream id is the variate's chain_id, persisted by save/load, not the
