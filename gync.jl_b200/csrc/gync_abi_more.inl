@@ -644,6 +644,16 @@ int gync_em_iterate_fused_dev(gync_em_comm* c, double* dw, const double* dL, int
 #undef CALL
 }
 
+#ifdef GYNC_EM_PHASES
+// profile builds only: read and clear the phase counters of the current device
+int gync_em_phase_read(uint64_t* out8) {
+  CK(cudaMemcpyFromSymbol(out8, gync_em_phase, sizeof(unsigned long long) * 8));
+  unsigned long long z[8] = {0};
+  CK(cudaMemcpyToSymbol(gync_em_phase, z, sizeof(z)));
+  return GYNC_OK;
+}
+#endif
+
 int gync_em_comm_error(gync_em_comm* c) {
   if (!c) return -1;
   int e = 0;

@@ -966,6 +966,16 @@ struct GyncEmSync {
   unsigned long long arrive0;   // value of *arrive when this launch starts
 };
 
+// -DGYNC_EM_PHASES builds only (tools/em_phase_breakdown.py): SM-clock ticks per phase, summed over blocks and iterations.
+// [0] local pass  [1] arrival -> all contributions read (what a block waits)  [2] gather by the last-arriving block
+// [3] its stores into the mailboxes  [4] rank-order sum + reciprocals  [5] block-iterations counted  [6] sends counted
+#ifdef GYNC_EM_PHASES
+__device__ unsigned long long gync_em_phase[8];
+#  define GYNC_EP(...) __VA_ARGS__
+#else
+#  define GYNC_EP(...)
+#endif
+
 template <int MH, bool FULL, bool RESIDENT>
 __global__ void __launch_bounds__(GYNC_EM_THREADS, 1)
 gync_em_kernel(double* __restrict__ w, const double* __restrict__ L, int64_t K, int M, int niter, int rows_per_block,
@@ -996,6 +1006,7 @@ gync_em_kernel(double* __restrict__ w, const double* __restrict__ L, int64_t K, 
   }
   for (int it = -1; it < niter; ++it) {
     double* pbuf = partials + (size_t)((it + 1) & 1) * nb * MT;      // double-buffered block partials
+    GYNC_EP(const long long ep0 = clock64();)
     // ---- local pass (it == -1: first denominators only)
     if (RESIDENT) {
       double acc[MH];
@@ -1041,6 +1052,7 @@ gync_em_kernel(double* __restrict__ w, const double* __restrict__ L, int64_t K, 
     const unsigned long long seq = sync.seq0 + (unsigned long long)(it + 1);
     const int slot = (int)(seq & 1ull);
     const unsigned long long want = sync.arrive0 + (unsigned long long)nb * (unsigned long long)(it + 2);
+    GYNC_EP(const long long ep1 = clock64();)
     if (threadIdx.x == 0) {
       __threadfence();
       const unsigned long long prev = atomicAdd(sync.arrive, 1ull);
@@ -1069,24 +1081,31 @@ gync_em_kernel(double* __restrict__ w, const double* __restrict__ L, int64_t K, 
     // rank's n+1, which this rank sends only once ALL its blocks have arrived for n+1, i.e. are done reading n.
     __syncthreads();
     if (sm.last) {
+      GYNC_EP(const long long eg0 = clock64();)
       __threadfence();
       em_gather_partials<MH>(pbuf, nb, M, sm, sm.rinv, false);                // this GPU's denominators (fixed order)
+      GYNC_EP(const long long eg1 = clock64();)
       for (int idx = threadIdx.x; idx < peer.world * MT; idx += GYNC_EM_THREADS) {
         const int p = idx / MT, m = idx % MT;
         gync_em_ll_store(peer.mail[p], ((size_t)slot * peer.world + peer.rank) * MT + m, sm.rinv[m], seq);
       }
+      GYNC_EP(if (threadIdx.x == 0) { atomicAdd(&gync_em_phase[2], (unsigned long long)(eg1 - eg0));
+                                      atomicAdd(&gync_em_phase[3], (unsigned long long)(clock64() - eg1)); atomicAdd(&gync_em_phase[6], 1ull); })
     }
     bool ok = true;
     for (int idx = threadIdx.x; idx < peer.world * MT; idx += GYNC_EM_THREADS)
       ok &= gync_em_ll_load(peer.mail[peer.rank], (size_t)slot * peer.world * MT + idx, seq, err_flag, &sm.part[idx]);
     // a timed-out wait anywhere (this GPU or, through the flag, a peer that gave up) ends the loop for every block
     if (__syncthreads_or(!ok || (threadIdx.x == 0 && *(volatile int*)err_flag != 0))) break;
+    GYNC_EP(const long long ep2 = clock64();)
     if (threadIdx.x < MT) {
       double v = 0.0;
       for (int r = 0; r < peer.world; ++r) v += sm.part[r * MT + threadIdx.x];     // rank order: identical everywhere
       sm.rinv[threadIdx.x] = (threadIdx.x < M) ? 1.0 / v : 0.0;
     }
     __syncthreads();
+    GYNC_EP(if (threadIdx.x == 0) { atomicAdd(&gync_em_phase[0], (unsigned long long)(ep1 - ep0)); atomicAdd(&gync_em_phase[1], (unsigned long long)(ep2 - ep1));
+                                    atomicAdd(&gync_em_phase[4], (unsigned long long)(clock64() - ep2)); atomicAdd(&gync_em_phase[5], 1ull); })
   }
 }
 

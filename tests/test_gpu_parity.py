@@ -570,7 +570,7 @@ def test_persistent_kernel_high_acceptance_and_edge_cases(gpu):
     cancelled and re-issued, generations turn over every other iteration) for one chain with a deep window and for many
     chains with a shallow one, bit-identical to the round loop; thin > iters (no output rows); an all-missing patient
     table (every proposal scores -Inf: the chain never moves, model.jl:161); zero iterations."""
-    small = gpu.api.uniformpropvar(0.002)
+    small = gpu.api.uniformpropvar(0.0007)
     nan_patient = gpu.Patient(np.full((31, 4), np.nan), "none")
     for pats, iters, thin in (((1,), 60, 1), (tuple(range(1, 25)), 30, 2)):
         runs = []
@@ -585,7 +585,7 @@ def test_persistent_kernel_high_acceptance_and_edge_cases(gpu):
         for a, b in zip(*runs):
             assert np.array_equal(a.samples, b.samples) and a.variate.naccept == b.variate.naccept and a.variate.logf == b.variate.logf
         acc = np.mean([x.variate.naccept for x in runs[0]]) / iters
-        assert 0.2 < acc < 0.9, acc
+        assert 0.15 < acc < 0.95, acc
     s = gpu.sample(gpu.Config(gpu.Lausanne(1), thin=50), 20, seed=2)
     assert s.samples.shape == (0, 116) and s.variate.iteration == 20
     s = gpu.sample_bang(s, 30)
