@@ -89,6 +89,8 @@ struct GyncLlhSink {
   double* acc;                         // LL + n   (stride N over patients)
   double* ymeas;                       // Ymeas + n (N x 62 x 4) or nullptr
   bool enabled = true;                 // mirror lanes of the TMEM kernel compute but do not write
+  double r0 = 0.0;                     // M == 1 (the bench shape, and every Metropolis sample): the sum stays in a register
+                                       // instead of a global read-modify-write per measurement hit
   __device__ __forceinline__ void operator()(int period, int day, const double* y) {
     if (!enabled) return;
     const double ym[GYNC_NMEAS] = {y[1], y[6], y[23], y[24]};   // measuredinds (model.jl:1)
@@ -106,7 +108,7 @@ struct GyncLlhSink {
           a = fma(r, r, a);
         }
       }
-      acc[N * m] += a;
+      if (M == 1) r0 += a; else acc[N * m] += a;
     }
   }
 };
@@ -461,7 +463,8 @@ gync_loglik_tm_kernel(const double* __restrict__ X, int64_t N, const double* __r
         sink.data = data + (size_t)GYNC_NDAYS * GYNC_NMEAS * mlo;
         sink.iscale = iscale + GYNC_NMEAS * mlo;
         sink.M = mcnt;
-        if (real) for (int m = 0; m < mcnt; ++m) LL[n + N * m] = 0.0;
+        if (real && mcnt > 1) for (int m = 0; m < mcnt; ++m) LL[n + N * m] = 0.0;
+        sink.r0 = 0.0;
         sink.acc = LL + n;
         sink.ymeas = Ymeas ? Ymeas + n : nullptr;
         i0 = i1 = 0;
@@ -528,7 +531,7 @@ gync_loglik_tm_kernel(const double* __restrict__ X, int64_t N, const double* __r
       if (finished) {
         if (real) {
           for (int m = 0; m < mcnt; ++m) {
-            const double a = LL[n + N * m];
+            const double a = (mcnt == 1) ? sink.r0 : LL[n + N * m];
             LL[n + N * m] = (st != GYNC_ST_OK || allnan[mlo + m]) ? ninf : -0.5 * a;
           }
           if (st != GYNC_ST_OK && Ymeas)
