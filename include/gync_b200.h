@@ -18,7 +18,12 @@
  * Environment switches (read per call; for A/B measurements and debugging, never needed for correctness):
  *   GYNC_NO_SCHED=1        run the solver's sample queue in input order (default: longest-first by a cost model the
  *                          library refits on the device after every batch; results are bit-identical either way)
- *   GYNC_MCMC_SPEC=K       speculation depth of the Metropolis rounds (default: fills the sample slots about twice)
+ *   GYNC_MCMC_SPEC=K       proposals each chain keeps in flight, fixed (default: its share of 1.1 per solver lane, by remaining
+ *                          iterations); the chains are bit-identical for every value
+ *   GYNC_MCMC_OVERSUB=f    that 1.1
+ *   GYNC_MCMC_ROUNDS=1     non-adaptive chains through the round-1 loop of propose / solve / accept launches instead of the
+ *                          persistent kernel (A/B reference; same chains)
+ *   GYNC_MCMC_MAXSTEPS=n   step budget of the likelihood solves inside gync_mcmc_run* (default: the caller's opts)
  *   GYNC_DHZ_TWO_PASS=1    dhz as the reference's two matvecs instead of the one-pass row-fused kernel
  *   GYNC_EM_NO_RESIDENT=1  EM always streams L from HBM (default: shared-memory resident when this GPU's rows fit)
  *   GYNC_SOLVE_SM=1        gync/forwardsol through the older shared-memory solver kernel
@@ -46,8 +51,8 @@ extern "C" {
 /* ---- lifecycle ------------------------------------------------------------------------ */
 int  gync_init(int device);              /* select device, create the library stream */
 /* Drive several GPUs of one NVLink domain from ONE process (the Julia host is a single process): the host-buffer
- * entry points gync_loglik_batch and gync_em_iterate then shard samples / rows over the devices (the EM through the
- * fused peer-memory kernel).  devices == NULL means 0..ndev-1. */
+ * entry points gync_loglik_batch, gync_mcmc_run(_ids) and gync_em_iterate then shard samples / chains / rows over the
+ * devices (the EM through the fused peer-memory kernel).  devices == NULL means 0..ndev-1. */
 int  gync_init_multi(int32_t ndev, const int32_t* devices);
 int  gync_ndev(void);
 void gync_shutdown(void);
