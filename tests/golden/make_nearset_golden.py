@@ -8,6 +8,8 @@ takes minutes of CPU, so its output is frozen here; the samples themselves are r
 
     set A: PCG64(99),        2048 samples x Lausanne patients (1, 2, 5)   (the round-1 validation set)
     set B: PCG64(20260101),  4096 samples x Lausanne patients (3, 8, 12)
+    set C: PCG64(31337),     4096 samples x Lausanne patients (4, 10, 21) — held out: added after the method and the default
+           tolerance had been chosen on A and B, never used to tune anything
 
 x = exp(log(init) + 0.0998 z), z ~ N(0, I_116): one default proposal step from the reference point
 (cfg 2 "near").
@@ -24,7 +26,9 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "..", "..", "oracle"))
 
-SETS = {"A": (99, 2048, (0, 1, 4)), "B": (20260101, 4096, (2, 7, 11))}
+SETS = {"A": (99, 2048, (0, 1, 4)), "B": (20260101, 4096, (2, 7, 11)),
+        # HELD OUT: drawn and solved after the solver, its tolerance and every other knob had been fixed on A and B
+        "C": (31337, 4096, (3, 9, 20))}
 
 
 def wide_set(seed, n):

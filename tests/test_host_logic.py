@@ -77,13 +77,13 @@ def test_solver_core_on_the_parity_tail_fixtures(host_shim):
     """CPU build of the device solver at the library default tolerance against the frozen near-set log-likelihoods
     (tests/golden/nearset_llh_golden.npz): a slice of both populations plus the two samples that were above the 1e-8
     bound in round 1 (RODAS4 at 1e-8/1e-10: 4.6e-8 and 1.1e-8), and a slice of the wide set incl. its failure set.
-    The -m gpu suite runs all 18 432 + 512 cases."""
+    The -m gpu suite runs all 30 720 + 512 cases."""
     sys.path.insert(0, G)
     import make_nearset_golden as mg
     g = np.load(os.path.join(G, "nearset_llh_golden.npz"))
     la = o.patients()[0]
     worst = 0.0
-    for name, idx in (("A", list(range(40)) + [187, 963, 740]), ("B", list(range(40)) + [2730, 2929])):
+    for name, idx in (("A", list(range(40)) + [187, 963, 740]), ("B", list(range(40)) + [2730, 2929]), ("C", list(range(40)))):
         seed, n, pats = mg.SETS[name]
         X = mg.near_set(seed, n)
         for i in idx:

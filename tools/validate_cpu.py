@@ -37,7 +37,7 @@ if __name__ == "__main__":
     for rt, at in tols:
         key = f"rtol{rt:g}_atol{at:g}"
         out[key] = {}
-        for name in ("A", "B"):
+        for name in ("A", "B", "C"):
             seed, n, pats = mg.SETS[name]
             X = mg.near_set(seed, n)
             with ThreadPoolExecutor(os.cpu_count()) as ex:
