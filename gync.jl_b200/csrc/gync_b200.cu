@@ -355,16 +355,18 @@ int em_launch_variant(EmLaunchState& st, const GyncEmPeer& peer, double* dw, con
   } else {
     nb = (int)std::min<int64_t>(g_num_sms, std::max<int64_t>((K + rows_per_pass - 1) / rows_per_pass, 1));
   }
-  CK(cudaFuncSetAttribute(gync_em_kernel<MH, FULL, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const void* kern = (peer.world > 1) ? (const void*)gync_em_kernel<MH, FULL, RESIDENT, true>
+                                      : (const void*)gync_em_kernel<MH, FULL, RESIDENT, false>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gync_em_kernel<MH, FULL, RESIDENT>, GYNC_EM_THREADS, smem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GYNC_EM_THREADS, smem));
   if (per_sm < 1) return RESIDENT ? GYNC_OK : fail(GYNC_ERR_CUDA, "EM kernel does not fit on an SM");
   GyncEmSync sync = {st.sync_words, st.sync_words + 1, st.seq, st.arrive0};
   GyncEmPeer pr = peer;
   int Ri = (int)R;
   void* args[] = {&dw, &dL, &K, &M, &niter, &Ri, &st.partials, &st.gnorm, &sync, &pr, &st.err, &d_hist};
   if (st.busy) CK(cudaStreamWaitEvent(s, st.busy, 0));
-  CK(cudaLaunchCooperativeKernel((void*)gync_em_kernel<MH, FULL, RESIDENT>, dim3(nb), dim3(GYNC_EM_THREADS), args, smem, s));
+  CK(cudaLaunchCooperativeKernel(kern, dim3(nb), dim3(GYNC_EM_THREADS), args, smem, s));
   if (st.busy) CK(cudaEventRecord(st.busy, s));
   st.seq += (unsigned long long)niter + 1ull;
   st.arrive0 += (unsigned long long)nb * ((unsigned long long)niter + 1ull);

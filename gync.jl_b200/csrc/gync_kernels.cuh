@@ -979,7 +979,10 @@ __device__ unsigned long long gync_em_phase[8];
 #  define GYNC_EP(...)
 #endif
 
-template <int MH, bool FULL, bool RESIDENT>
+// MULTI: the exchange with peer GPUs is compiled in.  A separate instantiation, because the exchange code in the same
+// body cost the single-GPU streaming pass 9 % (60.3 vs 54.9 us per iteration at K = 1e6: two registers over, a worse
+// schedule of the pass's loads) although it never executed there.
+template <int MH, bool FULL, bool RESIDENT, bool MULTI>
 __global__ void __launch_bounds__(GYNC_EM_THREADS, 1)
 gync_em_kernel(double* __restrict__ w, const double* __restrict__ L, int64_t K, int M, int niter, int rows_per_block,
                double* __restrict__ partials /* 2 x gridDim.x x 2MH */, double* __restrict__ gnorm /* 2 x 2MH */,
@@ -1059,9 +1062,9 @@ gync_em_kernel(double* __restrict__ w, const double* __restrict__ L, int64_t K, 
     if (threadIdx.x == 0) {
       __threadfence();
       const unsigned long long prev = atomicAdd(sync.arrive, 1ull);
-      sm.last = (prev + 1ull == want);
+      if constexpr (MULTI) sm.last = (prev + 1ull == want);
     }
-    if (peer.world == 1) {
+    if constexpr (!MULTI) {
       // single GPU: every block waits for all arrivals and gathers the partials itself (same fixed order
       // everywhere) — two L2 round trips shorter than publish-and-poll through block 0
       if (threadIdx.x == 0) {
@@ -1070,8 +1073,7 @@ gync_em_kernel(double* __restrict__ w, const double* __restrict__ L, int64_t K, 
       }
       if (__syncthreads_or(threadIdx.x == 0 && *(volatile int*)err_flag != 0)) break;
       em_gather_partials<MH>(partials + (size_t)((it + 1) & 1) * nb * MT, nb, M, sm, sm.rinv, true);
-      continue;
-    }
+    } else {
     // several GPUs: ONE-SHOT exchange.  The block that arrives LAST (it knows: the arrival counter told it) sums the
     // block partials in the fixed order and stores this GPU's M partial denominators straight into the mailbox of every
     // rank — its own included — as self-validating words over NVLink.  EVERY block of every rank then polls its own GPU's
@@ -1109,6 +1111,7 @@ gync_em_kernel(double* __restrict__ w, const double* __restrict__ L, int64_t K, 
     __syncthreads();
     GYNC_EP(if (threadIdx.x == 0) { atomicAdd(&gync_em_phase[0], (unsigned long long)(ep1 - ep0)); atomicAdd(&gync_em_phase[1], (unsigned long long)(ep2 - ep1));
                                     atomicAdd(&gync_em_phase[4], (unsigned long long)(clock64() - ep2)); atomicAdd(&gync_em_phase[5], 1ull); })
+    }
   }
 }
 
