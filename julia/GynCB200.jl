@@ -90,6 +90,15 @@ type B200Variate
   SigmaLm::Matrix{Float64}      # 116 x 116, the library stores the lower factor ROW-major == its transpose column-major
 end
 
+# SamplerVariate(c) (model.jl:97-107): state = log(init(c)), SigmaL = chol(propvar)'.  Chains created without a seed share a
+# per-process random seed and take the next value of a process-wide counter as their stream id, so separately launched
+# chains never share their noise (the reference draws from Julia's global RNG).
+const PROCESS_SEED  = UInt64[rand(RandomDevice(), UInt64)]
+const NEXT_CHAIN_ID = UInt64[0]
+function SamplerVariate(c::Config; seed::UInt64=PROCESS_SEED[1], chain_id::UInt64=(NEXT_CHAIN_ID[1] += 1) - 1)
+  B200Variate(log(init(c)), NaN, full(chol(c.propvar)'), seed, UInt64(0), chain_id, Int64[-1], zeros(116), zeros(116, 116), zeros(116, 116))
+end
+
 immutable AmmTune               # gync_amm_tune
   beta::Cdouble
   scale::Cdouble
