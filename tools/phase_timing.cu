@@ -1,5 +1,6 @@
-// Debug tool: per-phase clock64 attribution of one RODAS4 step (thread 0 of block 0).
-// slots: 0 rhs_w, 1 lu, 2 lusolve (first two only), 3 stage combos (first), 4 rhs (first), 5 everything after
+// Debug tool: per-phase clock64 attribution of the Rosenbrock step the library is built with (thread 0 of block 0; Rodas5P by
+// default, -DGYNC_ROS_ORDER=4 for RODAS4P).  slots: 0 rhs_w, 1 lu, 2 triangular solves, 3 stage sums (TMEM), 4 rhs, 5 e += v, 6 norm
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I gync.jl_b200/csrc tools/phase_timing.cu -o tools/phase_timing.bin
 #define GYNC_PHASE_TIMING
 #include <cstdio>
 #include "gync_kernels.cuh"
@@ -20,7 +21,11 @@ int main() {
   gync_loglik_tm_kernel<<<148, 128, GyncWorkTm::kSmemBytes>>>(X, N, D, isc, an, 1, nullptr, o, LL, nullptr, nullptr, nullptr, cnt, nullptr);
   cudaError_t e = cudaDeviceSynchronize(); printf("%s LL0=%f\n", cudaGetErrorString(e), LL[0]);
   long long h[8]; cudaMemcpyFromSymbol(h, gync_phase_clk, sizeof(h));
-  const char* nm[] = {"rhs_w", "lu", "lusolve x6", "stage combos (TMEM) x5", "rhs x5", "e += v (TMEM) x5", "norm", "outside step"};
+  #if GYNC_ROS_ORDER == 5
+  const char* nm[] = {"rhs_w (RHS + Jacobian + W)", "lu", "lusolve x8", "stage sums (TMEM) x7", "rhs x7", "e += v (TMEM) x7", "error norm", "outside step"};
+#else
+  const char* nm[] = {"rhs_w (RHS + Jacobian + W)", "lu", "lusolve x6", "stage sums (TMEM) x5", "rhs x5", "e += v (TMEM) x5", "error norm", "outside step"};
+#endif
   long long tot = 0; for (int i = 0; i < 7; ++i) tot += h[i];
   for (int i = 0; i < 7; ++i) printf("%-40s %12lld  %.1f%%\n", nm[i], h[i], 100.0 * h[i] / tot);
   return 0;
