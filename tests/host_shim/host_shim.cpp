@@ -61,6 +61,20 @@ int hs_meas_traj(const double* x, double rtol, double atol, int max_steps, doubl
   return status;
 }
 
+// the same with a step-size cap (order tests: a loose tolerance and hmax = h give fixed steps)
+int hs_meas_traj_hmax(const double* x, double rtol, double atol, double hmax, int max_steps, double* traj, int* nacc, int* nrej) {
+  GyncWork W;
+  double T;
+  gync_load_sample(W, [&](int k) { return x[k]; }, REFALLPARMS, SAMPLEDINDS, &T);
+  GyncSolverOpts o = {rtol, atol, hmax, hmax, max_steps};
+  MeasSink s = {traj};
+  GyncStepStats st = {0, 0};
+  int status = gync_run_meas_grid(W, T, o, s, &st);
+  *nacc = st.nacc; *nrej = st.nrej;
+  if (status) for (int i = 0; i < 248; ++i) traj[i] = NAN;
+  return status;
+}
+
 struct GridSink {
   double* Y;
   void operator()(int k, const double* y) { for (int i = 0; i < GYNC_NY; ++i) Y[k * GYNC_NY + i] = y[i]; }

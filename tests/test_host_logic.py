@@ -130,7 +130,7 @@ def _tableau():
 
 
 def test_rosenbrock_tableau_order_conditions():
-    """The solver's coefficient table (RODAS4P) is pinned by the Rosenbrock order conditions themselves
+    """The 6-stage alternative's coefficient table (RODAS4P, -DGYNC_ROS_ORDER=4 builds) is pinned by the Rosenbrock order conditions themselves
     (Hairer & Wanner II, Table IV.7.1): all 8 conditions up to order 4 for the propagated weights, the 4 conditions up
     to order 3 for the embedded weights, stiff accuracy (alpha_6 = 1, last stage weight 1) — a wrong digit in any
     coefficient breaks them at the 1e-6 level, they hold to 1e-13."""
@@ -153,6 +153,79 @@ def test_rosenbrock_tableau_order_conditions():
     mh[5] = 0.0
     ch = cond(mh @ Gam)
     assert np.max(np.abs(ch[:4])) < 1e-13 and np.max(np.abs(ch[4:])) > 1e-3     # embedded: order 3, not 4
+
+
+def _tableau5():
+    """R5_* macros of csrc/gync_solver.cuh -> (gamma, A, C, weights, embedded weights) of the 8-stage implementation form
+    of Rodas5P, with the structure the step function relies on: stage 7 = stage-6 point + k6, stage 8 = stage-7 point + k7,
+    new solution = stage-8 point + k8, error estimate = k8."""
+    src = open(os.path.join(ROOT, "gync.jl_b200", "csrc", "gync_solver.cuh")).read()
+    co_ = {m.group(1): float(m.group(2).strip("()")) for m in re.finditer(r"#define R5_([AGC]\d*)\s+(\(?-?[0-9.e+-]+\)?)", src)}
+    A, Cm = np.zeros((8, 8)), np.zeros((8, 8))
+    for k, v in co_.items():
+        if k[0] == "A":
+            A[int(k[1]) - 1, int(k[2]) - 1] = v
+        elif k[0] == "C":
+            Cm[int(k[1]) - 1, int(k[2]) - 1] = v
+    assert np.count_nonzero(A) == 15 and np.count_nonzero(Cm) == 28
+    A[6, :5] = A[5, :5]
+    A[6, 5] = 1.0
+    A[7, :6] = A[6, :6]
+    A[7, 6] = 1.0
+    m = A[7].copy()
+    m[7] = 1.0
+    return co_["G"], A, Cm, m, A[7].copy(), co_
+
+
+def test_rodas5p_tableau_order_conditions():
+    """The default method's table (Rodas5P, written from memory of the publication) is pinned by the Rosenbrock order
+    conditions themselves: tools/rodas5/order_conditions.py generates all 17 rooted trees up to order 5; the propagated
+    weights satisfy every one of them and the embedded weights the 8 up to order 4 — and NOT order 5 — at round-off.  A
+    wrong digit in any of the 44 coefficients breaks them at the 1e-6 level.  Also: stiff accuracy, and the identities
+    behind the five-vector storage (k6 absorbed into the stored k4, k5; gync_solver.cuh)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools", "rodas5"))
+    import order_conditions as oc
+    g, A, Cm, m, mh, co_ = _tableau5()
+    res = oc.residuals(g, A, Cm, m, 5)
+    assert len(res) == 17 and max(abs(r) for _, _, r in res) < 5e-13
+    rh = oc.residuals(g, A, Cm, mh, 5)
+    assert max(abs(r) for p_, _, r in rh if p_ <= 4) < 5e-13 and max(abs(r) for p_, _, r in rh if p_ == 5) > 1e-3
+    al, be, b, Gam = oc.from_impl(g, A, Cm, m)
+    assert np.allclose(np.diag(Gam), g, atol=1e-14) and np.allclose(np.triu(Gam, 1), 0, atol=1e-13)
+    assert np.allclose(al.sum(1)[5:], 1.0, atol=1e-13)                     # stages 6..8 sit at t + h: stiffly accurate
+    # a changed digit is caught
+    A2 = A.copy()
+    A2[3, 1] += 1e-7
+    assert max(abs(r) for _, _, r in oc.residuals(g, A2, Cm, m, 5)) > 1e-9
+    # the absorption of k6 into (k4, k5): a64 b + a65 a = 1, c84 b + c85 a = c86, and stage 7's corrected coefficient
+    det = co_["C84"] * co_["A65"] - co_["C85"] * co_["A64"]
+    beta, alpha = (co_["C86"] * co_["A65"] - co_["C85"]) / det, (co_["C84"] - co_["A64"] * co_["C86"]) / det
+    assert abs(co_["A64"] * beta + co_["A65"] * alpha - 1) < 1e-13 and abs(co_["C84"] * beta + co_["C85"] * alpha - co_["C86"]) < 1e-12
+    src = open(os.path.join(ROOT, "gync.jl_b200", "csrc", "gync_solver.cuh")).read()
+    assert "#define R5_BETA  ((R5_C86 * R5_A65 - R5_C85) / R5_DET)" in src and "#define R5_ALPHA ((R5_C84 - R5_A64 * R5_C86) / R5_DET)" in src
+    assert "R5_C76 - R5_C74 * R5_BETA - R5_C75 * R5_ALPHA" in src
+
+
+def test_rodas5p_fixed_step_convergence(host_shim):
+    """The step function as built (five stored stage vectors, k6 absorbed into k4 and k5) converges at least as fast as
+    its order promises on the GynCycle ODE itself: with FIXED steps (hmax = h and a tolerance loose enough that the
+    controller always proposes more) every halving of h shrinks the change of the log-likelihood at the reference point
+    by more than 2^5, down to the round-off floor of ~1e-10 that tens of thousands of steps accumulate.  (The problem has no
+    clean asymptotic regime — its LH surge makes the pre-asymptotic decay even faster — so this bounds the order from
+    below; the order conditions above pin it exactly.)"""
+    g_ = np.load(os.path.join(G, "solution_golden.npz"))
+    la = o.patients()[0]
+    x = np.ascontiguousarray(g_["X"][0])
+    LLs = []
+    for hmax in (0.032, 0.016, 0.008, 0.004):
+        tr = np.empty((62, 4))
+        na, nr = C.c_int(), C.c_int()
+        st = host_shim.hs_meas_traj_hmax(P(x), C.c_double(1e-2), C.c_double(1e-2), C.c_double(hmax), 2000000, P(tr), C.byref(na), C.byref(nr))
+        assert st == 0 and nr.value == 0 and na.value >= 58.0 / hmax
+        LLs.append(o.llh_from_traj(tr, la[0], 0.1))
+    d = np.abs(np.diff(LLs))
+    assert d[0] / d[1] > 32 and d[1] / d[2] > 32, d
+    assert abs(LLs[-1] - float(g_["LL"][0, 0])) < 1e-9 * abs(LLs[-1])          # and it converges to the golden value
 
 
 def test_default_tolerances_agree_everywhere():
