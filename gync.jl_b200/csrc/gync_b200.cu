@@ -479,7 +479,7 @@ int64_t gync_launch_count(void) { return g_launches.load(); }
 
 // FP64 flops of one step attempt of the method the library was built with: generated-code counts (add+mul; a
 // reciprocal = seed + 3 DFMA = 6, the real power = exp+log ~ 60) + the hand-written stage algebra of the step function.
-//   Rodas5P (gync_rodas5p_step_tm): 8 solves, 7 RHS; per element of the 33-vectors: newest-k terms 7 x 3, stored-k sums
+//   Rodas5P (gync_rodas5p_step_tm): 8 solves, 7 RHS (their real power by series); per element of the 33-vectors: newest-k terms 7 x 3, stored-k sums
 //   (0+1+2+3+4+5+5) x 4, adding the parked correction 7 x 2, absorbing k6 2 x 2, error norm 13.
 //   RODAS4P (gync_rodas4_step_tm): 6 solves, 5 RHS; 33 x [2+2+4+5+6+7+8+9+1+11+1] + 33 x 13.
 double gync_flops_per_step(void) {
@@ -489,7 +489,10 @@ double gync_flops_per_step(void) {
   const double lu = GYNC_OPS_LU_FLOP + rcp * GYNC_OPS_LU_RCP;
 #if GYNC_ROS_ORDER == 5
   const double stage = 33.0 * (7 * 3 + 20 * 4 + 7 * 2 + 4) + 33.0 * 13.0;
-  return rhsw + 7.0 * rhs + lu + 8.0 * GYNC_OPS_SOLVE_FLOP + stage;
+  // the seven stage evaluations take the real power from the step's start by a 10-term series (13 FMAs = 26 flops instead of
+  // the log + exp counted as 60; gync_pow0689), the first evaluation computes it in full and one extra reciprocal
+  const double rhs_stage = rhs - (pw - 26.0) * GYNC_OPS_RHS_POW;
+  return rhsw + rcp + 7.0 * rhs_stage + lu + 8.0 * GYNC_OPS_SOLVE_FLOP + stage;
 #else
   const double stage = 33.0 * (2 + 2 + 4 + 5 + 6 + 7 + 8 + 9 + 1 + 11 + 1) + 33.0 * 13.0;
   return rhsw + 5.0 * rhs + lu + 6.0 * GYNC_OPS_SOLVE_FLOP + stage;

@@ -327,8 +327,9 @@ __device__ __forceinline__ double gync_rodas4_step_tm(GyncWorkTm& W, const doubl
 // stage loop whose body is the proven RHS + triangular solve + two short tensor-memory sums.
 __device__ __forceinline__ double gync_rodas5p_step_tm(GyncWorkTm& W, const double h, const double rtol, const double atol) {
   const double ih = GYNC_RCP(h);
+  double pc[2];                      // the model's real power at the step's start and 1/base (gync_pow0689, gync_solver.cuh)
   GYNC_TICK_INIT
-  gync_rhs_w(W.y, gync_sm_ro<GYNC_TM_NSLOT>(W.q.p), ih * (1.0 / R5_G), W.e, W.A);
+  gync_rhs_w(W.y, GyncPowRec<GyncSmViewRO<GYNC_TM_NSLOT>>{gync_sm_ro<GYNC_TM_NSLOT>(W.q.p), pc}, ih * (1.0 / R5_G), W.e, W.A);
   GYNC_TICK(0)
   gync_lu(W.A);
   GYNC_TICK(1)
@@ -379,7 +380,7 @@ __device__ __forceinline__ double gync_rodas5p_step_tm(GyncWorkTm& W, const doub
     }
     gync_tm_store_vec(W.tm + GYNC_TM_COL_V, W.e);                          // park the correction
     GYNC_TICK(3)
-    gync_rhs(W.yn, gync_sm_ro<GYNC_TM_NSLOT>(W.q.p), W.e);
+    gync_rhs(W.yn, GyncPowUse<GyncSmViewRO<GYNC_TM_NSLOT>>{gync_sm_ro<GYNC_TM_NSLOT>(W.q.p), pc}, W.e);
     GYNC_TICK(4)
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {

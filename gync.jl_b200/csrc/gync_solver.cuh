@@ -28,8 +28,70 @@ __device__ __forceinline__ double gync_rcp_dev(double x) {
   return fma(r, t, r);
 }
 #  define GYNC_RCP(x) gync_rcp_dev(x)
-#  define GYNC_POW0689(x) exp(0.689 * log(x))
+#  define GYNC_POW_FULL(x) exp(0.689 * log(x))
+#else
+#  define GYNC_RCP(x) (1.0 / (x))
+#  define GYNC_POW_FULL(x) pow((x), 0.689)
 #endif
+#ifndef GYNC_HD
+#  ifdef __CUDACC__
+#    define GYNC_HD __host__ __device__ __forceinline__
+#  else
+#    define GYNC_HD inline
+#  endif
+#endif
+
+// The one real power of the model, r^0.689 (r = LH-receptor complex over its threshold, gyncycle.jl:144-164), costs 133
+// of the 1 295 instructions of a stage — a double-precision log and exp — and a ~60-deep dependency chain, eight times per
+// step.  Inside ONE step the stage points differ from the step's start by a few percent at most, so the seven stage
+// evaluations take it from the value computed at the start:  r^a = r0^a (1 + d)^a,  d = r/r0 - 1,  with the binomial series
+// to d^10 (|d| <= 1/16: truncation < 3e-16 relative); outside that range — rare — the full evaluation.  The context
+// (r0^a, 1/r0) rides on the parameter view: gync_rhs_w is called with a recording view, the stage evaluations with a
+// using view, everything else (initial step, unit tests of the generated code) with a plain one.
+template <class QT>
+GYNC_HD static double gync_pow0689(const QT&, const double x) { return GYNC_POW_FULL(x); }
+template <class QV>
+struct GyncPowRec {
+  QV v;
+  double* pc;
+  GYNC_HD auto operator[](int i) const -> decltype(v[i]) { return v[i]; }
+};
+template <class QV>
+struct GyncPowUse {
+  QV v;
+  const double* pc;
+  GYNC_HD auto operator[](int i) const -> decltype(v[i]) { return v[i]; }
+};
+template <class QV>
+GYNC_HD static double gync_pow0689(const GyncPowRec<QV>& q, const double x) {
+  const double p = GYNC_POW_FULL(x);
+  q.pc[0] = p;
+  q.pc[1] = GYNC_RCP(x);
+  return p;
+}
+#define GYNC_POW_A 0.689
+#define GYNC_PC1  (GYNC_POW_A)
+#define GYNC_PC2  (GYNC_PC1 * (GYNC_POW_A - 1.0) / 2.0)
+#define GYNC_PC3  (GYNC_PC2 * (GYNC_POW_A - 2.0) / 3.0)
+#define GYNC_PC4  (GYNC_PC3 * (GYNC_POW_A - 3.0) / 4.0)
+#define GYNC_PC5  (GYNC_PC4 * (GYNC_POW_A - 4.0) / 5.0)
+#define GYNC_PC6  (GYNC_PC5 * (GYNC_POW_A - 5.0) / 6.0)
+#define GYNC_PC7  (GYNC_PC6 * (GYNC_POW_A - 6.0) / 7.0)
+#define GYNC_PC8  (GYNC_PC7 * (GYNC_POW_A - 7.0) / 8.0)
+#define GYNC_PC9  (GYNC_PC8 * (GYNC_POW_A - 8.0) / 9.0)
+#define GYNC_PC10 (GYNC_PC9 * (GYNC_POW_A - 9.0) / 10.0)
+template <class QV>
+GYNC_HD static double gync_pow0689(const GyncPowUse<QV>& q, const double x) {
+  const double d = fma(x, q.pc[1], -1.0);
+  if (fabs(d) <= 0.0625) {
+    double s = GYNC_PC10;
+    s = fma(s, d, GYNC_PC9); s = fma(s, d, GYNC_PC8); s = fma(s, d, GYNC_PC7); s = fma(s, d, GYNC_PC6); s = fma(s, d, GYNC_PC5);
+    s = fma(s, d, GYNC_PC4); s = fma(s, d, GYNC_PC3); s = fma(s, d, GYNC_PC2); s = fma(s, d, GYNC_PC1);
+    return fma(q.pc[0] * d, s, q.pc[0]);
+  }
+  return GYNC_POW_FULL(x);       // also the NaN / negative-base cases: the step is then rejected as non-finite
+}
+#define GYNC_POW0689(x) gync_pow0689(q, (x))
 #include "gen/gync_model_gen.h"
 
 #define GYNC_NX 116        /* sample width: 82 parameters | 33 initial values | period (model.jl:82-84) */
@@ -298,7 +360,11 @@ GYNC_TABLE double R5_OC[7] = {R5_C21, R5_C32, R5_C43, R5_C54, R5_C65, R5_C76 - R
 template <class WK>
 GYNC_HD static double gync_rodas5p_step(WK& W, const double h, const double rtol, const double atol) {
   const double ih = GYNC_RCP(h);
-  gync_rhs_w(W.y, gync_ro(W.q), ih * (1.0 / R5_G), W.e, W.A);
+  double pc[2];                      // the real power at the step's start and 1/base (gync_pow0689)
+  {
+    auto qv = gync_ro(W.q);
+    gync_rhs_w(W.y, GyncPowRec<decltype(qv)>{qv, pc}, ih * (1.0 / R5_G), W.e, W.A);
+  }
   gync_lu(W.A);
   gync_lusolve(gync_ro(W.A), W.e);
 #pragma unroll 1
@@ -331,7 +397,10 @@ GYNC_HD static double gync_rodas5p_step(WK& W, const double h, const double rtol
     }
 #pragma unroll
     for (int i = 0; i < GYNC_NY; ++i) W.k[5 * GYNC_NY + i] = W.e[i];
-    gync_rhs(W.yn, gync_ro(W.q), W.e);
+    {
+      auto qv = gync_ro(W.q);
+      gync_rhs(W.yn, GyncPowUse<decltype(qv)>{qv, pc}, W.e);
+    }
 #pragma unroll
     for (int i = 0; i < GYNC_NY; ++i) W.e[i] = fma(ih, (double)W.k[5 * GYNC_NY + i], W.e[i]);
     gync_lusolve(gync_ro(W.A), W.e);
