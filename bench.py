@@ -319,8 +319,9 @@ def main():
     assert Xnp.flags.f_contiguous
     step_e2e()
     barrier()
-    # At least 12 blocking calls: the shared hosts of this pool stall a process for 0.2 - 1.5 s now and then (with and
-    # without the clock sampler running: measured), and with 5 calls a burst of stalls can reach the median.
+    # At least 12 blocking calls behind the median.  (Rounds 1-2 saw sporadic 0.2 - 1.5 s stalls of single calls here; traced
+    # with GYNC_TRACE_CALLS=1 they were the wake-up of the library's blocking-sync wait AFTER the device had finished — the
+    # library now polls the stream instead, and the calls are as regular as the kernel.)
     n_e2e = max(args.steps, 12)
     t0 = time.perf_counter()
     e2e_steps = []
@@ -330,9 +331,7 @@ def main():
         e2e_steps.append((time.perf_counter() - t1) * 1e3)
     barrier()
     ms_e2e_mean = max_over_ranks((time.perf_counter() - t0) * 1e3 / n_e2e)
-    # The shared hosts of this pool stall a process for 100-700 ms now and then (seen with and without this library: the
-    # kernel's event time stays within 1 % while the wall time of an occasional step doubles), so the end-to-end figure
-    # is the MEDIAN step; the mean and every step are reported beside it.
+    # the end-to-end figure is the MEDIAN call; the mean, the best and every call are reported beside it
     ms_e2e = max_over_ranks(float(np.median(e2e_steps)))
     clk = clocks.stop() if rank == 0 else None          # sampled over BOTH timed regions (device-resident and end-to-end)
     # the same call from PAGEABLE host memory (what a Julia Array is): the driver stages through its own pinned buffers

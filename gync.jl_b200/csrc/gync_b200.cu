@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <vector>
 #include "gync_kernels.cuh"
@@ -119,17 +120,19 @@ GyncSolverOpts to_opts(const gync_solver_opts* o) {
 
 inline unsigned blocks_for(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
-// Wait for a stream WITHOUT spinning: a blocking-sync event puts the host thread to sleep.  The host-buffer entry points
-// wait for hundreds of milliseconds on the solver kernel; a spinning cudaStreamSynchronize burns a core for that long,
-// which on CPU-quota'd hosts showed up as sporadic 100-700 ms stalls of the calling process.
+// Wait for a stream without spinning AND without the driver's blocking-sync wake-up.  Round 1 replaced the spinning
+// cudaStreamSynchronize (a core burnt for hundreds of milliseconds; on CPU-quota'd hosts that showed up as stalls of the
+// calling process) by a cudaEventBlockingSync event.  Traced in round 2 (GYNC_TRACE_CALLS=1): on the shared hosts of this
+// pool that wake-up itself takes ~10 ms when it is fast and 100 - 350 ms when it is not, AFTER the device has finished —
+// the "sporadic stalls" of the end-to-end figure.  So: poll cudaStreamQuery and sleep in between (20 us at first — short
+// kernels —, then 200 us: about 1 % of a core while a 480 ms batch runs).
 cudaError_t wait_stream(cudaStream_t s) {
-  cudaEvent_t ev;
-  cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming);
-  if (e != cudaSuccess) return e;
-  e = cudaEventRecord(ev, s);
-  if (e == cudaSuccess) e = cudaEventSynchronize(ev);
-  cudaEventDestroy(ev);
-  return e;
+  for (int i = 0;; ++i) {
+    const cudaError_t e = cudaStreamQuery(s);
+    if (e != cudaErrorNotReady) return e;
+    timespec ts = {0, i < 64 ? 20000L : 200000L};
+    nanosleep(&ts, nullptr);
+  }
 }
 
 // opt in to the large dynamic shared-memory carve-out the solver kernels need
@@ -676,16 +679,37 @@ int gync_loglik_batch(const double* X, int64_t N, const double* data, int32_t M,
   int32_t* dNs = nsteps ? (int32_t*)sp.get(6, sizeof(int32_t) * N * 2, g_device) : nullptr;
   if (!dX || !dD || !dS || !dLL || !dSt || (Ymeas && !dY) || (nsteps && !dNs))
     return fail(GYNC_ERR_NOMEM, "gync_loglik_batch: out of device memory");
+  // GYNC_TRACE_CALLS=1: host-side time stamps of this call and device-side event times on stderr (where does a slow call
+  // spend its time: enqueueing, the copies, the kernels, or waking up?)
+  const bool trace = getenv("GYNC_TRACE_CALLS") != nullptr;
+  auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  const double t0 = now();
+  if (trace) { for (auto& e : ev) cudaEventCreate(&e); cudaEventRecord(ev[0], g_stream); }
   CK(cudaMemcpyAsync(dX, X, sizeof(double) * N * GYNC_NX, cudaMemcpyHostToDevice, g_stream));
   CK(cudaMemcpyAsync(dD, data, sizeof(double) * 124 * M, cudaMemcpyHostToDevice, g_stream));
   CK(cudaMemcpyAsync(dS, sigma_rho, sizeof(double) * M, cudaMemcpyHostToDevice, g_stream));
+  const double t1 = now();
+  if (trace) cudaEventRecord(ev[1], g_stream);
   int rc = gync_loglik_batch_dev(dX, N, dD, M, dS, opts, dLL, dY, dSt, dNs, g_stream);
   if (rc) return rc;
+  const double t2 = now();
+  if (trace) cudaEventRecord(ev[2], g_stream);
   CK(cudaMemcpyAsync(LL, dLL, sizeof(double) * N * M, cudaMemcpyDeviceToHost, g_stream));
   if (Ymeas) CK(cudaMemcpyAsync(Ymeas, dY, sizeof(double) * N * GYNC_NT_MEAS * GYNC_NMEAS, cudaMemcpyDeviceToHost, g_stream));
   if (status) CK(cudaMemcpyAsync(status, dSt, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, g_stream));
   if (nsteps) CK(cudaMemcpyAsync(nsteps, dNs, sizeof(int32_t) * N * 2, cudaMemcpyDeviceToHost, g_stream));
+  const double t3 = now();
+  if (trace) cudaEventRecord(ev[3], g_stream);
   CK(wait_stream(g_stream));
+  if (trace) {
+    const double t4 = now();
+    float d01 = 0, d12 = 0, d23 = 0;
+    cudaEventElapsedTime(&d01, ev[0], ev[1]); cudaEventElapsedTime(&d12, ev[1], ev[2]); cudaEventElapsedTime(&d23, ev[2], ev[3]);
+    fprintf(stderr, "[gync trace] loglik_batch N=%lld host ms: h2d-enqueue %.2f launch-enqueue %.2f d2h-enqueue %.2f wait %.2f total %.2f | "
+                    "device ms: h2d %.2f kernels %.2f d2h %.2f\n", (long long)N, t1 - t0, t2 - t1, t3 - t2, t4 - t3, t4 - t0, d01, d12, d23);
+    for (auto& e : ev) cudaEventDestroy(e);
+  }
   return GYNC_OK;
 }
 

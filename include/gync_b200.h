@@ -27,6 +27,7 @@
  *   GYNC_DHZ_TWO_PASS=1    dhz as the reference's two matvecs instead of the one-pass row-fused kernel
  *   GYNC_EM_NO_RESIDENT=1  EM always streams L from HBM (default: shared-memory resident when this GPU's rows fit)
  *   GYNC_SOLVE_SM=1        gync/forwardsol through the older shared-memory solver kernel
+ *   GYNC_TRACE_CALLS=1     gync_loglik_batch prints host time stamps and device event times of the call on stderr
  */
 #ifndef GYNC_B200_H
 #define GYNC_B200_H
