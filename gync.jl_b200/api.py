@@ -521,6 +521,33 @@ class WeightedChain:
         """weightedchain.jl:74."""
         return self.upd * self.weights
 
+    # The likelihood matrix stays in HBM between emiteration!(w) calls (a host loop that calls it once per iteration would
+    # otherwise upload K x M doubles every time): one library handle per WeightedChain, re-created when `likelihoods` is
+    # rebound to another array.  In-place edits of the matrix are not noticed: call forget_device_matrix() after one.
+    _em = None
+    _em_key = None
+
+    def _em_handle(self):
+        L = self.likelihoods
+        key = (L.ctypes.data, L.shape)
+        if self._em is None or self._em_key != key:
+            self.forget_device_matrix()
+            h = C.c_void_p()
+            _L.check(_L.load().gync_em_create(_L.dptr(L), L.shape[0], L.shape[1], C.byref(h)))
+            self._em, self._em_key = h, key
+        return self._em
+
+    def forget_device_matrix(self):
+        if self._em is not None:
+            try:
+                _L.load().gync_em_destroy(self._em)
+            except Exception:
+                pass
+        self._em, self._em_key = None, None
+
+    def __del__(self):
+        self.forget_device_matrix()
+
     def sample(self, n=1, seed=0):
         """weightedchain.jl:18-26 — weighted resampling by inverse CDF."""
         cum = np.cumsum(self.weights)
@@ -575,7 +602,9 @@ def emiteration_bang(w, L=None, niter=1):
     """emiteration!(w,L) (em.jl:27-41) / emiteration!(c::WeightedChain) (em.jl:7): in place."""
     lib = _L.load()
     if isinstance(w, WeightedChain):
-        emiteration_bang(w.weights, w.likelihoods, niter)
+        if not (w.weights.dtype == np.float64 and w.weights.flags.c_contiguous):
+            w.weights = np.ascontiguousarray(w.weights, dtype=np.float64)
+        _L.check(lib.gync_em_iterate_handle(w._em_handle(), _L.dptr(w.weights), niter, None))
         return w
     if not (isinstance(w, np.ndarray) and w.dtype == np.float64 and w.flags.c_contiguous):
         raise TypeError("w must be a contiguous float64 vector (it is updated in place)")

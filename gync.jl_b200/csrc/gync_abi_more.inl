@@ -559,6 +559,72 @@ int gync_wc_normalize(const double* LL, const double* logprior, const int64_t* c
 }
 
 // ------------------------------------------------------------------------------------------
+// emiteration!(w, L) called ONCE PER ITERATION from a host loop — the way the reference's scripts drive it
+// (`for i in 1:n emiteration!(w) end`, em.jl:7) — would upload the K x M matrix on every call: 32 MB at the cfg-3 shape,
+// milliseconds over PCIe for microseconds of device work.  A handle keeps L (and a staging vector for w) in HBM: per call
+// only the K weights travel.  A WeightedChain owns one handle for its likelihood matrix (julia/GynCB200.jl, api.py).
+struct gync_em_handle {
+  int device = -1;
+  int64_t K = 0;
+  int32_t M = 0;
+  double *dL = nullptr, *dw = nullptr, *dH = nullptr;
+  int64_t hist_cap = 0;
+};
+
+int gync_em_create(const double* L, int64_t K, int32_t M, gync_em_handle** out) {
+  if (!out || K < 1 || M < 1 || !L) return fail(GYNC_ERR_ARG, "gync_em_create: bad arguments");
+  if (int rc = ensure_init()) return rc;
+  gync_em_handle* h = new gync_em_handle();
+  h->device = g_device; h->K = K; h->M = M;
+  auto body = [&]() -> int {
+    CK(cudaMalloc((void**)&h->dL, sizeof(double) * K * M));
+    CK(cudaMalloc((void**)&h->dw, sizeof(double) * K));
+    CK(cudaMemcpyAsync(h->dL, L, sizeof(double) * K * M, cudaMemcpyHostToDevice, g_stream));
+    CK(wait_stream(g_stream));
+    return GYNC_OK;
+  };
+  if (int rc = body()) {
+    const std::string why = g_err;
+    gync_em_destroy(h);
+    g_err = why;
+    return rc;
+  }
+  *out = h;
+  return GYNC_OK;
+}
+
+// w: K host doubles, updated in place `niter` times; history (nullable): K x niter, column i = weights after iteration i+1
+int gync_em_iterate_handle(gync_em_handle* h, double* w, int32_t niter, double* history) {
+  if (!h || !w || niter < 0) return fail(GYNC_ERR_ARG, "gync_em_iterate_handle: bad arguments");
+  if (niter == 0) return GYNC_OK;
+  if (h->device != g_device) return fail(GYNC_ERR_ARG, "gync_em_iterate_handle: the handle belongs to another device");
+  if (history && h->hist_cap < (int64_t)niter) {
+    if (h->dH) cudaFree(h->dH);
+    h->dH = nullptr; h->hist_cap = 0;
+    CK(cudaMalloc((void**)&h->dH, sizeof(double) * h->K * niter));
+    h->hist_cap = niter;
+  }
+  CK(cudaMemcpyAsync(h->dw, w, sizeof(double) * h->K, cudaMemcpyHostToDevice, g_stream));
+  if (int rc = gync_em_iterate_dev(h->dw, h->dL, h->K, h->M, niter, history ? h->dH : nullptr, g_stream)) return rc;
+  CK(cudaMemcpyAsync(w, h->dw, sizeof(double) * h->K, cudaMemcpyDeviceToHost, g_stream));
+  if (history) CK(cudaMemcpyAsync(history, h->dH, sizeof(double) * h->K * niter, cudaMemcpyDeviceToHost, g_stream));
+  CK(wait_stream(g_stream));
+  return GYNC_OK;
+}
+
+void gync_em_destroy(gync_em_handle* h) {
+  if (!h) return;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  if (h->device >= 0) cudaSetDevice(h->device);
+  if (h->dL) cudaFree(h->dL);
+  if (h->dw) cudaFree(h->dw);
+  if (h->dH) cudaFree(h->dH);
+  cudaSetDevice(cur);
+  delete h;
+}
+
+// ------------------------------------------------------------------------------------------
 // Fused multi-GPU EM: mailboxes in cudaMalloc'd memory exported with cudaIpc, so that each rank's
 // kernel can store its partial denominators directly into every peer's HBM over NVLink.
 struct gync_em_comm {

@@ -182,6 +182,13 @@ int gync_em_iterate(double* w, const double* L, int64_t K, int32_t M, int32_t ni
 int gync_em_iterate_dev(double* dw, const double* dL, int64_t K, int32_t M, int32_t niter,
                         double* d_history, void* stream);
 int gync_em_iterate_multi(double* w, const double* L, int64_t K, int32_t M, int32_t niter);   /* needs gync_init_multi */
+/* emiteration!(w) driven one iteration per call from a host loop (em.jl:7): keep L in HBM between the calls.  The handle
+ * copies L (K x M, column-major) to the current device once; every gync_em_iterate_handle then moves only the K weights.
+ * A WeightedChain owns one handle for its likelihood matrix. */
+typedef struct gync_em_handle gync_em_handle;
+int  gync_em_create(const double* L, int64_t K, int32_t M, gync_em_handle** out);
+int  gync_em_iterate_handle(gync_em_handle* h, double* w, int32_t niter, double* history);
+void gync_em_destroy(gync_em_handle* h);
 /* Sharded form (one process per GPU): one EM step on the local rows given the GLOBAL
  * denominators d_norms_in (M); writes this shard's partial denominators of the NEXT iteration
  * to d_norms_out (M) for the caller's allreduce.  em_norms_dev computes the first partials. */

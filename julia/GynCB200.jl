@@ -145,6 +145,23 @@ function emiteration!(w::DenseVector{Float64}, L::DenseMatrix{Float64})
   w
 end
 
+# emiteration!(c::WeightedChain) (em.jl:7), typically called once per iteration from a script loop: the likelihood matrix
+# stays in HBM between the calls (one handle per WeightedChain, freed by its finalizer); only the K weights travel.
+const EM_HANDLES = ObjectIdDict()
+function emhandle(c::WeightedChain)
+  get!(EM_HANDLES, c) do
+    K, M = size(c.likelihoods)
+    h = Ref{Ptr{Void}}(C_NULL)
+    check(ccall((:gync_em_create, LIBGYNC), Cint, (Ptr{Cdouble}, Int64, Cint, Ptr{Ptr{Void}}), c.likelihoods, K, M, h))
+    finalizer(c, x -> (ccall((:gync_em_destroy, LIBGYNC), Void, (Ptr{Void},), EM_HANDLES[x]); delete!(EM_HANDLES, x)))
+    h[]
+  end
+end
+function emiteration!(c::WeightedChain)
+  check(ccall((:gync_em_iterate_handle, LIBGYNC), Cint, (Ptr{Void}, Ptr{Cdouble}, Cint, Ptr{Cdouble}), emhandle(c), c.weights, 1, C_NULL))
+  c
+end
+
 # emiterations(w0,L,niter) (em.jl:5): all iterates in one launch
 function emiterations(w0, L, niter)
   K, M = size(L)

@@ -691,6 +691,33 @@ def test_mcmc_statistics_vs_independent_cpu_metropolis(gpu, gold):
     assert 0.6 < vr < 1.6, vr                                                       # total variance of the final states
 
 
+def test_em_resident_matrix_handle(gpu):
+    """emiteration!(c::WeightedChain) driven one iteration per call (em.jl:7): the likelihood matrix is uploaded once and stays
+    in HBM (gync_em_create / gync_em_iterate_handle); the iterates equal the oracle's and the one-shot host-array call."""
+    import gync_oracle as o
+    rng = np.random.default_rng(4)
+    K, M = 20_011, 40
+    Lm = rng.random((K, M))
+    Lm /= Lm.sum(0, keepdims=True)
+    wc = gpu.WeightedChain(rng.random((K, 116)), Lm, np.full(K, 1.0 / K), np.ones(K))
+    ref = np.full(K, 1.0 / K)
+    l0 = gpu.lib.load().gync_launch_count()
+    for _ in range(7):
+        gpu.emiteration_bang(wc)
+        ref = o.emiteration(ref, Lm)
+    assert relerr(wc.weights, ref) < RTOL_EM and abs(wc.weights.sum() - 1) < 1e-12
+    assert wc._em is not None and gpu.lib.load().gync_launch_count() - l0 == 7
+    w2 = np.full(K, 1.0 / K)
+    gpu.emiteration_bang(w2, Lm, niter=7)
+    assert relerr(w2, wc.weights) < 1e-13
+    h0 = wc._em.value
+    wc.likelihoods = np.asfortranarray(Lm[:, ::-1].copy())          # rebound: the handle follows
+    gpu.emiteration_bang(wc)
+    assert wc._em.value != h0 or wc._em_key[0] == wc.likelihoods.ctypes.data
+    wc.forget_device_matrix()
+    assert wc._em is None
+
+
 def test_wc_normalize_vs_oracle(gpu):
     import gync_oracle as o
     lib, L = gpu.lib.load(), gpu.lib
