@@ -304,6 +304,38 @@ def test_no_cpu_fallback(built):
         g.emiteration(np.ones(4) / 4, np.ones((4, 2)))
 
 
+def test_new_entry_points_validate_arguments_and_fail_without_a_device(built):
+    """The round-2 entry points follow the ABI's error convention: bad arguments -> GYNC_ERR_ARG before any device work (so this
+    runs without a GPU); good arguments without a CUDA device -> GYNC_ERR_CUDA with a message (no CPU fallback)."""
+    import torch
+    import gync_b200 as g
+    L = g.lib
+    lib = L.load()
+    st, lf = np.zeros((2, 116), order="F"), np.full(2, np.nan)
+    D, sig, pat = np.zeros((31, 4, 1), order="F"), np.array([0.1]), np.zeros(2, dtype=np.int32)
+    op = L.opts(1e-6, 1e-8)
+    ids = np.arange(2, dtype=np.uint64)
+    idp = ids.ctypes.data_as(C.POINTER(C.c_uint64))
+    # no prior / no proposal / thin < 1 / patient index out of range
+    prior = L.Prior()
+    bad = [dict(prior=None), dict(prop_sd=0.0), dict(thin=0), dict(pat=np.array([0, 5], dtype=np.int32))]
+    for b in bad:
+        p_ = b.get("pat", pat)
+        rc = lib.gync_mcmc_run_ids(L.dptr(st), L.dptr(lf), 2, None, b.get("prop_sd", 0.1), L.dptr(D), 1, L.dptr(sig),
+                                   p_.ctypes.data_as(L.c_int32_p), None if "prior" in b else C.byref(prior), C.byref(op), 10,
+                                   b.get("thin", 1), 1, 0, idp, None, None, None, None)
+        assert rc == -1, b
+    h = C.c_void_p()
+    assert lib.gync_em_create(None, 10, 2, C.byref(h)) == -1 and lib.gync_em_create(L.dptr(np.ones((4, 2), order="F")), 0, 2, C.byref(h)) == -1
+    assert lib.gync_em_iterate_handle(None, L.dptr(np.ones(4)), 1, None) == -1
+    lib.gync_em_destroy(None)                                    # a no-op
+    if not torch.cuda.is_available():
+        rc = lib.gync_mcmc_run_ids(L.dptr(st), L.dptr(lf), 2, None, 0.1, L.dptr(D), 1, L.dptr(sig), pat.ctypes.data_as(L.c_int32_p),
+                                   C.byref(prior), C.byref(op), 10, 1, 1, 0, idp, None, None, None, None)
+        assert rc == -2 and b"no CUDA device" in lib.gync_last_error()
+        assert lib.gync_em_create(L.dptr(np.ones((4, 2), order="F")), 4, 2, C.byref(h)) == -2
+
+
 def test_product_does_not_import_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "gync.jl_b200")):
         for f in files:
