@@ -466,10 +466,12 @@ def mcmc_leg(g, L, lib, Xh, world, rank, barrier, max_over_ranks, cpu=False):
                          "likelihood_solves_rank0": int(solves.value), "step_attempts_rank0": int(steps.value),
                          "iterations_per_solve_rank0": n_chains * iters / max(1, solves.value),
                          "solves_per_s_rank0": solves.value / dt, "slots_per_round": int(kk.value),
+                         "solves_stopped_early_rank0": int(lib.gync_mcmc_last_early()), "solves_cancelled_rank0": int(lib.gync_mcmc_last_cancelled()),
                          "extrapolated_cfg4_seconds_8gpu": 4096 * 1e4 / (8 * n_chains * iters / dt) if world == 1 else None,
                          "how": "one persistent kernel per GPU: proposals, solves, accept scan and re-proposal on the device, "
-                                "chains out of step with each other (gync_mcmc_persist.cuh); h2d = states + 40 patient "
-                                "tables, d2h = thinned samples"}
+                                "chains out of step with each other; a proposal is integrated only until its residual sum "
+                                "has passed what acceptance allows (exact: the sum only grows) (gync_mcmc_persist.cuh); "
+                                "h2d = states + 40 patient tables, d2h = thinned samples"}
     if cpu and world == 1:
         out["cpu_baseline"] = cpu_mcmc_leg(D)
     return out

@@ -25,7 +25,7 @@ int gync_logprior_batch(const double* X, int64_t N, const gync_prior* prior, dou
 // ---- K3p host side: one persistent launch per device (gync_mcmc_persist.cuh).  Chains shard over the devices of
 // gync_init_multi in contiguous blocks (independent chains, no data-path collective); every device runs
 // its block asynchronously and the host only waits once, at the end.
-struct McmcStats { unsigned long long solves = 0, steps = 0, cancelled = 0, failed = 0, hist[24] = {0}; };
+struct McmcStats { unsigned long long solves = 0, steps = 0, cancelled = 0, early = 0, failed = 0, hist[24] = {0}; };
 static McmcStats g_mcmc_stats;          // last gync_mcmc_run: likelihood solves started / step attempts (all devices)
 static int g_mcmc_K = 0;                // slots per chain round of the last run
 
@@ -199,10 +199,15 @@ static int mcmc_persist_impl(double* state, double* logf, int64_t C, const doubl
             (double)ctl.cyc_fetch / (double)(ctl.trips_active + ctl.trips_idle + ctl.sleeps + 1),
             (double)ctl.cyc_step / (double)(ctl.trips_active + ctl.trips_idle + 1),
             (double)ctl.cyc_complete / (double)(ctl.trips_active + ctl.trips_idle + 1));
+    if (e == cudaSuccess) {
+      fprintf(stderr, "[mcmc profile] proposals by logf + log u - logf' (<0 accept | 0-1 | 1-3 | 3-10 | 10-30 | 30-100 | 100-300 | 300-1e3 | 1e3-1e4 | >1e4 | -Inf):");
+      for (int b = 0; b < 11; ++b) fprintf(stderr, " %llu", ctl.deficit[b]);
+      fprintf(stderr, "\n");
+    }
 #endif
     if (e != cudaSuccess) rc_all = fail(GYNC_ERR_CUDA, std::string("gync_mcmc_run: ") + cudaGetErrorString(e));
     else if (ctl.abort) rc_all = fail(GYNC_ERR_CUDA, "gync_mcmc_run: the persistent kernel's watchdog fired (no progress)");
-    else { g_mcmc_stats.solves += ctl.solves; g_mcmc_stats.steps += ctl.steps; g_mcmc_stats.cancelled += ctl.cancelled;
+    else { g_mcmc_stats.solves += ctl.solves; g_mcmc_stats.steps += ctl.steps; g_mcmc_stats.cancelled += ctl.cancelled; g_mcmc_stats.early += ctl.early;
            g_mcmc_stats.failed += ctl.failed; for (int b = 0; b < 24; ++b) g_mcmc_stats.hist[b] += ctl.hist[b]; }
     J = McmcJob();                // free on the owning device
   }
@@ -425,6 +430,7 @@ void gync_mcmc_last_stats(uint64_t* solves, uint64_t* steps, int32_t* slots_per_
   if (slots_per_round) *slots_per_round = g_mcmc_K;
 }
 uint64_t gync_mcmc_last_cancelled(void) { return g_mcmc_stats.cancelled; }
+uint64_t gync_mcmc_last_early(void) { return g_mcmc_stats.early; }
 // completed solves of the last run by floor(log2(step attempts)) (24 bins), and how many of them failed
 void gync_mcmc_last_histogram(uint64_t* hist24, uint64_t* failed) {
   if (hist24) for (int b = 0; b < 24; ++b) hist24[b] = g_mcmc_stats.hist[b];

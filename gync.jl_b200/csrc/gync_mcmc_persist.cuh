@@ -23,6 +23,13 @@
 //     Advancing is serialised per chain by a combining counter (the lane that finds it busy leaves its result for the
 //     current advancer), never by a lock that spins.
 //
+//   * a proposal is integrated only as far as its fate is open.  The log-likelihood is -1/2 times a sum of squares that
+//     only grows as the measurement times go by, and acceptance needs  logprior' + sum(x') - 1/2 S > logf + log u  with
+//     everything but S known when the item is picked up (u is addressable like every draw): once S has passed
+//     2 (logprior' + sum(x') - logf - log u) the proposal IS rejected, whatever the rest of the trajectory does — the lane
+//     stops there.  The decisions, and therefore the chains, are exactly those of the full solves (most proposals of a
+//     random-walk chain miss acceptance by hundreds of log-units: they stop about half-way).
+//
 // No lane ever waits for another chain, for the slowest solve of a batch, or for the host; a lane is idle only when
 // the queue is empty.  Round 1 ran propose / solve / accept as separate launches per round with a device->host copy
 // and a host synchronisation after each (still in gync_abi_more.inl, GYNC_MCMC_ROUNDS=1, and used by the adaptive
@@ -39,10 +46,13 @@ struct GyncMcmcCtl {                 // one per launch, zero-initialised
   unsigned long long solves;         // likelihood solves started (bookkeeping: cost of the speculation)
   unsigned long long steps;          // Rosenbrock step attempts spent, cancelled solves included
   unsigned long long cancelled;      // solves given up or dropped because their chain had moved on
+  unsigned long long early;          // solves stopped early: their residual sum had already passed what acceptance allows
   unsigned long long failed;         // completed solves with a non-zero status (their proposal scores -Inf)
   unsigned long long hist[24];       // completed solves by floor(log2(step attempts))
   // -DGYNC_MCMC_PROFILE builds only: where the lanes' time goes (summed over lanes)
   unsigned long long trips_active, trips_idle, cyc_fetch, cyc_complete, cyc_step, sleeps;
+  unsigned long long deficit[12];    // completed proposals by how far they miss acceptance: logf + log u - logf' in
+                                     // (<0 = accept, 0-1, 1-3, 3-10, 10-30, 30-100, 100-300, 300-1e3, 1e3-1e4, >1e4, -Inf, unused)
 };
 #ifdef GYNC_MCMC_PROFILE
 #  define GYNC_MP(...) __VA_ARGS__
@@ -239,6 +249,15 @@ __device__ __forceinline__ void gync_mcmc_complete(const GyncMcmcP& P, int64_t i
   __stcg(P.done_tag + item, tag);
   __threadfence();
   atomicAdd(P.ncomp + 2 * c + (int)((tag >> 40) & 1ull), 1);
+  GYNC_MP({
+    const long long it = (long long)(tag & ((1ull << 40) - 1ull)) - 1;
+    double u, u1;
+    if (P.inj_u) u = P.inj_u[it + P.iters * c];
+    else gync_draw_u2(P.seed, gync_mcmc_chain_id(P, c), P.iter_offset + (uint64_t)it, (uint32_t)(GYNC_NX / 2), u, u1);
+    const double d = __ldcg(P.logf + c) + log(u) - lfp;
+    const int b = !(lfp > -INFINITY) ? 10 : d < 0 ? 0 : d < 1 ? 1 : d < 3 ? 2 : d < 10 ? 3 : d < 30 ? 4 : d < 100 ? 5 : d < 300 ? 6 : d < 1e3 ? 7 : d < 1e4 ? 8 : 9;
+    atomicAdd(&P.ctl->deficit[b], 1ull);
+  })
   gync_mcmc_try_advance(P, c);
 }
 // an item was dropped or given up: it only reports that it is no longer in flight
@@ -309,7 +328,7 @@ gync_mcmc_persist_kernel(const GyncMcmcP P) {
   int64_t c = 0, item = 0;
   unsigned long long tag = 0;
   int mygen = 0;
-  double T = 0.0, t = 0.0, tn = 0.0, lpr = 0.0;
+  double T = 0.0, t = 0.0, tn = 0.0, lpr = 0.0, accmax = INFINITY;
   int i0 = 0, i1 = 0, budget = 0, st = GYNC_ST_OK, mpat = 0;
   GyncCtrl ctl;
   gync_ctrl_init(ctl, 1e-3);
@@ -348,6 +367,15 @@ gync_mcmc_persist_kernel(const GyncMcmcP P) {
             gync_mcmc_complete(P, item, tag, -INFINITY);
           } else {
             lpr = lp + sumx;
+            {
+              // the residual sum beyond which this proposal is rejected for certain (a hair above the exact bound, so that the
+              // rounding of exp / log in the rule itself cannot matter); +Inf when the chain sits at -Inf and accepts anything
+              double u, u1;
+              if (P.inj_u) u = P.inj_u[it + P.iters * c];
+              else gync_draw_u2(P.seed, gync_mcmc_chain_id(P, c), P.iter_offset + (uint64_t)it, (uint32_t)(GYNC_NX / 2), u, u1);
+              const double b = 2.0 * (lpr - __ldcg(P.logf + c) - log(u));
+              accmax = (b == b) ? b + 1e-9 * fabs(b) + 1e-9 : INFINITY;
+            }
             gync_load_sample(W, [&](int k) { return x[k]; }, c_refallparms, c_sampledinds, &T);
             sink.data = P.data + (size_t)GYNC_NDAYS * GYNC_NMEAS * mpat;
             sink.iscale = P.iscale + GYNC_NMEAS * mpat;
@@ -438,7 +466,9 @@ gync_mcmc_persist_kernel(const GyncMcmcP P) {
         }
         if (i0 >= GYNC_NDAYS && i1 >= GYNC_NDAYS) finished = true;
       }
-      if (finished || cancelled) {
+      const bool hopeless = sink.acc > accmax;             // already past what acceptance allows: rejected for certain
+      if (hopeless && !finished && !cancelled) atomicAdd(&P.ctl->early, 1ull);
+      if (finished || cancelled || hopeless) {
         atomicAdd(&P.ctl->steps, (unsigned long long)(ctl.nacc + ctl.nrej));
         if (!cancelled) {
           atomicAdd(&P.ctl->hist[min(23, 31 - __clz(max(1, ctl.nacc + ctl.nrej)))], 1ull);
@@ -446,7 +476,7 @@ gync_mcmc_persist_kernel(const GyncMcmcP P) {
         }
         if (cancelled || __ldcg(P.gen + c) != mygen) gync_mcmc_cancelled(P, c, mygen);
         // failed solve -> NaN trajectory -> -Inf (gyncycle.jl:18-19, model.jl:138-141)
-        else gync_mcmc_complete(P, item, tag, (st == GYNC_ST_OK) ? __dadd_rn(lpr, __dmul_rn(-0.5, sink.acc)) : -INFINITY);
+        else gync_mcmc_complete(P, item, tag, (st == GYNC_ST_OK && !hopeless) ? __dadd_rn(lpr, __dmul_rn(-0.5, sink.acc)) : -INFINITY);
         active = false;
 #pragma unroll
         for (int i = 0; i < GYNC_NY; ++i) if (!(W.y[i] * 0.0 == 0.0)) W.y[i] = 1.0;

@@ -47,7 +47,7 @@ EXPORTS = [
     "gync_flops_per_step", "gync_method_order", "gync_em_comm_create", "gync_em_comm_connect", "gync_em_comm_destroy",
     "gync_em_iterate_fused_dev", "gync_em_comm_error", "gync_wc_normalize_dev", "gync_init_multi", "gync_ndev",
     "gync_em_iterate_multi", "gync_mcmc_run_amm", "gync_wc_colstats_dev", "gync_wc_expsum_dev", "gync_wc_rows_dev",
-    "gync_wc_scale_dev", "gync_collapse_duplicates", "gync_mcmc_run_ids", "gync_mcmc_run_amm_ids", "gync_mcmc_last_stats", "gync_mcmc_last_cancelled", "gync_mcmc_last_histogram", "gync_em_create", "gync_em_iterate_handle", "gync_em_destroy",
+    "gync_wc_scale_dev", "gync_collapse_duplicates", "gync_mcmc_run_ids", "gync_mcmc_run_amm_ids", "gync_mcmc_last_stats", "gync_mcmc_last_cancelled", "gync_mcmc_last_early", "gync_mcmc_last_histogram", "gync_em_create", "gync_em_iterate_handle", "gync_em_destroy",
     "gync_likelihoodmat", "gync_likelihoodmat_dev", "gync_phi_batch", "gync_projectsimplex", "gync_ebmodel_create",
     "gync_ebmodel_from_matrices", "gync_ebmodel_destroy", "gync_ebmodel_dims", "gync_ebmodel_matrices",
     "gync_ebmodel_device_ptrs", "gync_ebmodel_logl", "gync_ebmodel_dlogl", "gync_ebmodel_hz", "gync_ebmodel_dhz",
@@ -102,6 +102,7 @@ def load():
     lib.gync_mcmc_last_stats.argtypes = [c_uint64_p, c_uint64_p, c_int32_p]
     lib.gync_mcmc_last_stats.restype = None
     lib.gync_mcmc_last_cancelled.restype = C.c_uint64
+    lib.gync_mcmc_last_early.restype = C.c_uint64
     lib.gync_mcmc_last_histogram.argtypes = [c_uint64_p, c_uint64_p]
     lib.gync_mcmc_last_histogram.restype = None
     lib.gync_em_iterate.argtypes = [c_double_p, c_double_p, C.c_int64, C.c_int32, C.c_int32, c_double_p]

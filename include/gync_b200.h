@@ -145,6 +145,8 @@ int gync_mcmc_run_ids(double* state, double* logf, int64_t C, const double* chol
 void gync_mcmc_last_stats(uint64_t* solves, uint64_t* steps, int32_t* slots_per_round);
 /* solves dropped or given up because their chain had accepted an earlier proposal */
 uint64_t gync_mcmc_last_cancelled(void);
+/* solves stopped early because their residual sum had already passed what acceptance allows (the decision is exact) */
+uint64_t gync_mcmc_last_early(void);
 /* completed solves of the last run by floor(log2(step attempts)) (24 bins), and how many of them failed */
 void gync_mcmc_last_histogram(uint64_t* hist24, uint64_t* failed);
 

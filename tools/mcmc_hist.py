@@ -11,10 +11,10 @@ def chains(n):
         ss.append(g.new_sampling(cf,seed=1000,chain_id=c))
     return ss
 g.sample_chains(chains(64),20)
-for ov in ("1.1", "1.3"):
+for ov in ("1.1",):
     os.environ["GYNC_MCMC_OVERSUB"]=ov; ms=ov
     ss=chains(512); t0=time.time(); g.sample_chains(ss,2000); dt=time.time()-t0
     h=(C.c_uint64*24)(); f=C.c_uint64(); lib.gync_mcmc_last_histogram(h,C.byref(f))
     so,st,k=C.c_uint64(),C.c_uint64(),C.c_int32(); lib.gync_mcmc_last_stats(C.byref(so),C.byref(st),C.byref(k))
-    print("max_steps",ms,"chain-it/s %.0f"%(512*2000/dt),"solves",so.value,"steps",st.value,"cancelled",lib.gync_mcmc_last_cancelled(),"failed",f.value,"acc %.4f"%(np.mean([x.variate.naccept for x in ss])/2000))
+    print("max_steps",ms,"chain-it/s %.0f"%(512*2000/dt),"solves",so.value,"steps",st.value,"cancelled",lib.gync_mcmc_last_cancelled(),"early",lib.gync_mcmc_last_early(),"failed",f.value,"acc %.4f"%(np.mean([x.variate.naccept for x in ss])/2000))
     print("  hist log2(steps):",{b:int(h[b]) for b in range(24) if h[b]})
