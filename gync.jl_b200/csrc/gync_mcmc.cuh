@@ -25,15 +25,24 @@ GYNC_HD static double gync_logprior(const double* x, const GyncPriorDev* __restr
     istd[j] = 1.0 / pr->gmm_stds[j];
     logdet += log(pr->gmm_stds[j]);
   }
+  // 31 quadratic forms of 33 terms each.  Species-outer / component-inner: every component keeps its own summation order
+  // (bit-identical to the component-outer loop), but the 31 chains of dependent FMAs now run side by side — this function
+  // is executed by a single lane while the other 31 of its warp wait (gync_mcmc_persist.cuh).
   double lp[31];
-  double mx = ninf;
-  for (int i = 0; i < 31; ++i) {
-    double s = 0.0;
-    for (int j = 0; j < GYNC_NY; ++j) {
-      const double z = (x[GYNC_NS + j] - pr->gmm_means[i * GYNC_NY + j]) * istd[j];
-      s = fma(z, z, s);
+#pragma unroll
+  for (int i = 0; i < 31; ++i) lp[i] = 0.0;
+  for (int j = 0; j < GYNC_NY; ++j) {
+    const double xj = x[GYNC_NS + j], is = istd[j];
+#pragma unroll
+    for (int i = 0; i < 31; ++i) {
+      const double z = (xj - pr->gmm_means[i * GYNC_NY + j]) * is;
+      lp[i] = fma(z, z, lp[i]);
     }
-    lp[i] = -0.5 * s;
+  }
+  double mx = ninf;
+#pragma unroll
+  for (int i = 0; i < 31; ++i) {
+    lp[i] = -0.5 * lp[i];
     mx = fmax(mx, lp[i]);
   }
   if (!(mx > ninf)) return (mx == mx) ? ninf : mx;   // all components underflow / NaN input

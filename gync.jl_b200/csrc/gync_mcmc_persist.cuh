@@ -128,6 +128,7 @@ __device__ __noinline__ void gync_mcmc_proposal(const GyncMcmcP& P, int64_t c, l
     for (int d = 0; d < GYNC_NX; ++d) z[d] = P.inj_z[it + P.iters * (d + (int64_t)GYNC_NX * c)];
   } else {
     const uint64_t git = P.iter_offset + (uint64_t)it, cid = gync_mcmc_chain_id(P, c);
+#pragma unroll 4                     // independent draws side by side: one lane runs this while its warp waits
     for (int b = 0; b < GYNC_NX / 2; ++b) gync_draw_n2(P.seed, cid, git, (uint32_t)b, z[2 * b], z[2 * b + 1]);
   }
   if (P.chol) {
@@ -359,7 +360,9 @@ gync_mcmc_persist_kernel(const GyncMcmcP P) {
           gync_mcmc_cancelled(P, c, mygen);                   // its chain has moved on: nothing to solve
         } else {
           double sumx = 0.0;
-          for (int d = 0; d < GYNC_NX; ++d) { sumx += x[d]; x[d] = exp(x[d]); }
+          for (int d = 0; d < GYNC_NX; ++d) sumx += x[d];
+#pragma unroll 4
+          for (int d = 0; d < GYNC_NX; ++d) x[d] = exp(x[d]);
           const double lp = gync_logprior(x, P.pr);          // logf(x) = logpost(c, exp(x)) + sum(x)   (model.jl:102)
           mpat = P.patient_of_chain ? P.patient_of_chain[c] : 0;
           if (!(lp > -INFINITY) || P.allnan[mpat]) {
