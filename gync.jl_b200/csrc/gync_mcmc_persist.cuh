@@ -23,6 +23,10 @@
 //     Advancing is serialised per chain by a combining counter (the lane that finds it busy leaves its result for the
 //     current advancer), never by a lock that spins.
 //
+//   * W is not fixed: a chain's share of the ~1.1 proposals in flight per lane is proportional to its REMAINING iterations.
+//     Chains differ in cost per iteration by tens of percent; with equal shares the cheap ones finish early and leave their
+//     lanes idle, this way a chain that falls behind gets more lanes and all finish together.
+//
 //   * a proposal is integrated only as far as its fate is open.  The log-likelihood is -1/2 times a sum of squares that
 //     only grows as the measurement times go by, and acceptance needs  logprior' + sum(x') - 1/2 S > logf + log u  with
 //     everything but S known when the item is picked up (u is addressable like every draw): once S has passed
