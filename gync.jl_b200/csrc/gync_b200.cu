@@ -346,15 +346,19 @@ int em_launch_variant(EmLaunchState& st, const GyncEmPeer& peer, double* dw, con
   *done = false;
   const int64_t rows_per_pass = GYNC_EM_WARPS * 16;
   int nb;
-  int64_t R = 0;
+  int64_t R = 0, RR = 0;
   size_t smem = sizeof(EmSmem<MH>) + 16;
   if (RESIDENT) {
     nb = g_num_sms;
     R = (K + nb - 1) / nb;
-    smem += sizeof(double) * (size_t)M * R;
     int max_optin = 0;
     CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, g_device));
-    if (smem > (size_t)max_optin || R > 3 * rows_per_pass) return GYNC_OK;   // rows do not fit: caller streams instead
+    // rows of a block that shared memory (and the three register-held weights per thread) can hold; the rest streams.
+    // Worth it while at least half of the rows are resident; otherwise the caller streams everything.
+    const int64_t cap = std::min<int64_t>(((int64_t)max_optin - (int64_t)smem) / (int64_t)(sizeof(double) * M), 3 * rows_per_pass);
+    RR = std::min<int64_t>(R, cap);
+    if (RR < 1 || R - RR > RR || (RR < R && getenv("GYNC_EM_NO_HYBRID"))) return GYNC_OK;
+    smem += sizeof(double) * (size_t)M * RR;
   } else {
     nb = (int)std::min<int64_t>(g_num_sms, std::max<int64_t>((K + rows_per_pass - 1) / rows_per_pass, 1));
   }
@@ -366,8 +370,8 @@ int em_launch_variant(EmLaunchState& st, const GyncEmPeer& peer, double* dw, con
   if (per_sm < 1) return RESIDENT ? GYNC_OK : fail(GYNC_ERR_CUDA, "EM kernel does not fit on an SM");
   GyncEmSync sync = {st.sync_words, st.sync_words + 1, st.seq, st.arrive0};
   GyncEmPeer pr = peer;
-  int Ri = (int)R;
-  void* args[] = {&dw, &dL, &K, &M, &niter, &Ri, &st.partials, &st.gnorm, &sync, &pr, &st.err, &d_hist};
+  int Ri = (int)R, RRi = (int)RR;
+  void* args[] = {&dw, &dL, &K, &M, &niter, &Ri, &RRi, &st.partials, &st.gnorm, &sync, &pr, &st.err, &d_hist};
   if (st.busy) CK(cudaStreamWaitEvent(s, st.busy, 0));
   CK(cudaLaunchCooperativeKernel(kern, dim3(nb), dim3(GYNC_EM_THREADS), args, smem, s));
   if (st.busy) CK(cudaEventRecord(st.busy, s));

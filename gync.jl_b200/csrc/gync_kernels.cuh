@@ -986,17 +986,23 @@ __device__ unsigned long long gync_em_phase[8];
 template <int MH, bool FULL, bool RESIDENT, bool MULTI>
 __global__ void __launch_bounds__(GYNC_EM_THREADS, 1)
 gync_em_kernel(double* __restrict__ w, const double* __restrict__ L, int64_t K, int M, int niter, int rows_per_block,
+               int rows_resident /* RESIDENT: rows of each block held in shared memory (<= rows_per_block; the rest streams) */,
                double* __restrict__ partials /* 2 x gridDim.x x 2MH */, double* __restrict__ gnorm /* 2 x 2MH */,
                GyncEmSync sync, GyncEmPeer peer, int* __restrict__ err_flag, double* __restrict__ history) {
   extern __shared__ double em_dyn[];            // RESIDENT: [M][rows_per_block] then EmSmem ; else EmSmem only
   constexpr int MT = 2 * MH;
-  const int R = rows_per_block;
+  // RESIDENT: a block owns rows [row0, row0 + rows_per_block); the first `rows_resident` of them live in shared memory for
+  // the whole launch, the rest (none when everything fits) is streamed from L2 / HBM in every iteration.  The hybrid
+  // exists for the 8-GPU shard of cfg 5 (125 000 rows x 40 = 40 MB per GPU against 148 x ~215 KB = 31 MB of shared
+  // memory): 80 % of the pass then runs at shared-memory speed.
+  const int R = RESIDENT ? rows_resident : rows_per_block;
   double* sL = em_dyn;
   EmSmem<MH>& sm = *reinterpret_cast<EmSmem<MH>*>(em_dyn + (RESIDENT ? (size_t)M * R : 0));
   const int nb = gridDim.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = lane >> 4, rl = lane & 15;
-  const int64_t row0 = (int64_t)blockIdx.x * R;
-  const int nrows = RESIDENT ? (int)max((int64_t)0, min((int64_t)R, K - row0)) : 0;
+  const int64_t row0 = (int64_t)blockIdx.x * rows_per_block;
+  const int nrows_all = RESIDENT ? (int)max((int64_t)0, min((int64_t)rows_per_block, K - row0)) : 0;
+  const int nrows = min(nrows_all, R);
   if (RESIDENT) {
     for (int m = 0; m < M; ++m)
       for (int r = threadIdx.x; r < nrows; r += GYNC_EM_THREADS) sL[(size_t)m * R + r] = __ldg(L + row0 + r + K * (int64_t)m);
@@ -1048,6 +1054,32 @@ gync_em_kernel(double* __restrict__ w, const double* __restrict__ L, int64_t K, 
 #pragma unroll
           for (int j = 0; j < MH; ++j) acc[j] = fma(l[j], wk, acc[j]);
         }
+      }
+      // the rows of this block that did not fit: same arithmetic, operands from global memory
+      for (int rb = R + warp * 16; rb < nrows_all; rb += GYNC_EM_WARPS * 16) {      // warp-uniform bounds (the shuffle needs all lanes)
+        const int r = rb + rl;
+        const bool valid = r < nrows_all;
+        const int64_t k = row0 + (valid ? r : 0);
+        const double* p = L + k + K * (int64_t)(half * MH);
+        double l[MH];
+#pragma unroll
+        for (int j = 0; j < MH; ++j) { l[j] = (valid && (FULL || half * MH + j < M)) ? __ldg(p) : 0.0; p += K; }
+        double wk = valid ? w[k] : 0.0;
+        if (it >= 0) {
+          double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+          for (int j = 0; j + 1 < MH; j += 2) { s0 = fma(l[j], ri[j], s0); s1 = fma(l[j + 1], ri[j + 1], s1); }
+          if (MH & 1) s0 = fma(l[MH - 1], ri[MH - 1], s0);
+          double s = s0 + s1;
+          s += __shfl_xor_sync(0xffffffffu, s, 16);
+          wk = wk * invM * s;
+          if (valid && half == 0) {
+            w[k] = wk;
+            if (history) history[(size_t)it * K + k] = wk;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < MH; ++j) acc[j] = fma(l[j], wk, acc[j]);
       }
       em_block_reduce<MH>(acc, sm, pbuf + (size_t)blockIdx.x * MT, M);
     } else if (it < 0) {

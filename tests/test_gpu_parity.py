@@ -287,6 +287,33 @@ def test_em_edge_and_full_size(gpu):
     assert relerr(gpu.emiteration_bang(w0.copy(), Le), w0 / w0.sum()) < 1e-11
 
 
+def test_em_partly_resident_shard(gpu):
+    """Rows-per-block beyond what shared memory holds (cfg 5's 8-GPU shard: 125 000 x 40 per GPU): the kernel keeps the rows
+    that fit and streams the rest.  Result and trajectory equal the oracle's; with GYNC_EM_NO_HYBRID the all-streaming kernel
+    gives the same weights to rounding."""
+    import ctypes, gync_oracle as o
+    libc = ctypes.CDLL(None)
+    rng = np.random.default_rng(12)
+    for K, M in ((125_003, 40), (118_001, 37), (140_000, 12)):
+        Lm = rng.random((K, M))
+        Lm[rng.integers(0, K, 50)] = 0.0
+        w0 = rng.random(K)
+        w0 /= w0.sum()
+        ref = [w0]
+        for _ in range(4):
+            ref.append(o.emiteration(ref[-1], Lm))
+        traj = gpu.emiterations(w0, Lm, 5)                        # w0 first, like em.jl:5
+        for a, b in zip(traj, ref):
+            assert relerr(np.asarray(a), b) < RTOL_EM
+        w = gpu.emiteration_bang(w0.copy(), Lm, niter=4)
+        libc.setenv(b"GYNC_EM_NO_HYBRID", b"1", 1)
+        try:
+            ws = gpu.emiteration_bang(w0.copy(), Lm, niter=4)
+        finally:
+            libc.unsetenv(b"GYNC_EM_NO_HYBRID")
+        assert relerr(w, ref[-1]) < RTOL_EM and relerr(ws, w) < 1e-12 and abs(w.sum() - 1) < 1e-12
+
+
 def test_em_sharded_step_kernels(gpu):
     """The kernels behind the multi-GPU path (norms / step with external denominators), emulated
     on one device as two shards with the 'allreduce' done on the host."""

@@ -11,7 +11,7 @@ for p in libs:
     h = C.CDLL(os.path.join(ROOT, p)); assert h.gync_init(0) == 0
     h.gync_em_iterate_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     hs.append(h)
-for K in (100_000, 1_000_000):
+for K in [int(k) for k in os.environ.get("KS", "100000,1000000").split(",")]:
     M = 40
     Lm = torch.rand(M, K, dtype=torch.float64, device="cuda"); Lm /= Lm.sum(1, keepdim=True)
     ws = []
