@@ -362,8 +362,9 @@ int em_launch_variant(EmLaunchState& st, const GyncEmPeer& peer, double* dw, con
   } else {
     nb = (int)std::min<int64_t>(g_num_sms, std::max<int64_t>((K + rows_per_pass - 1) / rows_per_pass, 1));
   }
-  const void* kern = (peer.world > 1) ? (const void*)gync_em_kernel<MH, FULL, RESIDENT, true>
-                                      : (const void*)gync_em_kernel<MH, FULL, RESIDENT, false>;
+  const void* kern = !RESIDENT ? ((peer.world > 1) ? (const void*)gync_em_kernel<MH, FULL, 0, true> : (const void*)gync_em_kernel<MH, FULL, 0, false>)
+                     : RR == R ? ((peer.world > 1) ? (const void*)gync_em_kernel<MH, FULL, 1, true> : (const void*)gync_em_kernel<MH, FULL, 1, false>)
+                               : ((peer.world > 1) ? (const void*)gync_em_kernel<MH, FULL, 2, true> : (const void*)gync_em_kernel<MH, FULL, 2, false>);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GYNC_EM_THREADS, smem));

@@ -983,26 +983,27 @@ __device__ unsigned long long gync_em_phase[8];
 // MULTI: the exchange with peer GPUs is compiled in.  A separate instantiation, because the exchange code in the same
 // body cost the single-GPU streaming pass 9 % (60.3 vs 54.9 us per iteration at K = 1e6: two registers over, a worse
 // schedule of the pass's loads) although it never executed there.
-template <int MH, bool FULL, bool RESIDENT, bool MULTI>
+template <int MH, bool FULL, int RES /* 0 streaming, 1 all rows resident, 2 partly resident */, bool MULTI>
 __global__ void __launch_bounds__(GYNC_EM_THREADS, 1)
 gync_em_kernel(double* __restrict__ w, const double* __restrict__ L, int64_t K, int M, int niter, int rows_per_block,
                int rows_resident /* RESIDENT: rows of each block held in shared memory (<= rows_per_block; the rest streams) */,
                double* __restrict__ partials /* 2 x gridDim.x x 2MH */, double* __restrict__ gnorm /* 2 x 2MH */,
                GyncEmSync sync, GyncEmPeer peer, int* __restrict__ err_flag, double* __restrict__ history) {
+  constexpr bool RESIDENT = RES != 0;
   extern __shared__ double em_dyn[];            // RESIDENT: [M][rows_per_block] then EmSmem ; else EmSmem only
   constexpr int MT = 2 * MH;
   // RESIDENT: a block owns rows [row0, row0 + rows_per_block); the first `rows_resident` of them live in shared memory for
   // the whole launch, the rest (none when everything fits) is streamed from L2 / HBM in every iteration.  The hybrid
   // exists for the 8-GPU shard of cfg 5 (125 000 rows x 40 = 40 MB per GPU against 148 x ~215 KB = 31 MB of shared
   // memory): 80 % of the pass then runs at shared-memory speed.
-  const int R = RESIDENT ? rows_resident : rows_per_block;
+  const int R = RES == 2 ? rows_resident : rows_per_block;
   double* sL = em_dyn;
   EmSmem<MH>& sm = *reinterpret_cast<EmSmem<MH>*>(em_dyn + (RESIDENT ? (size_t)M * R : 0));
   const int nb = gridDim.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = lane >> 4, rl = lane & 15;
   const int64_t row0 = (int64_t)blockIdx.x * rows_per_block;
   const int nrows_all = RESIDENT ? (int)max((int64_t)0, min((int64_t)rows_per_block, K - row0)) : 0;
-  const int nrows = min(nrows_all, R);
+  const int nrows = RES == 2 ? min(nrows_all, R) : nrows_all;
   if (RESIDENT) {
     for (int m = 0; m < M; ++m)
       for (int r = threadIdx.x; r < nrows; r += GYNC_EM_THREADS) sL[(size_t)m * R + r] = __ldg(L + row0 + r + K * (int64_t)m);
@@ -1055,7 +1056,9 @@ gync_em_kernel(double* __restrict__ w, const double* __restrict__ L, int64_t K, 
           for (int j = 0; j < MH; ++j) acc[j] = fma(l[j], wk, acc[j]);
         }
       }
-      // the rows of this block that did not fit: same arithmetic, operands from global memory
+      // the rows of this block that did not fit: same arithmetic, operands from global memory.  (Its own instantiation:
+      // compiled into the all-resident kernel, this never-entered loop cost that kernel 4 %, 6.95 vs 6.70 us at K = 1e5.)
+      if constexpr (RES == 2)
       for (int rb = R + warp * 16; rb < nrows_all; rb += GYNC_EM_WARPS * 16) {      // warp-uniform bounds (the shuffle needs all lanes)
         const int r = rb + rl;
         const bool valid = r < nrows_all;
