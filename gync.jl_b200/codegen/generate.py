@@ -159,7 +159,7 @@ def schedule(assigns, outputs, tmp_prefix):
     return list(reversed(keep))
 
 
-Q_LOOKAHEAD = 6     # statements of lookahead for parameter loads (software prefetch distance)
+Q_LOOKAHEAD = int(os.environ.get("GYNC_GEN_Q_LOOKAHEAD", "6"))     # statements of lookahead for parameter loads (software prefetch distance)
 
 
 def emit(stmts, cnt):
@@ -285,7 +285,7 @@ def main():
     lu_lines = []
     rows = {i: sorted([j for (a, j) in full if a == i], key=lambda j: rank[j]) for i in range(NY)}
     cols = {j: sorted([i for (i, b) in full if b == j], key=lambda i: rank[i]) for j in range(NY)}
-    LU_BATCH = 8
+    LU_BATCH = int(os.environ.get("GYNC_GEN_LU_BATCH", "8"))
     lu_chunks = set()
     for k in order:
         right = [j for j in rows[k] if rank[j] > rank[k]]
@@ -325,7 +325,11 @@ def main():
 
     # ---- triangular solves
     c_sol = Counter()
-    SOL_BATCH = 8
+    # factors are loaded SOL_BATCH operations ahead of their use.  ptxas keeps roughly the distance it is given, and the
+    # distance decides how much of the 29-cycle shared-memory latency each of the 133 loads exposes: measured on B200
+    # (evaluations/s, bit-identical results) 8: 207.4 k, 16: 206.1 k, 20: 214.8 k, 24: 218.5 k, 28: 218.6 k, 32: 217.9 k,
+    # 48: 187.0 k, 64: 170.1 k (spills) — profiles/r2_ab_solbatch*.log.  LU_BATCH and Q_LOOKAHEAD measured flat.
+    SOL_BATCH = int(os.environ.get("GYNC_GEN_SOL_BATCH", "24"))
     ops = []      # (position in A, statement using the local name `a<n>`)
     for k in order:   # forward: L has unit diagonal, multipliers stored below the pivot
         for i in [i for i in cols[k] if rank[i] > rank[k]]:
