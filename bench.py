@@ -853,21 +853,29 @@ def em_leg(lib, L, torch, dist, dev, stream, world, rank, barrier, max_over_rank
     barrier()
     fem.iterate(10)
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    fem.iterate(niter)
-    e1.record()
+    # One launch runs all its iterations on the device, so the ranks' launch skew after the barrier (host side, tens to
+    # hundreds of microseconds) is charged to the first iteration: with 100 iterations of ~10 us that is tens of percent of
+    # the figure.  Time launches of 4 x niter iterations, several of them, and report the best (max over ranks each).
+    fem.iterate(niter)                                 # same iteration count as the NCCL path above: the two results are compared
     barrier()
-    msf = max_over_ranks(e0.elapsed_time(e1)) / niter
-    err = fem.error()
     dw = (w2 - w).abs().max()
     dist.all_reduce(dw, op=dist.ReduceOp.MAX)
+    reps = []
+    for _ in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fem.iterate(4 * niter)
+        e1.record()
+        barrier()
+        reps.append(max_over_ranks(e0.elapsed_time(e1)) / (4 * niter))
+    msf = min(reps)
+    err = fem.error()
     fem.close()
     out["cfg5_K1e6_sharded"] = {"K_total": K * world, "K_per_gpu": K, "M": M, "us_per_iter": msf * 1e3, "iters_per_s": 1e3 / msf,
                                 "algorithmic_GBps_per_gpu": by / msf / 1e6, "frac_of_hbm": by / msf / 1e6 / hbm,
                                 "collective": "fused: partial denominators stored into peer mailboxes over NVLink inside "
                                               "the persistent kernel (no NCCL in the loop)",
-                                "peer_wait_timeout": int(err), "max_abs_diff_vs_nccl_path": float(dw.item())}
+                                "peer_wait_timeout": int(err), "us_per_iter_each_launch": [r * 1e3 for r in reps], "max_abs_diff_vs_nccl_path": float(dw.item())}
     out["roofline"] = {"bound": "hbm", "achieved": by / msf / 1e6, "peak": hbm, "unit": "GB/s", "frac": by / msf / 1e6 / hbm,
                        "traffic": None, "kernel": "gync_em_kernel<20,true,*> with peers (compute + peer-memory allreduce)",
                        "peak_source": hbm_src}
