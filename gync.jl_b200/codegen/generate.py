@@ -29,7 +29,7 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from model import NY, Model, Rcp, RFrac, RPow  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-OUT = os.path.join(HERE, "..", "csrc", "gen", "gync_model_gen.h")
+OUT = os.environ.get("GYNC_GEN_OUT") or os.path.join(HERE, "..", "csrc", "gen", "gync_model_gen.h")
 
 
 # ----------------------------------------------------------------------------- printing

@@ -22,6 +22,20 @@ def relerr(a, b):
     return np.max(np.abs(a - b) / (np.abs(b) + 1e-300))
 
 
+def test_generated_header_is_reproducible(tmp_path):
+    """csrc/gen/gync_model_gen.h is the generator's output, byte for byte (nobody edits it by hand; the knobs of
+    codegen/generate.py — load distances of the straight-line code — are at their committed defaults)."""
+    import subprocess, sys
+    pytest.importorskip("sympy")
+    out = tmp_path / "gen.h"
+    env = {k: v for k, v in os.environ.items() if not k.startswith("GYNC_GEN_")}
+    env["GYNC_GEN_OUT"] = str(out)
+    subprocess.run([sys.executable, os.path.join(ROOT, "gync.jl_b200", "codegen", "generate.py")], check=True, env=env,
+                   stdout=subprocess.DEVNULL)
+    committed = open(os.path.join(ROOT, "gync.jl_b200", "csrc", "gen", "gync_model_gen.h")).read()
+    assert out.read_text() == committed
+
+
 def test_generated_rhs_vs_reference_text(host_shim):
     g = np.load(os.path.join(G, "rhs_golden.npz"))
     for y, p, f in zip(g["Y"], g["P"], g["F"]):
