@@ -26,6 +26,8 @@
  *   GYNC_MCMC_MAXSTEPS=n   step budget of the likelihood solves inside gync_mcmc_run* (default: the caller's opts)
  *   GYNC_DHZ_TWO_PASS=1    dhz as the reference's two matvecs instead of the one-pass row-fused kernel
  *   GYNC_EM_NO_RESIDENT=1  EM always streams L from HBM (default: shared-memory resident when this GPU's rows fit)
+ *   GYNC_EM_NO_HYBRID=1    no partly resident shard: when at least half (but not all) of a block's rows fit in shared
+ *                          memory the EM kernel keeps those and streams the rest; with this set it streams everything
  *   GYNC_SOLVE_SM=1        gync/forwardsol through the older shared-memory solver kernel
  *   GYNC_TRACE_CALLS=1     gync_loglik_batch prints host time stamps and device event times of the call on stderr
  */
