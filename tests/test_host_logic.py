@@ -87,6 +87,23 @@ def test_rodas4_solver_core_vs_converged_golden(host_shim):
             assert abs(l - g["LL"][i, m]) <= 1e-8 * abs(g["LL"][i, m]), (i, m, l, g["LL"][i, m])
 
 
+def test_solver_core_at_the_reference_tolerance(host_shim):
+    """A caller may keep GynC.jl's own tolerance (reltol = abstol = 1e-4, gyncycle.jl:8) instead of the library default:
+    the solver core then lands in the accuracy class of the reference-tolerance BDF (oracle, frozen in the goldens) — both
+    are 1e-4 .. 1e-2 relative away from the converged log-likelihood — in ~175 step attempts instead of ~4 100."""
+    g = np.load(os.path.join(G, "solution_golden.npz"))
+    ours, bdf, steps = [], [], []
+    for i in range(8):
+        st, tr, na, nr = host_traj(host_shim, g["X"][i], 1e-4, 1e-4)
+        assert st == 0
+        l = o.llh_from_traj(tr, g["data"][:, :, 0], 0.1)
+        ours.append(abs(l - g["LL"][i, 0]) / abs(g["LL"][i, 0]))
+        bdf.append(abs(g["LL_bdf1e4"][i, 0] - g["LL"][i, 0]) / abs(g["LL"][i, 0]))
+        steps.append(na + nr)
+    assert max(ours) < 1e-2 and max(ours) < 2 * max(bdf), (ours, bdf)
+    assert 100 < np.mean(steps) < 400, steps
+
+
 def test_solver_core_on_the_parity_tail_fixtures(host_shim):
     """CPU build of the device solver at the library default tolerance against the frozen near-set log-likelihoods
     (tests/golden/nearset_llh_golden.npz): a slice of both populations plus the two samples that were above the 1e-8
